@@ -1,0 +1,220 @@
+"""Generate tests/golden/track_a_reference.npz from the LIVE reference.
+
+TEST INFRASTRUCTURE ONLY; run in the build container (needs /root/reference, which does
+not exist on the GPU box):    python oracle/make_golden.py
+
+The reference files are Python 2 scripts that cannot be imported (print statements,
+missing obspy/matplotlib), but the hot-path function bodies are valid Python 3.  This
+script reads ``full_waveform_inversion.py`` as text, slices the top-level ``def`` blocks
+by a line scan, and ``exec``s the ones on the hot path into a namespace
+seeded with numpy / scipy.signal / eigh / random / math.  Nothing is copied into the
+repo: only the numeric inputs and outputs are stored.
+
+Random draws are replayed: the namespace's ``np.random.normal`` / ``np.random.uniform``
+/ ``random.random`` are replaced by objects that pop values from a recorded stream, so
+the same raw draws can be handed to our own transform (oracle + CUDA) for exact-input
+comparison of the deterministic arithmetic.
+"""
+from __future__ import annotations
+
+import math
+import os
+import random as _pyrandom
+import sys
+import types
+
+import numpy as np
+import scipy
+from numpy.linalg import eigh
+from scipy import signal
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import mc_oracle as orc  # noqa: E402
+
+REF = "/root/reference/full_waveform_inversion.py"
+WANTED = {
+    "get_full_MT_array", "get_six_MT_from_full_MT_array", "find_eigenvalues_from_sixMT",
+    "rot_mt_by_theta_phi", "rot_single_force_by_theta_phi", "perform_inversion", "forward_model",
+    "generate_random_MT", "generate_random_DC_MT", "generate_random_single_force_vector",
+    "generate_random_DC_single_force_coupled_tensor", "generate_random_DC_single_force_uncoupled_tensor",
+    "generate_random_DC_crack_coupled_tensor", "generate_random_single_force_crack_uncoupled_tensor",
+    "variance_reduction", "cross_corr_comparison", "cross_corr_comparison_shift_allowed",
+    "pearson_correlation_comparison", "gaussian_comparison", "compare_synth_to_real_waveforms",
+}
+GENERATOR = {
+    "full_mt": "generate_random_MT",
+    "DC": "generate_random_DC_MT",
+    "single_force": "generate_random_single_force_vector",
+    "DC_single_force_couple": "generate_random_DC_single_force_coupled_tensor",
+    "DC_single_force_no_coupling": "generate_random_DC_single_force_uncoupled_tensor",
+    "DC_crack_couple": "generate_random_DC_crack_coupled_tensor",
+    "single_force_crack_no_coupling": "generate_random_single_force_crack_uncoupled_tensor",
+}
+
+
+class _Replay:
+    """Replays a fixed list of draws and records which API consumed each one."""
+
+    def __init__(self):
+        self.stream = []
+        self.pos = 0
+        self.log = []
+
+    def load(self, values):
+        self.stream = list(values)
+        self.pos = 0
+        self.log = []
+
+    def _next(self, kind):
+        v = self.stream[self.pos]
+        self.pos += 1
+        self.log.append(kind)
+        return v
+
+    # np.random API used by the reference
+    def normal(self, loc=0.0, scale=1.0):
+        return loc + scale * self._next("n")
+
+    def uniform(self, low=0.0, high=1.0):
+        # stream stores the value already mapped to [low, high)
+        return self._next("u")
+
+    # stdlib random API used by the reference
+    def random(self):
+        return self._next("r")
+
+
+def load_reference_namespace(replay):
+    with open(REF) as fh:
+        lines = fh.read().split("\n")
+    starts = [i for i, ln in enumerate(lines) if ln.startswith("def ")]
+    starts.append(len(lines))
+    np_proxy = types.SimpleNamespace()
+    for name in dir(np):
+        if not name.startswith("__"):
+            setattr(np_proxy, name, getattr(np, name))
+    np_proxy.random = replay
+    ns = {"np": np_proxy, "signal": signal, "eigh": eigh, "random": replay, "math": math}
+    for a, b in zip(starts[:-1], starts[1:]):
+        name = lines[a][4:].split("(")[0].strip()
+        if name not in WANTED:
+            continue
+        body = "\n".join(lines[a:b])
+        # stop at the "# ---- End of defining" banner if it trails the last def
+        exec(compile(body, "%s:%d" % (REF, a + 1), "exec"), ns)
+    missing = WANTED - set(ns)
+    if missing:
+        raise RuntimeError("reference functions not found: %s" % sorted(missing))
+    return ns
+
+
+def main():
+    replay = _Replay()
+    ref = load_reference_namespace(replay)
+    out = {"numpy_version": np.__version__, "scipy_version": scipy.__version__}
+
+    # ---- deterministic path: forward model, LSQ, 5 metrics x 4 modes -------------------
+    K, C, T, N = 5, 9, 96, 6
+    d, G, m_true = orc.synthetic_inputs(K=K, C=C, T=T, seed=11)
+    rng = np.random.default_rng(12)
+    Ms = rng.standard_normal((N, C))
+    Ms[0] = m_true                       # a good fit
+    Ms[1] = -m_true                      # anti-correlated -> clamps (q8)
+    Ms[2] = m_true * 1.02 + 0.01 * rng.standard_normal(C)
+    out["det_d"], out["det_G"], out["det_Ms"] = d, G, Ms
+    out["det_synth"] = np.stack([ref["forward_model"](G, Ms[i].reshape(C, 1)) for i in range(N)])
+    out["det_lsq"] = ref["perform_inversion"](d, G)
+    for metric in orc.METRICS:
+        for norm in (False, True):
+            for simul in (False, True):
+                key = "det_sim_%s_%d_%d" % (metric, int(norm), int(simul))
+                out[key] = np.array([ref["compare_synth_to_real_waveforms"](
+                    d, out["det_synth"][i], metric, norm, simul) for i in range(N)], dtype=float)
+    # 3-component (single force) and 6-component variants of the forward model
+    for c in (3, 6):
+        d_c, G_c, _ = orc.synthetic_inputs(K=4, C=c, T=64, seed=20 + c)
+        M_c = np.random.default_rng(30 + c).standard_normal((3, c))
+        out["fm%d_G" % c], out["fm%d_Ms" % c] = G_c, M_c
+        out["fm%d_synth" % c] = np.stack([ref["forward_model"](G_c, M_c[i].reshape(c, 1)) for i in range(3)])
+
+    # ---- samplers: replayed draws -> reference tensors ----------------------------------
+    n_s = 64
+    for itype, gen in GENERATOR.items():
+        raw = orc.draw_raw(itype, np.random.default_rng(100 + list(GENERATOR).index(itype)), n_s)
+        # make sure every quadrant / coin-flip branch of the crack generator is visited
+        pat = orc.DRAW_PATTERN[itype]
+        r_cols = [j for j, ch in enumerate(pat) if ch == "r"]
+        if itype in ("DC_crack_couple", "single_force_crack_no_coupling"):
+            raw[:8, r_cols[0]] = [0.1, 0.9, 0.1, 0.9, 0.3, 0.7, 0.5, 0.50001]
+            raw[:8, r_cols[1]] = [0.1, 0.3, 0.6, 0.9, 0.25, 0.5, 0.75, 1.0 - 1e-12]
+        tens = np.zeros((n_s, orc.N_COMPONENTS[itype]))
+        fracs = np.full(n_s, np.nan)
+        for i in range(n_s):
+            replay.load(raw[i])
+            res = ref[gen]()
+            if isinstance(res, tuple):
+                tens[i] = np.asarray(res[0])[:, 0]
+                fracs[i] = res[1]
+            else:
+                tens[i] = np.asarray(res)[:, 0]
+            assert replay.pos == len(raw[i]), (itype, replay.pos)
+            assert "".join(replay.log) == pat, (itype, "".join(replay.log), pat)
+        out["smp_%s_raw" % itype] = raw
+        out["smp_%s_M" % itype] = tens
+        out["smp_%s_frac" % itype] = fracs
+
+    # ---- worker-loop restatement on the reference's own functions (default config) -------
+    # sampler + forward + per-trace VR + likelihood + Bayes normalisation (FWI:713-774, 847-848)
+    K, C, T, N = 21, 9, 128, 40
+    d, G, _ = orc.synthetic_inputs(K=K, C=C, T=T, seed=0)
+    amp = float(np.sqrt(np.sum(ref["perform_inversion"](d, G) ** 2)))
+    itype = "single_force_crack_no_coupling"
+    raw = orc.draw_raw(itype, np.random.default_rng(99), N)
+    MTs = np.zeros((C, N))
+    sim = np.zeros(N)
+    frac = np.zeros(N)
+    for i in range(N):
+        replay.load(raw[i])
+        M, f = ref[GENERATOR[itype]]()
+        M = M * amp
+        synth = ref["forward_model"](G, M)
+        sim[i] = ref["compare_synth_to_real_waveforms"](d, synth, "VR", False, False)
+        MTs[:, i] = M[:, 0]
+        frac[i] = f
+    L = np.exp(-(1.0 - sim) / 2.0)
+    p_model = 1.0 / N
+    MTp = L * p_model / np.sum(p_model * L)
+    out.update(mc_d=d, mc_G=G, mc_amp=amp, mc_raw=raw, mc_MTs=np.vstack((MTs, frac)), mc_sim=sim,
+               mc_L=L, mc_MTp=MTp)
+
+    # ---- two-media mixes (FWI:715-731) -----------------------------------------------------
+    d2, G2, _ = orc.synthetic_inputs(K=6, C=6, T=80, seed=5, n_media=2)
+    M2 = np.random.default_rng(6).standard_normal((4, 6))
+    f1 = np.array([0.0, 0.25, 0.8, 1.0])
+    f3 = np.random.default_rng(7).random((4, 3))
+    labels = ["P", "P", "S", "S", "surface", "S"]
+    sim_single = np.zeros(4)
+    sim_phase = np.zeros(4)
+    for i in range(4):
+        Gm = (1.0 - f1[i]) * G2[:, :, :, 0] + f1[i] * G2[:, :, :, 1]
+        sim_single[i] = ref["compare_synth_to_real_waveforms"](
+            d2, ref["forward_model"](Gm, M2[i].reshape(6, 1)), "VR", False, False)
+        Gp = np.zeros(G2.shape[:3])
+        fd = dict(zip(("P", "S", "surface"), f3[i]))
+        for j, lab in enumerate(labels):
+            Gp[j] = (1.0 - fd[lab]) * G2[j, :, :, 0] + fd[lab] * G2[j, :, :, 1]
+        sim_phase[i] = ref["compare_synth_to_real_waveforms"](
+            d2, ref["forward_model"](Gp, M2[i].reshape(6, 1)), "PCC", True, True)
+    out.update(med_d=d2, med_G=G2, med_M=M2, med_f1=f1, med_f3=f3,
+               med_phase_index=np.array([orc.PHASE_ORDER.index(x) for x in labels]),
+               med_sim_single=sim_single, med_sim_phase=sim_phase)
+
+    dst = os.path.join(os.path.dirname(HERE), "tests", "golden", "track_a_reference.npz")
+    np.savez_compressed(dst, **out)
+    print("wrote", dst, "%.1f KB" % (os.path.getsize(dst) / 1024.0))
+
+
+if __name__ == "__main__":
+    _pyrandom.seed(0)
+    main()
