@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py - the driver's benchmark contract.
+
+Headline (BASELINE.json): stencil Gpt-updates/s per GPU and FWI-gradient shots/s on config[1]
+"2D acoustic synthetic layered model 1000x3000 grid, 8th-order space, 5k time steps, 64 shots, one FWI gradient".
+
+One STEP = one shot's FWI gradient: 5000 forward leapfrog steps (source injection + receiver sampling fused,
+forward field w_n streamed to HBM) + residual + 5000 adjoint steps with the imaging condition fused.  Weak
+scaling: every rank runs its own shots (BASELINE config 3's shot-parallel layout) and the timed region ends with
+the NCCL all-reduce of the gradient.  `value` counts wavefield point-updates (2 * nt * nz * nx per shot).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nt 5000] [--grid 1000x3000]
+
+`--impl reference`: the reference repository has no propagator, so the CPU arm is the self-oracle port
+(oracle/fd_oracle_c.c, OpenMP over all host cores; NumPy fallback) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nt", type=int, default=5000)
+    ap.add_argument("--grid", default="1000x3000")
+    ap.add_argument("--tile", default="")
+    ap.add_argument("--no-track-a", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    from oracle import fd_oracle as fo
+    nz, nx = (int(x) for x in args.grid.lower().split("x"))
+    h = 10.0
+    v = fo.layered_model((nz, nx), 1500.0, 4500.0, 6).astype(np.float32)
+    dt = fo.stable_dt(4500.0, h, 2)
+    nt = args.nt
+    wav = fo.ricker(nt, dt, 10.0).astype(np.float32)
+    n_shots = 64
+    sx = np.linspace(60, nx - 61, n_shots).astype(int)
+    shots = [([(4, int(s))], [(4, x) for x in range(nx)]) for s in sx]
+    return dict(nz=nz, nx=nx, h=h, dt=dt, nt=nt, v=v, wav=wav, shots=shots, nabs=40, alpha=0.3)
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------------------- CPU arm
+def cpu_stencil_rate(w, seconds_target=12.0):
+    """Times the self-oracle on the host: forward + adjoint point-updates per second on the full grid for a bounded
+    number of time steps.  Prefers the OpenMP C port; falls back to the NumPy oracle (1 core)."""
+    from oracle import fd_oracle as fo
+    nz, nx = w["nz"], w["nx"]
+    try:
+        from oracle import fd_oracle_c as foc
+        lib = foc.load()
+    except Exception:
+        lib = None
+    if lib is not None:
+        cores = foc.num_threads()
+        n_steps = 4
+        t = foc.time_forward_adjoint(w["v"], w["h"], w["dt"], w["nabs"], w["alpha"], n_steps)
+        n_steps = max(4, int(seconds_target / max(t / n_steps, 1e-6)))
+        n_steps = min(n_steps, 400)
+        t = foc.time_forward_adjoint(w["v"], w["h"], w["dt"], w["nabs"], w["alpha"], n_steps)
+        rate = 2.0 * n_steps * nz * nx / t
+        return rate, cores, "port", "oracle/fd_oracle_c.c (OpenMP): %d forward-with-save + %d adjoint steps on the full %dx%d grid, %.1f s" % (n_steps, n_steps, nz, nx, t)
+    p = fo.Problem(w["v"].astype(np.float64), w["h"], w["dt"], w["shots"][0][0], w["shots"][0][1][::8], nabs=w["nabs"], alpha=w["alpha"])
+    cur = np.zeros((nz, nx)); old = np.zeros((nz, nx))
+    n_steps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds_target:
+        new, wv = p.step(cur, old, p.src, np.ones(1))
+        old, cur = cur, new
+        n_steps += 1
+    t = time.perf_counter() - t0
+    return n_steps * nz * nx / t, 1, "port", "oracle/fd_oracle.py (NumPy, 1 core): %d forward steps on the full %dx%d grid, %.1f s" % (n_steps, nz, nx, t)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = workload(args)
+    per_shot = 2.0 * w["nt"] * w["nz"] * w["nx"]
+    vals = []
+    for i in range(args.warmup + args.steps):
+        rate, cores, kind, sample = cpu_stencil_rate(w, seconds_target=4.0)
+        if i >= args.warmup:
+            vals.append(rate)
+    rate = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "stencil_gpt_updates_per_s", "value": rate / 1e9, "unit": "Gpt-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_shot / rate * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "shots_per_s": rate / per_shot,
+        "config": {"workload": "2D acoustic layered %dx%d, 8th order, nt=%d, one shot gradient per step (CPU: bounded sample of time steps, extrapolated)" % (w["nz"], w["nx"], w["nt"])},
+        "cpu_baseline": {"value": rate / 1e9, "unit": "Gpt-updates/s", "cores": cores, "kind": kind, "sample": sample,
+                         "note": "the reference repository has no propagator (SURVEY 0); this is the self-oracle port"},
+        "e2e": {"value": rate / 1e9, "unit": "Gpt-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------- Track A extra
+def track_a_numbers(device):
+    """Secondary numbers for the reference-pinned Monte-Carlo path (BASELINE configs 1 and 5)."""
+    import torch
+    from full_waveform_inversion_b200 import full_waveform_inversion as fw
+    from oracle import mc_oracle as orc
+    K, C, T = 21, 9, 512
+    d, G, _ = orc.synthetic_inputs(K=K, C=C, T=T, seed=0)
+    amp = float(np.linalg.norm(orc.perform_inversion(d, G)))
+    prob = fw.SourceInversion(d, G, device=device)
+    out = {"workload": "MC source inversion K=21 C=9 T=512, VR per-trace, type single_force_crack_no_coupling"}
+    flops = (2 * C + 3) * K * T
+    for N in (10_000, 4_000_000):
+        for _ in range(3):
+            prob.sample_eval_dev(6, 1, 0, N, amp, 0, 0)
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for r in range(reps):
+            prob.sample_eval_dev(6, 1 + r, 0, N, amp, 0, 0, reduce=False)
+        e1.record()
+        torch.cuda.synchronize(device)
+        dt = e0.elapsed_time(e1) / reps * 1e-3
+        out["N=%d" % N] = {"samples_per_s": N / dt, "ms": dt * 1e3, "fp32_tflops_direct": N * flops / dt / 1e12}
+    # host-buffer e2e of config 5: 10k caller-supplied source vectors, float64 in / float64 out
+    Ms = np.random.default_rng(0).standard_normal((10_000, C)) * amp
+    prob.similarity(Ms, "VR", False, False)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        prob.similarity(Ms, "VR", False, False)
+    out["cfg5_e2e_likelihood_evals_per_s"] = 5 * 10_000 / (time.perf_counter() - t0)
+    # CPU: vectorised NumPy oracle, 1 core (the "fair CPU" line of BASELINE.md)
+    t0 = time.perf_counter()
+    orc.similarity_batch_fast_vr(d, G, Ms[:2000])
+    out["cpu_numpy_vectorised_samples_per_s_1core"] = 2000 / (time.perf_counter() - t0)
+    prob.close()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from full_waveform_inversion_b200 import acoustic as ac
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = workload(args)
+    nz, nx, nt = w["nz"], w["nx"], w["nt"]
+    tile = tuple(int(x) for x in args.tile.split(",")) if args.tile else None
+    prop = ac.Propagator2D((nz, nx), w["h"], w["dt"], nabs=w["nabs"], alpha=w["alpha"], device=local, tile=tile)
+    v_dev = torch.from_numpy(w["v"]).to(dev)
+    prop.set_model(v_dev)
+    wav_dev = torch.from_numpy(w["wav"]).to(dev)
+
+    # "observed" data: synthetics of a perturbed model for this rank's first shot, reused for each of its shots
+    # (the arithmetic of a gradient does not depend on what the residual is).
+    my_shots = [w["shots"][(rank + i * world) % len(w["shots"])] for i in range(args.warmup + args.steps)]
+    prop.set_model(v_dev * 1.02)
+    prop.set_geometry(*my_shots[0])
+    obs_dev = prop.forward(wav_dev).clone()
+    prop.set_model(v_dev)
+    obs_host = obs_dev.cpu().pin_memory()
+    wav_host = torch.from_numpy(w["wav"]).pin_memory()
+    grad = torch.zeros((nz, nx), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_step(i, host_io):
+        src, rec = my_shots[i]
+        prop.set_geometry(src, rec)
+        if host_io:
+            o = obs_host.to(dev, non_blocking=True)
+            wv = wav_host.to(dev, non_blocking=True)
+            J, _, _ = prop.gradient(wv, o, grad=grad, want_misfit=True)        # D2H read of the misfit
+            return J
+        prop.gradient(wav_dev, obs_dev, grad=grad, want_misfit=False)
+        return None
+
+    # ---- device-resident timing (value) ------------------------------------------------------------------
+    for i in range(args.warmup):
+        one_step(i, False)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = prop.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.warmup, args.warmup + args.steps):
+        one_step(i, False)
+    if world > 1:
+        dist.all_reduce(grad)                       # one FWI gradient = sum over every rank's shots
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = prop.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end through the public API with host buffers (e2e) ------------------------------------------
+    grad.zero_()
+    one_step(0, True)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    J_last = None
+    for i in range(args.warmup, args.warmup + args.steps):
+        J_last = one_step(i, True)
+    if world > 1:
+        dist.all_reduce(grad)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    per_shot = 2.0 * nt * nz * nx
+    total_updates = per_shot * args.steps * world
+    value = total_updates / (ms * 1e-3) / 1e9
+    e2e = total_updates / (ms_e2e * 1e-3) / 1e9
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        avg_launch_s = (ms * 1e-3) / max(1, launches)
+        achieved = 16.0 * nz * nx / avg_launch_s / 1e9
+        line = {
+            "metric": "stencil_gpt_updates_per_s", "value": value, "unit": "Gpt-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "shots_per_s": args.steps * world / (ms * 1e-3),
+            "config": {"workload": "BASELINE config[1]: 2D acoustic layered %dx%d, 8th-order space, %d time steps, one shot's FWI gradient per step (64-shot survey geometry, %d receivers/shot), forward field w_n held in HBM" % (nz, nx, nt, nx),
+                       "grid": [nz, nx], "nt": nt, "shots_per_rank": args.steps, "parallelism": "shot-parallel x%d, NCCL gradient all-reduce" % world,
+                       "l2": "inputs larger than L2: %.1f GB of forward-field snapshots stream through HBM per step; the 12 MB wavefields are L2-resident within a shot by design" % (nt * nz * prop_px(nx) * 4 / 1e9),
+                       "parity": "vs self-oracle oracle/fd_oracle.py - the reference has no propagator (SURVEY 0)"},
+            "gpu_launches": int(launches),
+            "e2e": {"value": e2e, "unit": "Gpt-updates/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(obs_host.numel() * 4 + wav_host.numel() * 4), "d2h_bytes_per_step": 8,
+                    "misfit_last_step": J_last},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "fd2d_step_kernel (forward-save and adjoint-image variants, averaged)",
+                         "algorithmic_bytes_per_launch": 16 * nz * nx,
+                         "avg_launch_us": avg_launch_s * 1e6,
+                         "note": "16 B per point-update (SURVEY 8d) over the mean step-kernel time incl. launch gaps; the snapshot stream adds 4 B/pt of real HBM traffic per step on top"},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            rate, cores, kind, sample = cpu_stencil_rate(w)
+            line["cpu_baseline"] = {"value": rate / 1e9, "unit": "Gpt-updates/s", "cores": cores, "kind": kind, "sample": sample}
+        if not args.no_track_a and world == 1:
+            try:
+                line["track_a"] = track_a_numbers(local)
+            except Exception as exc:  # secondary numbers must never take the headline down
+                line["track_a"] = {"error": repr(exc)}
+        print(json.dumps(line))
+    prop.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def prop_px(nx):
+    return (nx + 31) // 32 * 32
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,624 @@
+// Track B, 2-D: leapfrog acoustic step with fused source injection / receiver sampling, forward-field
+// snapshotting and adjoint imaging, for sm_100a.
+//
+//   w_n     = lap(u_n) + f_n
+//   u_{n+1} = g * (2 u_n - g * u_{n-1} + m * w_n)           (oracle/fd_oracle.py, spec B1-B3)
+//
+// Data layout: every field is [nz][px] fp32, x contiguous, px = nx rounded up to 32 floats so each row
+// starts on a 128-byte line; no ghost cells in memory.  The (BX+8) x (BZ+8) input tile of u_n is staged
+// into shared memory by ONE TMA tiled load per CTA (cp.async.bulk.tensor.2d); the hardware zero-fills
+// the part of the box that falls outside the grid, which is the Dirichlet halo.  Each lane owns four
+// consecutive x points (one float4), reads its x-neighbours as two more float4 from the tile, and keeps
+// the nine z-neighbours in a register window that rotates down the column, so shared memory is read
+// ~4 x 16 B per float4 of output.  u_{n-1} and m are touched once per point straight from global
+// (coalesced float4) and u_{n+1} overwrites u_{n-1} in place: 16 B of algorithmic traffic per update.
+// The forward pass can stream w_n to an HBM snapshot (evict-first stores); the adjoint pass reads it
+// back and accumulates the zero-lag cross-correlation in the same kernel.
+#include "fd_common.cuh"
+#include <vector>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace fwi {
+
+enum { STEP_FWD = 0, STEP_FWD_SAVE = 1, STEP_ADJ = 2 };
+
+struct Step2DArgs {
+    float* oldnew;        // u_{n-1} in, u_{n+1} out (in place)
+    const float* m;
+    const float* gx;
+    const float* gz;
+    float* snap;          // w_n: written (FWD_SAVE) or read (ADJ)
+    float* acc;           // imaging accumulator (ADJ)
+    int nx, nz, px;
+    PointListDev inj;     // sources (forward) / receivers (adjoint)
+    const float* inj_vals;
+    PointListDev rec;     // receivers to sample (forward only; tile_ptr == nullptr otherwise)
+    float* rec_out;
+};
+
+template <int BZ, int NW, int MODE>
+__global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constant__ CUtensorMap tm_cur, Step2DArgs a) {
+    constexpr int BX = 128, SX = BX + 2 * kHalo, SZ = BZ + 2 * kHalo, RPW = BZ / NW;
+    static_assert(BZ % NW == 0, "rows must split evenly over warps");
+    extern __shared__ __align__(128) float tile[];          // [SZ][SX]
+    __shared__ __align__(8) uint64_t bar;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx0 = blockIdx.x * BX, tz0 = blockIdx.y * BZ;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        fence_proxy_async();
+        mbar_expect_tx(&bar, SX * SZ * (uint32_t)sizeof(float));
+        tma_load_2d(tile, &tm_cur, tx0 - kHalo, tz0 - kHalo, &bar);
+    }
+    __syncthreads();        // barrier init visible to every waiter
+
+    const int x = tx0 + 4 * lane;
+    const int zw = tz0 + warp * RPW;
+    const bool col_ok = x < a.px;
+    float4 gx4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (col_ok) gx4 = ld4(a.gx + x);
+
+    mbar_wait(&bar, 0);
+
+    if (col_ok && zw < a.nz) {
+        // register window over z: win[k] holds row (z - 4 + k) of this lane's float4 column
+        float4 win[9];
+        const float* tcol = tile + (warp * RPW) * SX + kHalo + 4 * lane;     // row z-4 of the first output row
+#pragma unroll
+        for (int k = 0; k < 8; ++k) win[k + 1] = ld4(tcol + k * SX);
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const int z = zw + r;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) win[k] = win[k + 1];
+            win[8] = ld4(tcol + (r + 8) * SX);
+            if (z < a.nz) {
+                const float* trow = tile + (warp * RPW + r + kHalo) * SX + 4 * lane;
+                const float4 L = ld4(trow), R = ld4(trow + 8);
+                const float4 C = win[4];
+                const float ax[12] = {L.x, L.y, L.z, L.w, C.x, C.y, C.z, C.w, R.x, R.y, R.z, R.w};
+                float zc[9][4];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { zc[k][0] = win[k].x; zc[k][1] = win[k].y; zc[k][2] = win[k].z; zc[k][3] = win[k].w; }
+                const size_t off = (size_t)z * a.px + x;
+                const float4 o4 = ld4(a.oldnew + off);
+                const float4 m4 = ld4(a.m + off);
+                const float gzv = __ldg(a.gz + z);
+                const float ov[4] = {o4.x, o4.y, o4.z, o4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w};
+                const float gv[4] = {gx4.x * gzv, gx4.y * gzv, gx4.z * gzv, gx4.w * gzv};
+                float wv[4], nv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float c = ax[4 + j];
+                    float lap = (2.0f * kC0) * c;
+                    lap = fmaf(kC1, (ax[3 + j] + ax[5 + j]) + (zc[3][j] + zc[5][j]), lap);
+                    lap = fmaf(kC2, (ax[2 + j] + ax[6 + j]) + (zc[2][j] + zc[6][j]), lap);
+                    lap = fmaf(kC3, (ax[1 + j] + ax[7 + j]) + (zc[1][j] + zc[7][j]), lap);
+                    lap = fmaf(kC4, (ax[0 + j] + ax[8 + j]) + (zc[0][j] + zc[8][j]), lap);
+                    wv[j] = lap;
+                    nv[j] = gv[j] * fmaf(mv[j], lap, fmaf(-gv[j], ov[j], 2.0f * c));
+                }
+                st4(a.oldnew + off, make_float4(nv[0], nv[1], nv[2], nv[3]));
+                if (MODE == STEP_FWD_SAVE) st4_stream(a.snap + off, make_float4(wv[0], wv[1], wv[2], wv[3]));
+                if (MODE == STEP_ADJ) {
+                    const float4 s4 = ld4_stream(a.snap + off);
+                    float4 c4 = ld4(a.acc + off);
+                    c4.x = fmaf(nv[0], s4.x, c4.x); c4.y = fmaf(nv[1], s4.y, c4.y);
+                    c4.z = fmaf(nv[2], s4.z, c4.z); c4.w = fmaf(nv[3], s4.w, c4.w);
+                    st4(a.acc + off, c4);
+                }
+            }
+        }
+    }
+
+    // ---- sparse fix-ups for the points this tile owns: injection, then receiver sampling ----------
+    const int tid = blockIdx.y * gridDim.x + blockIdx.x;
+    const int i0 = a.inj.tile_ptr ? a.inj.tile_ptr[tid] : 0, i1 = a.inj.tile_ptr ? a.inj.tile_ptr[tid + 1] : 0;
+    const int r0 = a.rec.tile_ptr ? a.rec.tile_ptr[tid] : 0, r1 = a.rec.tile_ptr ? a.rec.tile_ptr[tid + 1] : 0;
+    if (i1 > i0 || r1 > r0) {             // uniform per CTA
+        __syncthreads();
+        for (int e = i0 + threadIdx.x; e < i1; e += blockDim.x) {
+            const int off = a.inj.off[e];
+            const int z = off / a.px, xx = off - z * a.px;
+            const float val = a.inj_vals[a.inj.id[e]];
+            const float gm = a.gx[xx] * a.gz[z] * a.m[off];
+            atomicAdd(a.oldnew + off, gm * val);                       // u_{n+1} += g m f
+            if (MODE == STEP_FWD_SAVE) atomicAdd(a.snap + off, val);   // w_n includes f_n
+            if (MODE == STEP_ADJ) atomicAdd(a.acc + off, gm * val * a.snap[off]);
+        }
+        if (r1 > r0) {
+            __syncthreads();
+            for (int e = r0 + threadIdx.x; e < r1; e += blockDim.x)
+                a.rec_out[a.rec.id[e]] = __ldcg(a.oldnew + a.rec.off[e]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ small kernels
+__global__ void fd_model_kernel(const float* __restrict__ v, int nz, int nx, int px, float dt_over_h,
+                                float* __restrict__ m, float* __restrict__ vp) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+    if (x >= px || z >= nz) return;
+    float val = 0.f, vv = 0.f;
+    if (x < nx) { vv = v[(size_t)z * nx + x]; const float c = vv * dt_over_h; val = c * c; }
+    m[(size_t)z * px + x] = val;
+    vp[(size_t)z * px + x] = vv;
+}
+
+__global__ void fd_grad_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ vp, int nz, int nx,
+                                        int px, float* __restrict__ grad) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+    if (x >= nx || z >= nz) return;
+    const size_t o = (size_t)z * px + x;
+    grad[(size_t)z * nx + x] += 2.0f * acc[o] / vp[o];                 // dJ/dv = (2/v) I
+}
+
+__global__ void fd_unpitch_kernel(const float* __restrict__ src, int nz, int nx, int px, float* __restrict__ dst) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+    if (x < nx && z < nz) dst[(size_t)z * nx + x] = src[(size_t)z * px + x];
+}
+
+__global__ void fd_residual_kernel(const float* __restrict__ syn, const float* __restrict__ obs, int64_t n,
+                                   float* __restrict__ res, double* __restrict__ J) {
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float r = syn[i] - obs[i];
+        res[i] = r;
+        s += (double)r * (double)r;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double ws[32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += ws[w];
+        atomicAdd(J, 0.5 * t);
+    }
+}
+
+__global__ void fd_update_kernel(float* __restrict__ v, const float* __restrict__ g, float step, float vmin, float vmax,
+                                 int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = fminf(vmax, fmaxf(vmin, v[i] - step * g[i]));
+}
+
+__global__ void fd_absmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* __restrict__ out) {
+    float mx = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        mx = fmaxf(mx, fabsf(x[i]));
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(mx));     // non-negative floats order like uints
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_tiled_f32(CUtensorMap* out, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        FWI_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available from the driver"); return FWI_ECUDA; }
+        fn = (EncodeTiledFn)p;
+    }
+    cuuint64_t d[5]; cuuint64_t s[5]; cuuint32_t b[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i < rank - 1; ++i) s[i] = strides_bytes[i];
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return FWI_ECUDA; }
+    return FWI_OK;
+}
+
+}  // namespace fwi
+
+using namespace fwi;
+
+// =============================================================================================== host plan
+namespace {
+
+struct PointList {
+    int n = 0;
+    int* d_tile_ptr = nullptr; int* d_off = nullptr; int* d_id = nullptr;
+    void release() {
+        if (d_tile_ptr) cudaFree(d_tile_ptr);
+        if (d_off) cudaFree(d_off);
+        if (d_id) cudaFree(d_id);
+        d_tile_ptr = d_off = d_id = nullptr; n = 0;
+    }
+    PointListDev dev() const { return PointListDev{d_tile_ptr, d_off, d_id}; }
+};
+
+constexpr int kBX = 128;
+
+}  // namespace
+
+struct fwi_fd2d {
+    int device = 0, nz = 0, nx = 0, px = 0, nabs = 0;
+    float h = 0, dt = 0, alpha = 0;
+    int bz = 32, nw = 4;              // tile rows / warps per CTA (tunable)
+    int tiles_x = 0, tiles_z = 0;
+    float *m = nullptr, *vp = nullptr, *gx = nullptr, *gz = nullptr;
+    float* fld[4] = {nullptr, nullptr, nullptr, nullptr};   // forward pair 0/1, adjoint pair 2/3
+    CUtensorMap tmap[4];
+    float* acc = nullptr;
+    float* snap = nullptr; size_t snap_steps = 0;
+    float* ckpt = nullptr; size_t ckpt_slots = 0;
+    float* resid = nullptr; size_t resid_cap = 0;
+    float* syn = nullptr; size_t syn_cap = 0;
+    double* d_J = nullptr;
+    unsigned int* d_absmax = nullptr;
+    PointList src, rec;
+    int nsrc = 0, nrec = 0;
+    size_t mem_limit = 0;             // 0 = automatic (fraction of free memory)
+    int fwd_cur = 0;                  // which of fld[0/1] holds u_n after the last forward
+    bool model_set = false;
+    int64_t launches = 0;
+    size_t plane() const { return (size_t)nz * px; }
+};
+
+static int make_tmaps(fwi_fd2d* p) {
+    for (int i = 0; i < 4; ++i) {
+        const uint64_t dims[2] = {(uint64_t)p->nx, (uint64_t)p->nz};
+        const uint64_t strides[1] = {(uint64_t)p->px * sizeof(float)};
+        const uint32_t box[2] = {(uint32_t)(kBX + 2 * kHalo), (uint32_t)(p->bz + 2 * kHalo)};
+        int rc = encode_tiled_f32(&p->tmap[i], p->fld[i], 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    return FWI_OK;
+}
+
+static int build_point_list(fwi_fd2d* p, PointList& pl, int n, const int* iz, const int* ix, const char* what) {
+    pl.release();
+    const int ntiles = p->tiles_x * p->tiles_z;
+    std::vector<int> tile_ptr(ntiles + 1, 0), off(std::max(n, 1)), id(std::max(n, 1));
+    for (int i = 0; i < n; ++i) {
+        FWI_REQUIRE(iz[i] >= 0 && iz[i] < p->nz && ix[i] >= 0 && ix[i] < p->nx, "%s %d at (z=%d, x=%d) is outside the %d x %d grid", what, i, iz[i], ix[i], p->nz, p->nx);
+        tile_ptr[(iz[i] / p->bz) * p->tiles_x + ix[i] / kBX + 1]++;
+    }
+    for (int t = 0; t < ntiles; ++t) tile_ptr[t + 1] += tile_ptr[t];
+    std::vector<int> fill(tile_ptr.begin(), tile_ptr.end() - 1);
+    for (int i = 0; i < n; ++i) {
+        const int t = (iz[i] / p->bz) * p->tiles_x + ix[i] / kBX;
+        const int e = fill[t]++;
+        off[e] = iz[i] * p->px + ix[i];
+        id[e] = i;
+    }
+    FWI_CUDA(cudaMalloc(&pl.d_tile_ptr, (ntiles + 1) * sizeof(int)));
+    FWI_CUDA(cudaMalloc(&pl.d_off, std::max(n, 1) * sizeof(int)));
+    FWI_CUDA(cudaMalloc(&pl.d_id, std::max(n, 1) * sizeof(int)));
+    FWI_CUDA(cudaMemcpy(pl.d_tile_ptr, tile_ptr.data(), (ntiles + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    FWI_CUDA(cudaMemcpy(pl.d_off, off.data(), std::max(n, 1) * sizeof(int), cudaMemcpyHostToDevice));
+    FWI_CUDA(cudaMemcpy(pl.d_id, id.data(), std::max(n, 1) * sizeof(int), cudaMemcpyHostToDevice));
+    pl.n = n;
+    return FWI_OK;
+}
+
+template <int BZ, int NW>
+static int launch_step_cfg(fwi_fd2d* p, int mode, int cur, float* oldnew, const PointList* inj, const float* inj_vals,
+                           const PointList* rec, float* rec_out, float* snap, cudaStream_t st) {
+    Step2DArgs a{};
+    a.oldnew = oldnew; a.m = p->m; a.gx = p->gx; a.gz = p->gz; a.snap = snap; a.acc = p->acc;
+    a.nx = p->nx; a.nz = p->nz; a.px = p->px;
+    a.inj = (inj && inj->n) ? inj->dev() : PointListDev{nullptr, nullptr, nullptr};
+    a.inj_vals = inj_vals;
+    a.rec = (rec && rec->n) ? rec->dev() : PointListDev{nullptr, nullptr, nullptr};
+    a.rec_out = rec_out;
+    const dim3 grid(p->tiles_x, p->tiles_z), block(NW * 32);
+    const size_t smem = (size_t)(kBX + 2 * kHalo) * (BZ + 2 * kHalo) * sizeof(float);
+    if (mode == STEP_FWD) fd2d_step_kernel<BZ, NW, STEP_FWD><<<grid, block, smem, st>>>(p->tmap[cur], a);
+    else if (mode == STEP_FWD_SAVE) fd2d_step_kernel<BZ, NW, STEP_FWD_SAVE><<<grid, block, smem, st>>>(p->tmap[cur], a);
+    else fd2d_step_kernel<BZ, NW, STEP_ADJ><<<grid, block, smem, st>>>(p->tmap[cur], a);
+    p->launches++;
+    return FWI_OK;
+}
+
+static int launch_step(fwi_fd2d* p, int mode, int cur, float* oldnew, const PointList* inj, const float* inj_vals,
+                       const PointList* rec, float* rec_out, float* snap, cudaStream_t st) {
+#define CFG(BZV, NWV) if (p->bz == BZV && p->nw == NWV) return launch_step_cfg<BZV, NWV>(p, mode, cur, oldnew, inj, inj_vals, rec, rec_out, snap, st)
+    CFG(32, 4); CFG(32, 8); CFG(16, 4); CFG(64, 8); CFG(16, 2); CFG(64, 4);
+#undef CFG
+    set_error("fd2d: unsupported tile configuration bz=%d nw=%d", p->bz, p->nw);
+    return FWI_EINVAL;
+}
+
+static int ensure_bytes(float** ptr, size_t* cap, size_t need_floats) {
+    if (*cap >= need_floats) return FWI_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *cap = 0;
+    FWI_CUDA(cudaMalloc(ptr, need_floats * sizeof(float)));
+    *cap = need_floats;
+    return FWI_OK;
+}
+
+// forward time loop over steps [n0, n1); `cur` indexes fld[] holding u_n on entry, returns the new cur
+static int run_forward(fwi_fd2d* p, const float* wavelet, int n0, int n1, float* traces, bool save, size_t snap_base,
+                       int& cur, cudaStream_t st) {
+    for (int n = n0; n < n1; ++n) {
+        float* snap = save ? p->snap + (size_t)(n - snap_base) * p->plane() : nullptr;
+        int rc = launch_step(p, save ? STEP_FWD_SAVE : STEP_FWD, cur, p->fld[cur ^ 1], &p->src, wavelet + (size_t)n * p->nsrc,
+                             traces ? &p->rec : nullptr, traces ? traces + (size_t)n * p->nrec : nullptr, snap, st);
+        if (rc) return rc;
+        cur ^= 1;
+    }
+    FWI_CUDA(cudaGetLastError());
+    return FWI_OK;
+}
+
+// adjoint steps for trace rows n1-1 down to n0 (fields fld[2/3]); `acur` indexes the pair
+static int run_adjoint(fwi_fd2d* p, const float* resid, int n0, int n1, size_t snap_base, int& acur, cudaStream_t st) {
+    for (int n = n1 - 1; n >= n0; --n) {
+        int rc = launch_step(p, STEP_ADJ, 2 + acur, p->fld[2 + (acur ^ 1)], &p->rec, resid + (size_t)n * p->nrec, nullptr, nullptr,
+                             p->snap + (size_t)(n - snap_base) * p->plane(), st);
+        if (rc) return rc;
+        acur ^= 1;
+    }
+    FWI_CUDA(cudaGetLastError());
+    return FWI_OK;
+}
+
+extern "C" {
+
+int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, float alpha, fwi_fd2d** out) {
+    FWI_REQUIRE(out != nullptr, "fwi_fd2d_create: out is NULL");
+    FWI_REQUIRE(nz >= 1 && nx >= 1, "fwi_fd2d_create: grid must be at least 1 x 1 (got %d x %d)", nz, nx);
+    FWI_REQUIRE(h > 0.f && dt > 0.f, "fwi_fd2d_create: h and dt must be positive");
+    FWI_REQUIRE(nabs >= 0 && alpha >= 0.f, "fwi_fd2d_create: nabs and alpha must be non-negative");
+    int ndev = 0;
+    FWI_CUDA(cudaGetDeviceCount(&ndev));
+    FWI_REQUIRE(device >= 0 && device < ndev, "fwi_fd2d_create: device %d out of range (%d visible)", device, ndev);
+    DeviceGuard g(device);
+    auto* p = new fwi_fd2d();
+    p->device = device; p->nz = nz; p->nx = nx; p->h = h; p->dt = dt; p->nabs = nabs; p->alpha = alpha;
+    p->px = (nx + 31) & ~31;
+    p->tiles_x = (nx + kBX - 1) / kBX;
+    p->tiles_z = (nz + p->bz - 1) / p->bz;
+    const size_t pl = p->plane();
+    FWI_CUDA(cudaMalloc(&p->m, pl * sizeof(float)));
+    FWI_CUDA(cudaMalloc(&p->vp, pl * sizeof(float)));
+    FWI_CUDA(cudaMalloc(&p->acc, pl * sizeof(float)));
+    for (int i = 0; i < 4; ++i) { FWI_CUDA(cudaMalloc(&p->fld[i], pl * sizeof(float))); FWI_CUDA(cudaMemset(p->fld[i], 0, pl * sizeof(float))); }
+    FWI_CUDA(cudaMalloc(&p->gx, p->px * sizeof(float)));
+    FWI_CUDA(cudaMalloc(&p->gz, nz * sizeof(float)));
+    FWI_CUDA(cudaMalloc(&p->d_J, sizeof(double)));
+    FWI_CUDA(cudaMalloc(&p->d_absmax, sizeof(unsigned int)));
+    // sponge profiles (oracle/fd_oracle.py sponge_profile), float64 on the host then rounded once
+    auto profile = [&](int n, int padded) {
+        std::vector<float> prof(padded, 1.0f);
+        for (int i = 0; i < std::min(nabs, n); ++i) {
+            const double t = (double)alpha * (nabs - i) / nabs;
+            const float val = (float)std::exp(-t * t);
+            prof[i] = std::min(prof[i], val);
+            prof[n - 1 - i] = std::min(prof[n - 1 - i], val);
+        }
+        return prof;
+    };
+    std::vector<float> gxh = profile(nx, p->px), gzh = profile(nz, nz);
+    FWI_CUDA(cudaMemcpy(p->gx, gxh.data(), p->px * sizeof(float), cudaMemcpyHostToDevice));
+    FWI_CUDA(cudaMemcpy(p->gz, gzh.data(), nz * sizeof(float), cudaMemcpyHostToDevice));
+    int rc = make_tmaps(p);
+    if (rc) return rc;
+    *out = p;
+    return FWI_OK;
+}
+
+int fwi_fd2d_destroy(fwi_fd2d* p) {
+    if (!p) return FWI_OK;
+    DeviceGuard g(p->device);
+    cudaFree(p->m); cudaFree(p->vp); cudaFree(p->acc); cudaFree(p->gx); cudaFree(p->gz); cudaFree(p->d_J); cudaFree(p->d_absmax);
+    for (int i = 0; i < 4; ++i) cudaFree(p->fld[i]);
+    if (p->snap) cudaFree(p->snap);
+    if (p->ckpt) cudaFree(p->ckpt);
+    if (p->resid) cudaFree(p->resid);
+    if (p->syn) cudaFree(p->syn);
+    p->src.release(); p->rec.release();
+    delete p;
+    return FWI_OK;
+}
+
+int fwi_fd2d_set_tile(fwi_fd2d* p, int bz, int nw) {
+    FWI_REQUIRE(p, "fwi_fd2d_set_tile: NULL plan");
+    const bool ok = (bz == 32 && (nw == 4 || nw == 8)) || (bz == 16 && (nw == 4 || nw == 2)) || (bz == 64 && (nw == 8 || nw == 4));
+    FWI_REQUIRE(ok, "fwi_fd2d_set_tile: unsupported (bz=%d, nw=%d)", bz, nw);
+    DeviceGuard g(p->device);
+    p->bz = bz; p->nw = nw;
+    p->tiles_z = (p->nz + bz - 1) / bz;
+    p->src.release(); p->rec.release(); p->nsrc = p->nrec = 0;      // tile binning changed
+    return make_tmaps(p);
+}
+
+int fwi_fd2d_set_memory_limit(fwi_fd2d* p, uint64_t bytes) {
+    FWI_REQUIRE(p, "fwi_fd2d_set_memory_limit: NULL plan");
+    p->mem_limit = (size_t)bytes;
+    return FWI_OK;
+}
+
+int fwi_fd2d_set_model(fwi_fd2d* p, const float* v_dev, void* stream) {
+    FWI_REQUIRE(p && v_dev, "fwi_fd2d_set_model: NULL argument");
+    DeviceGuard g(p->device);
+    dim3 grid((p->px + 127) / 128, p->nz);
+    fd_model_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(v_dev, p->nz, p->nx, p->px, p->dt / p->h, p->m, p->vp);
+    FWI_CUDA(cudaGetLastError());
+    p->model_set = true;
+    return FWI_OK;
+}
+
+int fwi_fd2d_set_geometry(fwi_fd2d* p, int nsrc, const int* src_z, const int* src_x, int nrec, const int* rec_z,
+                          const int* rec_x) {
+    FWI_REQUIRE(p, "fwi_fd2d_set_geometry: NULL plan");
+    FWI_REQUIRE(nsrc >= 0 && nrec >= 0 && (nsrc == 0 || (src_z && src_x)) && (nrec == 0 || (rec_z && rec_x)), "fwi_fd2d_set_geometry: bad arguments");
+    DeviceGuard g(p->device);
+    int rc = build_point_list(p, p->src, nsrc, src_z, src_x, "source");
+    if (rc) return rc;
+    rc = build_point_list(p, p->rec, nrec, rec_z, rec_x, "receiver");
+    if (rc) return rc;
+    p->nsrc = nsrc; p->nrec = nrec;
+    return FWI_OK;
+}
+
+int fwi_fd2d_forward(fwi_fd2d* p, const float* wavelet_dev, int nt, float* traces_dev, void* stream) {
+    FWI_REQUIRE(p && p->model_set, "fwi_fd2d_forward: set the model first");
+    FWI_REQUIRE(nt >= 0 && (p->nsrc == 0 || wavelet_dev), "fwi_fd2d_forward: bad wavelet / nt");
+    FWI_REQUIRE(p->nrec == 0 || traces_dev, "fwi_fd2d_forward: traces_dev is NULL but receivers are set");
+    DeviceGuard g(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    FWI_CUDA(cudaMemsetAsync(p->fld[0], 0, p->plane() * sizeof(float), st));
+    FWI_CUDA(cudaMemsetAsync(p->fld[1], 0, p->plane() * sizeof(float), st));
+    int cur = 0;
+    int rc = run_forward(p, wavelet_dev, 0, nt, p->nrec ? traces_dev : nullptr, false, 0, cur, st);
+    p->fwd_cur = cur;
+    return rc;
+}
+
+int fwi_fd2d_wavefield(fwi_fd2d* p, int which, float* out_dev, void* stream) {
+    FWI_REQUIRE(p && out_dev && which >= 0 && which <= 2, "fwi_fd2d_wavefield: bad arguments");
+    DeviceGuard g(p->device);
+    const float* src = (which == 0) ? p->fld[p->fwd_cur] : (which == 1 ? p->fld[p->fwd_cur ^ 1] : p->acc);
+    dim3 grid((p->nx + 127) / 128, p->nz);
+    fd_unpitch_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(src, p->nz, p->nx, p->px, out_dev);
+    FWI_CUDA(cudaGetLastError());
+    return FWI_OK;
+}
+
+int fwi_fd2d_gradient(fwi_fd2d* p, const float* wavelet_dev, const float* obs_dev, int nt, float* grad_dev,
+                      float* traces_dev, double* misfit_host, void* stream) {
+    FWI_REQUIRE(p && p->model_set, "fwi_fd2d_gradient: set the model first");
+    FWI_REQUIRE(wavelet_dev && obs_dev && grad_dev && nt >= 1, "fwi_fd2d_gradient: NULL argument or nt < 1");
+    FWI_REQUIRE(p->nsrc >= 1 && p->nrec >= 1, "fwi_fd2d_gradient: geometry needs at least one source and one receiver");
+    DeviceGuard g(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t pl = p->plane();
+    // ---- choose between holding every w_n in HBM and two-level checkpointing --------------------------
+    size_t budget = p->mem_limit;
+    if (!budget) {
+        size_t fr = 0, tot = 0;
+        FWI_CUDA(cudaMemGetInfo(&fr, &tot));
+        budget = (size_t)((fr + (p->snap_steps + 2 * p->ckpt_slots) * pl * sizeof(float)) * 0.85);
+    }
+    const size_t max_planes = budget / (pl * sizeof(float));
+    int seg = nt, nseg = 1;
+    if ((size_t)nt > max_planes) {
+        // segment length S with S + 2*ceil(nt/S) planes minimal-ish: start from sqrt(2 nt)
+        seg = std::max(1, (int)std::ceil(std::sqrt(2.0 * nt)));
+        nseg = (nt + seg - 1) / seg;
+        FWI_REQUIRE((size_t)seg + 2 * (size_t)nseg <= max_planes, "fwi_fd2d_gradient: %zu bytes are not enough even with checkpointing (need %zu planes of %zu bytes)", budget, (size_t)seg + 2 * (size_t)nseg, pl * sizeof(float));
+    }
+    if (p->snap_steps < (size_t)seg) {
+        if (p->snap) cudaFree(p->snap);
+        p->snap = nullptr; p->snap_steps = 0;
+        FWI_CUDA(cudaMalloc(&p->snap, (size_t)seg * pl * sizeof(float)));
+        p->snap_steps = seg;
+    }
+    if (nseg > 1 && p->ckpt_slots < (size_t)nseg) {
+        if (p->ckpt) cudaFree(p->ckpt);
+        p->ckpt = nullptr; p->ckpt_slots = 0;
+        FWI_CUDA(cudaMalloc(&p->ckpt, (size_t)nseg * 2 * pl * sizeof(float)));
+        p->ckpt_slots = nseg;
+    }
+    const size_t ntr = (size_t)nt * p->nrec;
+    int rc = ensure_bytes(&p->resid, &p->resid_cap, ntr);
+    if (rc) return rc;
+    float* syn = traces_dev;
+    if (!syn) { rc = ensure_bytes(&p->syn, &p->syn_cap, ntr); if (rc) return rc; syn = p->syn; }
+
+    // ---- forward -----------------------------------------------------------------------------------------
+    FWI_CUDA(cudaMemsetAsync(p->fld[0], 0, pl * sizeof(float), st));
+    FWI_CUDA(cudaMemsetAsync(p->fld[1], 0, pl * sizeof(float), st));
+    int cur = 0;
+    std::vector<int> seg_cur(nseg, 0);
+    if (nseg == 1) {
+        rc = run_forward(p, wavelet_dev, 0, nt, syn, true, 0, cur, st);
+        if (rc) return rc;
+    } else {
+        for (int s = 0; s < nseg; ++s) {
+            FWI_CUDA(cudaMemcpyAsync(p->ckpt + (size_t)(2 * s) * pl, p->fld[cur], pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            FWI_CUDA(cudaMemcpyAsync(p->ckpt + (size_t)(2 * s + 1) * pl, p->fld[cur ^ 1], pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            seg_cur[s] = cur;
+            rc = run_forward(p, wavelet_dev, s * seg, std::min(nt, (s + 1) * seg), syn, false, 0, cur, st);
+            if (rc) return rc;
+        }
+    }
+    p->fwd_cur = cur;
+    // ---- residual + misfit -----------------------------------------------------------------------------
+    FWI_CUDA(cudaMemsetAsync(p->d_J, 0, sizeof(double), st));
+    fd_residual_kernel<<<(unsigned)std::min<size_t>(1024, (ntr + 255) / 256), 256, 0, st>>>(syn, obs_dev, (int64_t)ntr, p->resid, p->d_J);
+    FWI_CUDA(cudaGetLastError());
+    p->launches += 2;      // residual + gradient finalize
+    // ---- adjoint + imaging -------------------------------------------------------------------------------
+    FWI_CUDA(cudaMemsetAsync(p->fld[2], 0, pl * sizeof(float), st));
+    FWI_CUDA(cudaMemsetAsync(p->fld[3], 0, pl * sizeof(float), st));
+    FWI_CUDA(cudaMemsetAsync(p->acc, 0, pl * sizeof(float), st));
+    int acur = 0;
+    if (nseg == 1) {
+        rc = run_adjoint(p, p->resid, 0, nt, 0, acur, st);
+        if (rc) return rc;
+    } else {
+        for (int s = nseg - 1; s >= 0; --s) {
+            const int n0 = s * seg, n1 = std::min(nt, (s + 1) * seg);
+            int c = seg_cur[s];
+            FWI_CUDA(cudaMemcpyAsync(p->fld[c], p->ckpt + (size_t)(2 * s) * pl, pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            FWI_CUDA(cudaMemcpyAsync(p->fld[c ^ 1], p->ckpt + (size_t)(2 * s + 1) * pl, pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            rc = run_forward(p, wavelet_dev, n0, n1, nullptr, true, n0, c, st);     // recompute w_n for this segment
+            if (rc) return rc;
+            rc = run_adjoint(p, p->resid, n0, n1, n0, acur, st);
+            if (rc) return rc;
+        }
+    }
+    dim3 grid((p->nx + 127) / 128, p->nz);
+    fd_grad_finalize_kernel<<<grid, 128, 0, st>>>(p->acc, p->vp, p->nz, p->nx, p->px, grad_dev);
+    FWI_CUDA(cudaGetLastError());
+    if (misfit_host) {
+        FWI_CUDA(cudaMemcpyAsync(misfit_host, p->d_J, sizeof(double), cudaMemcpyDeviceToHost, st));
+        FWI_CUDA(cudaStreamSynchronize(st));
+    }
+    return FWI_OK;
+}
+
+int64_t fwi_fd2d_launch_count(fwi_fd2d* p) { return p ? p->launches : 0; }
+
+int fwi_fd_misfit(const float* syn_dev, const float* obs_dev, int64_t n, float* resid_dev, double* misfit_host, void* stream) {
+    FWI_REQUIRE(syn_dev && obs_dev && resid_dev && misfit_host && n >= 0, "fwi_fd_misfit: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* dJ = nullptr;
+    FWI_CUDA(cudaMallocAsync(&dJ, sizeof(double), st));
+    FWI_CUDA(cudaMemsetAsync(dJ, 0, sizeof(double), st));
+    if (n > 0) fd_residual_kernel<<<(unsigned)std::min<int64_t>(1024, (n + 255) / 256), 256, 0, st>>>(syn_dev, obs_dev, n, resid_dev, dJ);
+    FWI_CUDA(cudaGetLastError());
+    FWI_CUDA(cudaMemcpyAsync(misfit_host, dJ, sizeof(double), cudaMemcpyDeviceToHost, st));
+    FWI_CUDA(cudaFreeAsync(dJ, st));
+    FWI_CUDA(cudaStreamSynchronize(st));
+    return FWI_OK;
+}
+
+int fwi_fd_model_update(float* v_dev, const float* grad_dev, int64_t n, float step, float vmin, float vmax, void* stream) {
+    FWI_REQUIRE(v_dev && grad_dev && n >= 0 && vmin <= vmax, "fwi_fd_model_update: bad arguments");
+    if (n > 0) fd_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(v_dev, grad_dev, step, vmin, vmax, n);
+    FWI_CUDA(cudaGetLastError());
+    return FWI_OK;
+}
+
+int fwi_fd_absmax(const float* x_dev, int64_t n, float* out_host, void* stream) {
+    FWI_REQUIRE(x_dev && out_host && n >= 1, "fwi_fd_absmax: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int* d = nullptr;
+    FWI_CUDA(cudaMallocAsync(&d, sizeof(unsigned int), st));
+    FWI_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned int), st));
+    fd_absmax_kernel<<<(unsigned)std::min<int64_t>(1024, (n + 255) / 256), 256, 0, st>>>(x_dev, n, d);
+    FWI_CUDA(cudaGetLastError());
+    unsigned int h = 0;
+    FWI_CUDA(cudaMemcpyAsync(&h, d, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    FWI_CUDA(cudaFreeAsync(d, st));
+    FWI_CUDA(cudaStreamSynchronize(st));
+    memcpy(out_host, &h, sizeof(float));
+    return FWI_OK;
+}
+
+}  // extern "C"

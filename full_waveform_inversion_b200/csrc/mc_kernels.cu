@@ -1,0 +1,995 @@
+// Track A: batched Monte-Carlo source-inversion hot path for sm_100a.
+//
+//   sample -> forward model -> misfit -> likelihood            (FWI:713-774)
+//
+// One warp owns one trace k at a time and streams that trace's prepared rows
+// [t][G_0..G_{CC-1}, d, d'] with warp-uniform 16-byte loads (one LDG.128 feeds four FMAs of
+// every lane); each lane owns S source samples whose coefficient vectors live in registers, so
+// the K*T*C contraction needs no cross-thread reduction at all.  Per-(trace,sample) statistics go
+// to shared memory and are folded into the similarity in float64 by one thread per sample.
+// The path is FP32-FMA bound (G is ~0.4 MB and L2/L1 resident; ~40-80 B of HBM traffic per sample).
+#include "common.cuh"
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+namespace fwi {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct TraceConst {
+    double mean_d;   // mean of the trace's data (the centring constant used for d')
+    double ssd;      // sum (d - mean_d)^2
+    double sumd2;    // sum d^2
+    double maxd;     // max |d| of the ORIGINAL trace (normalisation, FWI:598)
+    double sigma;    // mean |d[-60:-10]| (FWI:580), NaN when T < 60
+    double d_first, d_last;
+};
+
+struct FlatConst {   // constants of the flattened (K*Tv) data array; index = normalised?
+    double n;
+    double D1[2], D2[2];   // sum d, sum d^2
+    double sigma[2];       // gaussian noise level of the flattened array
+};
+
+enum { MODE_SSE = 0, MODE_MOM = 1, MODE_MOM_MAX = 2 };
+
+struct EvalParams {
+    const float* rows;
+    const float* gbar;
+    const TraceConst* tc;
+    FlatConst fc;
+    const int* phase;
+    const float* M;
+    int64_t ldm;
+    const float* frac;
+    int nfrac;
+    int64_t N;
+    int K, Tv, metric, flags, boundary_fix;
+    float* sim;
+    float* like;
+};
+
+__host__ __device__ constexpr int row_width(int CC) { return (CC + 2 + 3) & ~3; }
+__host__ __device__ constexpr int nstat(int mode) { return mode == MODE_SSE ? 1 : (mode == MODE_MOM ? 3 : 4); }
+
+template <int C, int NM>
+__device__ __forceinline__ void make_coef(float (&coef)[C * NM], const float (&m)[C], float f) {
+    if (NM == 1) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) coef[c] = m[c];
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            coef[c] = m[c] * (1.0f - f);     // synth = (1-f) G0.M + f G1.M   (FWI:727, FWI:731)
+            coef[C + c] = m[c] * f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int C, int NM, int S, int MODE>
+__global__ void __launch_bounds__(384) mc_eval_kernel(EvalParams p) {
+    constexpr int CC = C * NM;
+    constexpr int RW = row_width(CC);
+    constexpr int RW4 = RW / 4;
+    constexpr int NST = nstat(MODE);
+    constexpr int SPB = 32 * S;
+    constexpr int CHUNK = 64;
+    extern __shared__ float stats[];          // [K][NST][SPB]
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * SPB;
+
+    float m[S][C];
+    float fr[S][3];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        int64_t n = base + s * 32 + lane;
+        if (n >= p.N) n = p.N - 1;            // tail lanes recompute the last sample, never stored
+#pragma unroll
+        for (int c = 0; c < C; ++c) m[s][c] = __ldg(p.M + (int64_t)c * p.ldm + n);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) fr[s][j] = 0.f;
+        if (NM == 2) {
+            for (int j = 0; j < p.nfrac; ++j) fr[s][j] = __ldg(p.frac + (int64_t)j * p.ldm + n);
+        }
+    }
+
+    for (int k = warp; k < p.K; k += nwarps) {
+        float coef[S][CC];
+        float mu[S];
+        const int ph = (NM == 2 && p.nfrac == 3 && p.phase) ? p.phase[k] : 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            make_coef<C, NM>(coef[s], m[s], fr[s][ph]);
+            float a = 0.f;
+            if (MODE != MODE_SSE) {
+#pragma unroll
+                for (int c = 0; c < CC; ++c) a = fmaf(__ldg(p.gbar + k * CC + c), coef[s][c], a);
+            }
+            mu[s] = a;
+        }
+        double t0[S], t1[S];
+        float vmax[S], vmin[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) { t0[s] = 0.0; t1[s] = 0.0; vmax[s] = -INFINITY; vmin[s] = INFINITY; }
+
+        const float4* rp = reinterpret_cast<const float4*>(p.rows) + (size_t)k * p.Tv * RW4;
+        for (int tb = 0; tb < p.Tv; tb += CHUNK) {
+            const int te = min(p.Tv, tb + CHUNK);
+            float a0[S], a1[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
+#pragma unroll 4
+            for (int t = tb; t < te; ++t) {
+                float r[RW];
+#pragma unroll
+                for (int q = 0; q < RW4; ++q) {
+                    float4 v = __ldg(rp + (size_t)t * RW4 + q);
+                    r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    float v = (MODE == MODE_SSE) ? 0.f : -mu[s];
+#pragma unroll
+                    for (int c = 0; c < CC; ++c) v = fmaf(r[c], coef[s][c], v);
+                    if (MODE == MODE_SSE) {
+                        float e = r[CC] - v;                 // raw d - raw synth (FWI:515)
+                        a0[s] = fmaf(e, e, a0[s]);
+                    } else {
+                        a0[s] = fmaf(v, v, a0[s]);           // sum s'^2
+                        a1[s] = fmaf(r[CC + 1], v, a1[s]);   // sum d' s'
+                        if (MODE == MODE_MOM_MAX) { vmax[s] = fmaxf(vmax[s], v); vmin[s] = fminf(vmin[s], v); }
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) { t0[s] += (double)a0[s]; t1[s] += (double)a1[s]; }
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            float* st = stats + (size_t)k * NST * SPB + s * 32 + lane;
+            st[0] = (float)t0[s];
+            if (MODE != MODE_SSE) { st[SPB] = (float)t1[s]; st[2 * SPB] = mu[s]; }
+            if (MODE == MODE_MOM_MAX) st[3 * SPB] = fmaxf(fabsf(vmax[s] + mu[s]), fabsf(vmin[s] + mu[s]));
+        }
+    }
+    __syncthreads();
+
+    // ---- fold the per-trace statistics into the similarity, one thread per sample (float64)
+    for (int i = threadIdx.x; i < SPB; i += blockDim.x) {
+        const int64_t n = base + i;
+        if (n >= p.N) continue;
+        const bool norm = p.flags & FWI_FLAG_NORMALISED;
+        const bool simul = p.flags & FWI_FLAG_SIMULTANEOUS;
+        const double Tn = (double)p.Tv;
+        const float* st = stats + i;
+        double result;
+        if (p.metric == FWI_METRIC_VR || p.metric == FWI_METRIC_GAU) {
+            double acc = 0.0, tot_sse = 0.0, tot_dd = 0.0;
+            for (int k = 0; k < p.K; ++k) {
+                const TraceConst tc = p.tc[k];
+                const float* q = st + (size_t)k * NST * SPB;
+                double sse, dd, sig = tc.sigma;
+                if (MODE == MODE_SSE) {
+                    sse = q[0];
+                    dd = tc.sumd2;
+                } else {
+                    const double s2 = q[0], sd = q[SPB], mu = q[2 * SPB];
+                    const double a = 1.0 / (double)q[3 * SPB], b = 1.0 / tc.maxd;    // FWI:598-599
+                    const double Sss = (s2 + Tn * mu * mu) * a * a;
+                    const double Sds = (sd + Tn * tc.mean_d * mu) * a * b;
+                    dd = tc.sumd2 * b * b;
+                    sse = dd - 2.0 * Sds + Sss;
+                    sig = tc.sigma * b;
+                }
+                tot_sse += sse;
+                tot_dd += dd;
+                if (p.metric == FWI_METRIC_VR) acc += fmax(0.0, 1.0 - sse / dd);      // FWI:515-519
+                else acc += exp(-sse / (2.0 * sig * sig));                             // FWI:581
+            }
+            if (simul) {
+                if (p.metric == FWI_METRIC_VR) result = fmax(0.0, 1.0 - tot_sse / tot_dd);
+                else { const double sg = p.fc.sigma[norm ? 1 : 0]; result = exp(-tot_sse / (2.0 * sg * sg)); }
+            } else {
+                result = acc / p.K;                                                    // FWI:682
+                if (p.metric == FWI_METRIC_GAU && (p.flags & FWI_FLAG_STRICT_REF)) result = 0.0;   // quirk q1
+            }
+        } else {   // CC, PCC, CC-shift: Pearson on the (possibly 4x interpolated) rows
+            if (!simul) {
+                double acc = 0.0;
+                for (int k = 0; k < p.K; ++k) {
+                    const float* q = st + (size_t)k * NST * SPB;
+                    const double pcc = (double)q[SPB] / sqrt((double)q[0] * p.tc[k].ssd);   // FWI:572-573
+                    acc += (pcc < 0.0) ? 0.0 : pcc;                                          // FWI:574-575
+                }
+                result = acc / p.K;
+            } else {
+                double A1 = 0.0, A2 = 0.0, A3 = 0.0;
+                for (int k = 0; k < p.K; ++k) {
+                    const TraceConst tc = p.tc[k];
+                    const float* q = st + (size_t)k * NST * SPB;
+                    const double s2 = q[0], sd = q[SPB], mu = q[2 * SPB];
+                    double a = 1.0, b = 1.0;
+                    if (MODE == MODE_MOM_MAX) { a = 1.0 / (double)q[3 * SPB]; b = 1.0 / tc.maxd; }
+                    A1 += a * Tn * mu;
+                    A2 += a * a * (s2 + Tn * mu * mu);
+                    A3 += a * b * (sd + Tn * tc.mean_d * mu);
+                }
+                if (MODE == MODE_MOM_MAX && p.boundary_fix) {
+                    // CC-shift, normalised, flattened: np.interp runs across trace boundaries on the
+                    // already-normalised flattened arrays (FWI:612, FWI:554-555); the rows hold the
+                    // per-trace clamped interpolation, so patch the 3 points after each internal boundary.
+                    float mm[C];
+                    for (int c = 0; c < C; ++c) mm[c] = __ldg(p.M + (int64_t)c * p.ldm + n);
+                    float ff[3] = {0.f, 0.f, 0.f};
+                    if (NM == 2) for (int j = 0; j < p.nfrac; ++j) ff[j] = __ldg(p.frac + (int64_t)j * p.ldm + n);
+                    double prev_c = 0.0, prev_cd = 0.0;
+                    for (int k = 0; k < p.K; ++k) {
+                        const TraceConst tc = p.tc[k];
+                        float coef[CC];
+                        const int ph = (NM == 2 && p.nfrac == 3 && p.phase) ? p.phase[k] : 0;
+                        make_coef<C, NM>(coef, mm, ff[ph]);
+                        const float* r0 = p.rows + ((size_t)k * p.Tv) * RW;
+                        const float* r1 = p.rows + ((size_t)k * p.Tv + p.Tv - 1) * RW;
+                        double first = 0.0, last = 0.0;
+                        for (int c = 0; c < CC; ++c) { first += (double)r0[c] * coef[c]; last += (double)r1[c] * coef[c]; }
+                        const double a = 1.0 / (double)st[((size_t)k * NST + 3) * SPB], b = 1.0 / tc.maxd;
+                        if (k > 0) {
+                            const double c_ = prev_c, cd = prev_cd;
+                            const double dl = first * a - c_, dd = tc.d_first * b - cd;
+                            A1 += 1.5 * dl;
+                            A2 += 3.0 * c_ * dl + 0.875 * dl * dl;
+                            A3 += 1.5 * (cd * dl + c_ * dd) + 0.875 * dd * dl;
+                        }
+                        prev_c = last * a;
+                        prev_cd = tc.d_last * b;
+                    }
+                }
+                const int ni = norm ? 1 : 0;
+                const double nn = p.fc.n, D1 = p.fc.D1[ni], D2 = p.fc.D2[ni];
+                const double cov = A3 - A1 * D1 / nn, vs = A2 - A1 * A1 / nn, vd = D2 - D1 * D1 / nn;
+                const double pcc = cov / sqrt(vs * vd);
+                result = (pcc < 0.0) ? 0.0 : pcc;
+            }
+        }
+        p.sim[n] = (float)result;
+        if (p.like) p.like[n] = (float)exp(-(1.0 - result) * 0.5);                   // FWI:774
+    }
+}
+
+// --------------------------------------------------------------------------------------------- forward traces
+template <int C, int NM>
+__global__ void mc_forward_kernel(const float* __restrict__ rows, const int* __restrict__ phase,
+                                  const float* __restrict__ M, int64_t ldm, int n_comp,
+                                  const float* __restrict__ frac, int nfrac, int64_t N, int K, int T,
+                                  float* __restrict__ out) {
+    constexpr int CC = C * NM;
+    constexpr int RW = row_width(CC);
+    const int64_t kt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (kt >= (int64_t)K * T) return;
+    const int k = (int)(kt / T);
+    float r[RW];
+    const float4* rp = reinterpret_cast<const float4*>(rows) + kt * (RW / 4);
+#pragma unroll
+    for (int q = 0; q < RW / 4; ++q) {
+        float4 v = __ldg(rp + q);
+        r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+    }
+    const int ph = (NM == 2 && nfrac == 3 && phase) ? phase[k] : 0;
+    for (int64_t n = blockIdx.y; n < N; n += gridDim.y) {
+        float f = 0.f;
+        if (NM == 2 && frac) f = __ldg(frac + (int64_t)ph * ldm + n);
+        float v = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if (c < n_comp) {                                                          // FWI:262
+                const float mc = __ldg(M + (int64_t)c * ldm + n);
+                if (NM == 1) v = fmaf(r[c], mc, v);
+                else { v = fmaf(r[c], mc * (1.0f - f), v); v = fmaf(r[C + c], mc * f, v); }
+            }
+        }
+        out[n * (int64_t)K * T + kt] = v;
+    }
+}
+
+// --------------------------------------------------------------------------------------------- samplers
+struct Philox {
+    uint32_t c[4], k[2];
+    __device__ __forceinline__ void round_() {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k[0], n2 = hi0 ^ c[3] ^ k[1];
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+    }
+    __device__ __forceinline__ void run() {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) round_();
+    }
+};
+
+__device__ __forceinline__ void philox4(uint64_t seed, uint64_t index, uint32_t block, uint32_t out[4]) {
+    Philox p;
+    p.c[0] = (uint32_t)index; p.c[1] = (uint32_t)(index >> 32); p.c[2] = block; p.c[3] = 0x46574921u;
+    p.k[0] = (uint32_t)seed; p.k[1] = (uint32_t)(seed >> 32);
+    p.run();
+    out[0] = p.c[0]; out[1] = p.c[1]; out[2] = p.c[2]; out[3] = p.c[3];
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0,1)
+
+__device__ __forceinline__ void unit3(const float* a, float* o) {
+    const float inv = rsqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    // one Newton step on the reciprocal root keeps the norm within 1 ulp
+    const float n2 = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+    const float r = inv * (1.5f - 0.5f * n2 * inv * inv);
+    o[0] = a[0] * r; o[1] = a[1] * r; o[2] = a[2] * r;
+}
+
+// R = Rz(phi) Ry(theta) from cos/sin (FWI:228-229)
+__device__ __forceinline__ void make_rot(float ct, float st, float cp, float sp, float R[3][3]) {
+    R[0][0] = cp * ct; R[0][1] = -sp; R[0][2] = cp * st;
+    R[1][0] = sp * ct; R[1][1] = cp;  R[1][2] = sp * st;
+    R[2][0] = -st;     R[2][1] = 0.f; R[2][2] = ct;
+}
+// B = R A R^T for symmetric A, returned as the 6-vector of FWI:206-208
+__device__ __forceinline__ void rot_sym6(const float R[3][3], const float A[3][3], float o[6]) {
+    float RA[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) RA[i][j] = R[i][0] * A[0][j] + R[i][1] * A[1][j] + R[i][2] * A[2][j];
+    float B[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) B[i][j] = RA[i][0] * R[j][0] + RA[i][1] * R[j][1] + RA[i][2] * R[j][2];
+    const float sq2 = 1.41421356237309515f;
+    o[0] = B[0][0]; o[1] = B[1][1]; o[2] = B[2][2]; o[3] = sq2 * B[0][1]; o[4] = sq2 * B[0][2]; o[5] = sq2 * B[1][2];
+}
+__device__ __forceinline__ void unit6(float* v) {
+    float n2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) n2 = fmaf(v[i], v[i], n2);
+    const float r = 1.0f / sqrtf(n2);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v[i] *= r;
+}
+// theta = atan2(sqrt(x^2+y^2), z), phi = atan2(y, x) of a unit vector (FWI:308-309): only the
+// cosines and sines are ever used, and those are algebraic in (x,y,z).
+__device__ __forceinline__ void rot_from_vec_atan2(const float* a, float R[3][3]) {
+    float u[3];
+    unit3(a, u);
+    const float rho = sqrtf(u[0] * u[0] + u[1] * u[1]);
+    make_rot(u[2], rho, u[0] / rho, u[1] / rho, R);
+}
+// theta = arccos(z), phi = arccos(x / sin(theta)) (FWI:497-498): phi in [0, pi] so sin(phi) >= 0.
+__device__ __forceinline__ void rot_from_vec_acos(const float* a, float R[3][3]) {
+    float u[3];
+    unit3(a, u);
+    const float rho = sqrtf(u[0] * u[0] + u[1] * u[1]);
+    make_rot(u[2], rho, u[0] / rho, fabsf(u[1]) / rho, R);
+}
+// crack tensor on the lune perimeter (FWI:395-423): diag entries
+__device__ __forceinline__ void crack_diag(float u, float r1, float r2, float dg[3]) {
+    const float a = (r1 <= 0.5f) ? 0.f : 0.866025403784438597f;   // sin(phi_lune): 0 or sin(pi/3)
+    const float b = sinpif(0.5f * u);                             // sin(theta_lune)
+    const float h = 1.0f / sqrtf(a * a + b * b);
+    float ca = fabsf(b) * h, sa = copysignf(a, b) * h;            // alpha = arctan(a/b)
+    if (r2 > 0.25f && r2 <= 0.5f) { ca = -ca; sa = -sa; }                         // + pi
+    else if (r2 > 0.5f && r2 <= 0.75f) { const float t = ca; ca = -sa; sa = t; }  // + pi/2
+    else if (r2 > 0.75f && r2 <= 1.0f) { const float t = ca; ca = sa; sa = -t; }  // + 3pi/2
+    const float sq2 = 1.41421356237309515f;
+    const float sc = 1.0f / (sqrtf(4.f * sa * sa + ca * ca) * 1.73205080756887729f);
+    dg[0] = sc * (ca - sq2 * sa); dg[1] = dg[0]; dg[2] = sc * (ca + 2.f * sq2 * sa);
+}
+
+// raw draws (reference consumption order) -> tensor rows; returns amp-frac (or -1)
+__device__ float transform_draws(int type, const float* q, float amp, float* out) {
+    const float DC0[3][3] = {{0.f, 0.f, 1.f}, {0.f, 0.f, 0.f}, {1.f, 0.f, 0.f}};   // FWI:299
+    float R[3][3];
+    float frac = -1.f;
+    switch (type) {
+        case FWI_TYPE_FULL_MT: {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) out[i] = q[i];
+            unit6(out);
+        } break;
+        case FWI_TYPE_SINGLE_FORCE: unit3(q, out); break;
+        case FWI_TYPE_DC: {
+            rot_from_vec_atan2(q, R);
+            rot_sym6(R, DC0, out);
+            unit6(out);
+        } break;
+        case FWI_TYPE_DC_SF_COUPLE: {
+            rot_from_vec_atan2(q, R);
+            rot_sym6(R, DC0, out);
+            unit6(out);
+            frac = q[3];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) out[i] *= frac;
+            // force = R [1,0,0] = first column of R, NED -> END swaps the first two (FWI:359)
+            out[6] = R[1][0] * (1.f - frac); out[7] = R[0][0] * (1.f - frac); out[8] = R[2][0] * (1.f - frac);
+        } break;
+        case FWI_TYPE_DC_SF_NO_COUPLING: {
+            rot_from_vec_atan2(q, R);
+            rot_sym6(R, DC0, out);
+            unit6(out);
+            frac = q[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) out[i] *= frac;
+            unit3(q + 3, out + 6);
+            out[6] *= (1.f - frac); out[7] *= (1.f - frac); out[8] *= (1.f - frac);
+        } break;
+        case FWI_TYPE_DC_CRACK_COUPLE: {
+            float dg[3];
+            crack_diag(q[0], q[1], q[2], dg);
+            frac = q[3];
+            float A[3][3] = {{(1.f - frac) * dg[0], 0.f, frac}, {0.f, (1.f - frac) * dg[1], 0.f}, {frac, 0.f, (1.f - frac) * dg[2]}};
+            rot_from_vec_atan2(q + 4, R);
+            rot_sym6(R, A, out);
+            unit6(out);
+        } break;
+        case FWI_TYPE_SF_CRACK_NO_COUPLING: {
+            float sf[3];
+            unit3(q, sf);
+            float dg[3];
+            crack_diag(q[3], q[4], q[5], dg);
+            const float A[3][3] = {{dg[0], 0.f, 0.f}, {0.f, dg[1], 0.f}, {0.f, 0.f, dg[2]}};
+            rot_from_vec_acos(q + 6, R);
+            rot_sym6(R, A, out);                      // not re-normalised (FWI:501-503)
+            frac = q[9];                              // fraction of the force (FWI:505-507)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) out[i] *= (1.f - frac);
+            out[6] = sf[0] * frac; out[7] = sf[1] * frac; out[8] = sf[2] * frac;
+        } break;
+    }
+    const int nc = (type == FWI_TYPE_SINGLE_FORCE) ? 3 : ((type == FWI_TYPE_FULL_MT || type == FWI_TYPE_DC || type == FWI_TYPE_DC_CRACK_COUPLE) ? 6 : 9);
+    for (int i = 0; i < nc; ++i) out[i] *= amp;
+    return frac;
+}
+
+__host__ __device__ inline int type_components(int t) {
+    return (t == FWI_TYPE_SINGLE_FORCE) ? 3 : ((t == FWI_TYPE_FULL_MT || t == FWI_TYPE_DC || t == FWI_TYPE_DC_CRACK_COUPLE) ? 6 : 9);
+}
+__host__ __device__ inline int type_draws(int t) {
+    const int nd[7] = {6, 3, 3, 4, 7, 7, 10};
+    return nd[t];
+}
+__host__ __device__ inline bool type_combined(int t) { return t >= FWI_TYPE_DC_SF_COUPLE; }
+
+__global__ void mc_transform_kernel(int type, const float* __restrict__ draws, int64_t ldn, int64_t N, float amp,
+                                    float* __restrict__ out, int64_t ldo) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float q[10], o[9];
+    const int nd = type_draws(type);
+    for (int j = 0; j < nd; ++j) q[j] = draws[(int64_t)j * ldn + n];
+    const float frac = transform_draws(type, q, amp, o);
+    const int nc = type_components(type);
+    for (int c = 0; c < nc; ++c) out[(int64_t)c * ldo + n] = o[c];
+    if (type_combined(type)) out[(int64_t)nc * ldo + n] = frac;
+}
+
+// draw pattern per type: 'n' normal, 'u' U(-1,1), 'r' U[0,1)   (oracle/mc_oracle.py DRAW_PATTERN)
+__device__ __constant__ char c_patterns[7][11] = {"nnnnnn", "nnn", "nnn", "nnnr", "nnnnnnr", "urrrnnn", "nnnurrnnnr"};
+
+__global__ void mc_sample_kernel(int type, uint64_t seed, int64_t first, int64_t N, float amp, int nfrac,
+                                 float* __restrict__ out, int64_t ldo) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint64_t gidx = (uint64_t)(first + n);
+    uint32_t w[16];
+    philox4(seed, gidx, 0, w);
+    philox4(seed, gidx, 1, w + 4);
+    philox4(seed, gidx, 2, w + 8);
+    philox4(seed, gidx, 3, w + 12);
+    // six normals from three Box-Muller pairs, then four uniforms, then three media fractions
+    float nrm[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float r = sqrtf(-2.f * logf(u01(w[2 * j])));
+        float s, c;
+        sincospif(2.f * u01(w[2 * j + 1]), &s, &c);
+        nrm[2 * j] = r * c; nrm[2 * j + 1] = r * s;
+    }
+    float q[10], o[9];
+    int in = 0, iu = 6;
+    const int nd = type_draws(type);
+    for (int j = 0; j < nd; ++j) {
+        const char ch = c_patterns[type][j];
+        if (ch == 'n') q[j] = nrm[in++];
+        else if (ch == 'u') q[j] = 2.f * u01(w[iu++]) - 1.f;
+        else q[j] = u01(w[iu++]);
+    }
+    const float frac = transform_draws(type, q, amp, o);
+    const int nc = type_components(type);
+    for (int c = 0; c < nc; ++c) out[(int64_t)c * ldo + n] = o[c];
+    int row = nc;
+    if (type_combined(type)) out[(int64_t)(row++) * ldo + n] = frac;
+    for (int j = 0; j < nfrac; ++j) out[(int64_t)(row++) * ldo + n] = u01(w[10 + j]);     // FWI:719-721, FWI:730
+}
+
+// --------------------------------------------------------------------------------------------- reductions
+__global__ void mc_reduce_kernel(const float* __restrict__ L, int64_t N, double* __restrict__ psum,
+                                 float* __restrict__ pmax, long long* __restrict__ parg) {
+    __shared__ double ssum[32];
+    __shared__ float smax[32];
+    __shared__ long long sarg[32];
+    double s = 0.0;
+    float mx = -INFINITY;
+    long long am = -1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = L[i];
+        s += (double)v;
+        if (v > mx) { mx = v; am = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+        const long long oam = __shfl_xor_sync(0xffffffffu, am, o);
+        if (omx > mx || (omx == mx && oam >= 0 && (am < 0 || oam < am))) { mx = omx; am = oam; }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { ssum[warp] = s; smax[warp] = mx; sarg[warp] = am; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int w = 1; w < nw; ++w) {
+            s += ssum[w];
+            if (smax[w] > mx || (smax[w] == mx && sarg[w] >= 0 && (am < 0 || sarg[w] < am))) { mx = smax[w]; am = sarg[w]; }
+        }
+        psum[blockIdx.x] = s; pmax[blockIdx.x] = mx; parg[blockIdx.x] = am;
+    }
+}
+
+__global__ void mc_normalise_kernel(const float* __restrict__ L, int64_t N, double scale, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) out[i] = (float)((double)L[i] * scale);
+}
+
+}  // namespace fwi
+
+// =============================================================================================== host side
+using namespace fwi;
+
+struct RowSet {
+    float* rows = nullptr;
+    float* gbar = nullptr;
+    TraceConst* tc = nullptr;
+    FlatConst fc{};
+    int Tv = 0;
+    bool built = false;
+};
+
+struct fwi_mc_ctx {
+    int device = 0, K = 0, C = 0, T = 0, NM = 1, CC = 0, RW = 0;
+    std::vector<double> G, d;     // host copies (reference layout) for the lazily built CC-shift rows
+    std::vector<int> phase;
+    int* phase_dev = nullptr;
+    RowSet base, hr, hrflat;
+    // scratch
+    float* stage_M = nullptr; float* stage_sim = nullptr; float* stage_frac = nullptr; int64_t stage_cap = 0;
+    double* h_pin = nullptr; int64_t h_pin_bytes = 0;
+    double* red_sum = nullptr; float* red_max = nullptr; long long* red_arg = nullptr;
+    int sm_count = 148;
+    bool uploaded = false;
+};
+
+static void free_rowset(RowSet& r) {
+    if (r.rows) cudaFree(r.rows);
+    if (r.gbar) cudaFree(r.gbar);
+    if (r.tc) cudaFree(r.tc);
+    r = RowSet{};
+}
+
+// data(k, t) accessors on the host copies
+static inline double G_at(const fwi_mc_ctx* c, int k, int comp, int t, int med) {
+    return c->G[(((size_t)k * c->C + comp) * c->T + t) * c->NM + med];
+}
+
+// Build one prepared row set.  variant 0: base (Tv = T); 1: 4x linear interpolation clamped per trace
+// (np.interp on each trace, FWI:554-555); 2: 4x interpolation of the flattened array (runs into the
+// next trace's first sample; only the very last trace clamps).
+static int build_rowset(fwi_mc_ctx* c, RowSet& rs, int variant) {
+    const int K = c->K, C = c->C, T = c->T, NM = c->NM, CC = c->CC, RW = c->RW;
+    const int Tv = (variant == 0) ? T : 4 * T;
+    std::vector<float> rows((size_t)K * Tv * RW, 0.f);
+    std::vector<float> gbar((size_t)K * CC, 0.f);
+    std::vector<TraceConst> tc(K);
+    std::vector<double> dv((size_t)K * Tv);
+    auto interp = [&](auto&& val, int k, int tv) -> double {   // val(k, t) on the original grid
+        if (variant == 0) return val(k, tv);
+        const int i = tv >> 2, j = tv & 3;
+        const double a = val(k, i);
+        if (j == 0) return a;
+        double b;
+        if (i + 1 < T) b = val(k, i + 1);
+        else if (variant == 2 && k + 1 < K) b = val(k + 1, 0);
+        else return a;                                          // right edge clamps
+        return a + (b - a) * (0.25 * j);
+    };
+    for (int k = 0; k < K; ++k) {
+        auto dval = [&](int kk, int t) { return c->d[(size_t)kk * T + t]; };
+        double sum = 0.0, sum2 = 0.0;
+        for (int tv = 0; tv < Tv; ++tv) {
+            const double x = interp(dval, k, tv);
+            dv[(size_t)k * Tv + tv] = x;
+            sum += x; sum2 += x * x;
+        }
+        TraceConst& q = tc[k];
+        q.mean_d = sum / Tv;
+        q.sumd2 = sum2;
+        double ssd = 0.0, mx = 0.0;
+        for (int tv = 0; tv < Tv; ++tv) { const double e = dv[(size_t)k * Tv + tv] - q.mean_d; ssd += e * e; }
+        for (int t = 0; t < T; ++t) mx = std::max(mx, std::fabs(c->d[(size_t)k * T + t]));
+        q.ssd = ssd; q.maxd = mx;
+        q.sigma = NAN;
+        if (Tv >= 60) { double s = 0.0; for (int tv = Tv - 60; tv < Tv - 10; ++tv) s += std::fabs(dv[(size_t)k * Tv + tv]); q.sigma = s / 50.0; }
+        q.d_first = dv[(size_t)k * Tv]; q.d_last = dv[(size_t)k * Tv + Tv - 1];
+        for (int med = 0; med < NM; ++med)
+            for (int comp = 0; comp < C; ++comp) {
+                auto gval = [&](int kk, int t) { return G_at(c, kk, comp, t, med); };
+                double gs = 0.0;
+                for (int tv = 0; tv < Tv; ++tv) {
+                    const double x = interp(gval, k, tv);
+                    rows[((size_t)k * Tv + tv) * RW + med * C + comp] = (float)x;
+                    gs += (double)(float)x;
+                }
+                gbar[(size_t)k * CC + med * C + comp] = (float)(gs / Tv);
+            }
+        for (int tv = 0; tv < Tv; ++tv) {
+            rows[((size_t)k * Tv + tv) * RW + CC] = (float)dv[(size_t)k * Tv + tv];
+            rows[((size_t)k * Tv + tv) * RW + CC + 1] = (float)(dv[(size_t)k * Tv + tv] - q.mean_d);
+        }
+    }
+    // flattened constants (raw and normalised)
+    FlatConst fc{};
+    fc.n = (double)K * Tv;
+    for (int norm = 0; norm < 2; ++norm) {
+        // the normalised flattened array is built from the normalised ORIGINAL traces and then (for the
+        // CC-shift variants) interpolated, exactly as FWI:598 followed by FWI:554 does.
+        std::vector<double> flat((size_t)K * Tv);
+        for (int k = 0; k < K; ++k) {
+            auto dn = [&](int kk, int t) { return c->d[(size_t)kk * T + t] / (norm ? tc[kk].maxd : 1.0); };
+            for (int tv = 0; tv < Tv; ++tv) flat[(size_t)k * Tv + tv] = interp(dn, k, tv);
+        }
+        double s1 = 0.0, s2 = 0.0;
+        for (double x : flat) { s1 += x; s2 += x * x; }
+        fc.D1[norm] = s1; fc.D2[norm] = s2;
+        fc.sigma[norm] = NAN;
+        if (flat.size() >= 60) { double s = 0.0; for (size_t i = flat.size() - 60; i < flat.size() - 10; ++i) s += std::fabs(flat[i]); fc.sigma[norm] = s / 50.0; }
+    }
+    FWI_CUDA(cudaMalloc(&rs.rows, rows.size() * sizeof(float)));
+    FWI_CUDA(cudaMalloc(&rs.gbar, gbar.size() * sizeof(float)));
+    FWI_CUDA(cudaMalloc(&rs.tc, tc.size() * sizeof(TraceConst)));
+    FWI_CUDA(cudaMemcpy(rs.rows, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice));
+    FWI_CUDA(cudaMemcpy(rs.gbar, gbar.data(), gbar.size() * sizeof(float), cudaMemcpyHostToDevice));
+    FWI_CUDA(cudaMemcpy(rs.tc, tc.data(), tc.size() * sizeof(TraceConst), cudaMemcpyHostToDevice));
+    rs.fc = fc; rs.Tv = Tv; rs.built = true;
+    return FWI_OK;
+}
+
+template <int C, int NM, int S, int MODE>
+static int launch_eval_t(const EvalParams& p, int nwarps, cudaStream_t st) {
+    constexpr int SPB = 32 * S;
+    const size_t smem = (size_t)p.K * nstat(MODE) * SPB * sizeof(float);
+    auto kern = mc_eval_kernel<C, NM, S, MODE>;
+    if (smem > 48 * 1024) FWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = ceil_div(p.N, SPB);
+    kern<<<(unsigned)blocks, nwarps * 32, smem, st>>>(p);
+    FWI_CUDA(cudaGetLastError());
+    return FWI_OK;
+}
+template <int C, int NM, int MODE>
+static int launch_eval_s(const EvalParams& p, int S, int nwarps, cudaStream_t st) {
+    if (S == 4) return launch_eval_t<C, NM, (NM == 1 ? 4 : 2), MODE>(p, nwarps, st);
+    if (S == 2) return launch_eval_t<C, NM, (NM == 1 ? 2 : 1), MODE>(p, nwarps, st);
+    return launch_eval_t<C, NM, 1, MODE>(p, nwarps, st);
+}
+template <int C, int NM>
+static int launch_eval_m(const EvalParams& p, int mode, int S, int nwarps, cudaStream_t st) {
+    if (mode == MODE_SSE) return launch_eval_s<C, NM, MODE_SSE>(p, S, nwarps, st);
+    if (mode == MODE_MOM) return launch_eval_s<C, NM, MODE_MOM>(p, S, nwarps, st);
+    return launch_eval_s<C, NM, MODE_MOM_MAX>(p, S, nwarps, st);
+}
+
+static int pick_warps(int K) {
+    // warps per CTA so that ceil(K/nw)*nw wastes the least; ties -> more warps
+    int best = 4; double best_w = 1e9;
+    for (int nw = 4; nw <= 12; ++nw) {
+        const double waste = (double)(((K + nw - 1) / nw) * nw) / K;
+        if (waste <= best_w + 1e-12) { best_w = waste; best = nw; }
+    }
+    return std::min(best, std::max(1, K));
+}
+
+extern "C" {
+
+const char* fwi_last_error(void) { return g_err; }
+int fwi_version(void) { return 100; }
+int fwi_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int fwi_mc_type_components(int t) { return (t < 0 || t > 6) ? FWI_EINVAL : type_components(t); }
+int fwi_mc_type_draws(int t) { return (t < 0 || t > 6) ? FWI_EINVAL : type_draws(t); }
+int fwi_mc_type_rows(int t) { return (t < 0 || t > 6) ? FWI_EINVAL : type_components(t) + (type_combined(t) ? 1 : 0); }
+
+int fwi_mc_create(int device, int K, int C, int T, int n_media, fwi_mc_ctx** out) {
+    FWI_REQUIRE(out != nullptr, "fwi_mc_create: out is NULL");
+    FWI_REQUIRE(K >= 1 && T >= 1, "fwi_mc_create: K and T must be >= 1 (got K=%d T=%d)", K, T);
+    FWI_REQUIRE(C == 3 || C == 6 || C == 9, "fwi_mc_create: C must be 3, 6 or 9 (got %d)", C);
+    FWI_REQUIRE(n_media == 1 || n_media == 2, "fwi_mc_create: n_media must be 1 or 2 (got %d)", n_media);
+    int ndev = 0;
+    FWI_CUDA(cudaGetDeviceCount(&ndev));
+    FWI_REQUIRE(device >= 0 && device < ndev, "fwi_mc_create: device %d out of range (%d visible)", device, ndev);
+    DeviceGuard g(device);
+    auto* c = new fwi_mc_ctx();
+    c->device = device; c->K = K; c->C = C; c->T = T; c->NM = n_media; c->CC = C * n_media; c->RW = row_width(c->CC);
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    FWI_CUDA(cudaMalloc(&c->red_sum, 1024 * sizeof(double)));
+    FWI_CUDA(cudaMalloc(&c->red_max, 1024 * sizeof(float)));
+    FWI_CUDA(cudaMalloc(&c->red_arg, 1024 * sizeof(long long)));
+    *out = c;
+    return FWI_OK;
+}
+
+int fwi_mc_destroy(fwi_mc_ctx* c) {
+    if (!c) return FWI_OK;
+    DeviceGuard g(c->device);
+    free_rowset(c->base); free_rowset(c->hr); free_rowset(c->hrflat);
+    if (c->phase_dev) cudaFree(c->phase_dev);
+    if (c->stage_M) cudaFree(c->stage_M);
+    if (c->stage_sim) cudaFree(c->stage_sim);
+    if (c->stage_frac) cudaFree(c->stage_frac);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    cudaFree(c->red_sum); cudaFree(c->red_max); cudaFree(c->red_arg);
+    delete c;
+    return FWI_OK;
+}
+
+int fwi_mc_upload(fwi_mc_ctx* c, const double* G, const double* d, const int* phase) {
+    FWI_REQUIRE(c && G && d, "fwi_mc_upload: NULL argument");
+    DeviceGuard g(c->device);
+    const size_t nG = (size_t)c->K * c->C * c->T * c->NM, nd = (size_t)c->K * c->T;
+    c->G.assign(G, G + nG);
+    c->d.assign(d, d + nd);
+    free_rowset(c->base); free_rowset(c->hr); free_rowset(c->hrflat);
+    if (c->phase_dev) { cudaFree(c->phase_dev); c->phase_dev = nullptr; }
+    c->phase.clear();
+    if (phase) {
+        for (int k = 0; k < c->K; ++k) FWI_REQUIRE(phase[k] >= 0 && phase[k] <= 2, "fwi_mc_upload: phase_index[%d]=%d not in {0,1,2}", k, phase[k]);
+        c->phase.assign(phase, phase + c->K);
+        FWI_CUDA(cudaMalloc(&c->phase_dev, c->K * sizeof(int)));
+        FWI_CUDA(cudaMemcpy(c->phase_dev, phase, c->K * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    for (int k = 0; k < c->K; ++k) {
+        double mx = 0.0;
+        for (int t = 0; t < c->T; ++t) mx = std::max(mx, std::fabs(d[(size_t)k * c->T + t]));
+        FWI_REQUIRE(std::isfinite(mx), "fwi_mc_upload: non-finite value in data trace %d", k);
+    }
+    int rc = build_rowset(c, c->base, 0);
+    if (rc) return rc;
+    c->uploaded = true;
+    return FWI_OK;
+}
+
+static int check_media(const fwi_mc_ctx* c, const float* frac, int nfrac, const char* who) {
+    if (c->NM == 1) { FWI_REQUIRE(frac == nullptr && nfrac == 0, "%s: media fractions given but the context has one medium", who); }
+    else {
+        FWI_REQUIRE(frac != nullptr && (nfrac == 1 || nfrac == 3), "%s: two-media context needs media_frac with nfrac 1 or 3 (got %d)", who, nfrac);
+        FWI_REQUIRE(nfrac == 1 || c->phase_dev, "%s: nfrac=3 needs phase_index at upload", who);
+    }
+    return FWI_OK;
+}
+
+int fwi_mc_forward(fwi_mc_ctx* c, const float* M, int64_t ldm, int n_comp, const float* frac, int nfrac,
+                   int64_t N, float* traces, void* stream) {
+    FWI_REQUIRE(c && c->uploaded, "fwi_mc_forward: context has no data (call fwi_mc_upload)");
+    FWI_REQUIRE(M && traces && N >= 0 && ldm >= N, "fwi_mc_forward: bad M / traces / N / ldm");
+    FWI_REQUIRE(n_comp >= 0 && n_comp <= c->C, "fwi_mc_forward: n_comp=%d exceeds C=%d", n_comp, c->C);
+    int rc = check_media(c, frac, nfrac, "fwi_mc_forward");
+    if (rc) return rc;
+    if (N == 0) return FWI_OK;
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t KT = (int64_t)c->K * c->T;
+    dim3 grid((unsigned)ceil_div(KT, 128), (unsigned)std::min<int64_t>(N, 4096));
+#define FWD(CV, NMV) mc_forward_kernel<CV, NMV><<<grid, 128, 0, st>>>(c->base.rows, c->phase_dev, M, ldm, n_comp, frac, nfrac, N, c->K, c->T, traces)
+    if (c->NM == 1) { if (c->C == 3) FWD(3, 1); else if (c->C == 6) FWD(6, 1); else FWD(9, 1); }
+    else { if (c->C == 3) FWD(3, 2); else if (c->C == 6) FWD(6, 2); else FWD(9, 2); }
+#undef FWD
+    FWI_CUDA(cudaGetLastError());
+    return FWI_OK;
+}
+
+int fwi_mc_eval(fwi_mc_ctx* c, const float* M, int64_t ldm, const float* frac, int nfrac, int64_t N, int metric,
+                int flags, float* sim, float* like, void* stream) {
+    FWI_REQUIRE(c && c->uploaded, "fwi_mc_eval: context has no data (call fwi_mc_upload)");
+    FWI_REQUIRE(M && sim && N >= 0 && ldm >= N, "fwi_mc_eval: bad M / similarity / N / ldm");
+    FWI_REQUIRE(metric >= 0 && metric <= 4, "fwi_mc_eval: unknown metric %d", metric);
+    int rc = check_media(c, frac, nfrac, "fwi_mc_eval");
+    if (rc) return rc;
+    if (N == 0) return FWI_OK;
+    DeviceGuard g(c->device);
+    const bool norm = flags & FWI_FLAG_NORMALISED, simul = flags & FWI_FLAG_SIMULTANEOUS;
+    if (metric == FWI_METRIC_GAU) {
+        const int tv = simul ? c->K * c->T : c->T;
+        FWI_REQUIRE(tv >= 60, "fwi_mc_eval: 'gau' needs at least 60 samples for its noise window (FWI:580), got %d", tv);
+    }
+    RowSet* rs = &c->base;
+    int boundary_fix = 0;
+    if (metric == FWI_METRIC_CC_SHIFT) {
+        if (simul && !norm) rs = &c->hrflat; else rs = &c->hr;
+        if (!rs->built) { rc = build_rowset(c, *rs, rs == &c->hr ? 1 : 2); if (rc) return rc; }
+        if (simul && norm) {
+            // data constants of the normalised flattened interpolated array come from variant 2
+            if (!c->hrflat.built) { rc = build_rowset(c, c->hrflat, 2); if (rc) return rc; }
+            boundary_fix = 1;
+        }
+    }
+    int mode;
+    if (metric == FWI_METRIC_VR || metric == FWI_METRIC_GAU) mode = norm ? MODE_MOM_MAX : MODE_SSE;
+    else mode = (simul && norm) ? MODE_MOM_MAX : MODE_MOM;
+
+    EvalParams p{};
+    p.rows = rs->rows; p.gbar = rs->gbar; p.tc = rs->tc; p.fc = rs->fc;
+    if (boundary_fix) { p.fc.D1[1] = c->hrflat.fc.D1[1]; p.fc.D2[1] = c->hrflat.fc.D2[1]; }
+    p.phase = c->phase_dev; p.M = M; p.ldm = ldm; p.frac = frac; p.nfrac = nfrac; p.N = N; p.K = c->K; p.Tv = rs->Tv;
+    p.metric = metric; p.flags = flags; p.boundary_fix = boundary_fix; p.sim = sim; p.like = like;
+
+    // samples per lane: 4 when there is enough work to fill the machine twice over, else fewer
+    int S = 4;
+    const int64_t full = (int64_t)c->sm_count * 2 * 128;
+    if (N < full) S = 2;
+    if (N < full / 4) S = 1;
+    while (S > 1 && (size_t)c->K * nstat(mode) * 32 * (c->NM == 1 ? S : std::max(1, S / 2)) * 4 > 200 * 1024) S >>= 1;
+    const int Seff = (c->NM == 1) ? S : std::max(1, S / 2);
+    FWI_REQUIRE((size_t)c->K * nstat(mode) * 32 * Seff * 4 <= 220 * 1024, "fwi_mc_eval: K=%d traces exceed the shared-memory statistics buffer", c->K);
+    const int nw = pick_warps(c->K);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c->NM == 1) {
+        if (c->C == 3) return launch_eval_m<3, 1>(p, mode, S, nw, st);
+        if (c->C == 6) return launch_eval_m<6, 1>(p, mode, S, nw, st);
+        return launch_eval_m<9, 1>(p, mode, S, nw, st);
+    }
+    if (c->C == 3) return launch_eval_m<3, 2>(p, mode, S, nw, st);
+    if (c->C == 6) return launch_eval_m<6, 2>(p, mode, S, nw, st);
+    return launch_eval_m<9, 2>(p, mode, S, nw, st);
+}
+
+int fwi_mc_transform_draws(int type, const float* draws, int64_t ldn, int64_t N, float amp, float* out, int64_t ldo,
+                           void* stream) {
+    FWI_REQUIRE(type >= 0 && type <= 6, "fwi_mc_transform_draws: unknown inversion type %d", type);
+    FWI_REQUIRE(draws && out && N >= 0 && ldn >= N && ldo >= N, "fwi_mc_transform_draws: bad pointers / sizes");
+    if (N == 0) return FWI_OK;
+    mc_transform_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(type, draws, ldn, N, amp, out, ldo);
+    FWI_CUDA(cudaGetLastError());
+    return FWI_OK;
+}
+
+int fwi_mc_reduce(const float* L, int64_t N, double* sum_host, int64_t* argmax_host, float* max_host, void* stream) {
+    FWI_REQUIRE(L && N >= 1, "fwi_mc_reduce: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = (int)std::min<int64_t>(1024, ceil_div(N, 1024));
+    double* psum; float* pmax; long long* parg;
+    FWI_CUDA(cudaMallocAsync(&psum, blocks * sizeof(double), st));
+    FWI_CUDA(cudaMallocAsync(&pmax, blocks * sizeof(float), st));
+    FWI_CUDA(cudaMallocAsync(&parg, blocks * sizeof(long long), st));
+    mc_reduce_kernel<<<blocks, 256, 0, st>>>(L, N, psum, pmax, parg);
+    FWI_CUDA(cudaGetLastError());
+    std::vector<double> hs(blocks); std::vector<float> hm(blocks); std::vector<long long> ha(blocks);
+    FWI_CUDA(cudaMemcpyAsync(hs.data(), psum, blocks * sizeof(double), cudaMemcpyDeviceToHost, st));
+    FWI_CUDA(cudaMemcpyAsync(hm.data(), pmax, blocks * sizeof(float), cudaMemcpyDeviceToHost, st));
+    FWI_CUDA(cudaMemcpyAsync(ha.data(), parg, blocks * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    FWI_CUDA(cudaFreeAsync(psum, st)); FWI_CUDA(cudaFreeAsync(pmax, st)); FWI_CUDA(cudaFreeAsync(parg, st));
+    FWI_CUDA(cudaStreamSynchronize(st));
+    double s = 0.0; float mx = -INFINITY; long long am = -1;
+    for (int b = 0; b < blocks; ++b) {
+        s += hs[b];
+        if (hm[b] > mx || (hm[b] == mx && ha[b] >= 0 && (am < 0 || ha[b] < am))) { mx = hm[b]; am = ha[b]; }
+    }
+    if (sum_host) *sum_host = s;
+    if (argmax_host) *argmax_host = am;
+    if (max_host) *max_host = mx;
+    return FWI_OK;
+}
+
+int fwi_mc_sample_eval(fwi_mc_ctx* c, int type, uint64_t seed, int64_t first, int64_t N, float amp, int metric, int flags,
+                       int nfrac, float* MTs, int64_t ldn, float* sim, float* L, double* sumL, int64_t* argmax,
+                       float* maxL, void* stream) {
+    FWI_REQUIRE(c && c->uploaded, "fwi_mc_sample_eval: context has no data (call fwi_mc_upload)");
+    FWI_REQUIRE(type >= 0 && type <= 6, "fwi_mc_sample_eval: unknown inversion type %d", type);
+    FWI_REQUIRE(type_components(type) == c->C, "fwi_mc_sample_eval: inversion type %d produces %d components but the Green's functions have %d", type, type_components(type), c->C);
+    FWI_REQUIRE(MTs && sim && L && N >= 0 && ldn >= N && first >= 0, "fwi_mc_sample_eval: bad pointers / sizes");
+    FWI_REQUIRE((c->NM == 1 && nfrac == 0) || (c->NM == 2 && (nfrac == 1 || nfrac == 3)), "fwi_mc_sample_eval: nfrac=%d inconsistent with n_media=%d", nfrac, c->NM);
+    if (N == 0) { if (sumL) *sumL = 0.0; if (argmax) *argmax = -1; if (maxL) *maxL = 0.f; return FWI_OK; }
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    mc_sample_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, st>>>(type, seed, first, N, amp, nfrac, MTs, ldn);
+    FWI_CUDA(cudaGetLastError());
+    const int rows = type_components(type) + (type_combined(type) ? 1 : 0);
+    const float* frac = nfrac ? MTs + (int64_t)rows * ldn : nullptr;
+    int rc = fwi_mc_eval(c, MTs, ldn, frac, nfrac, N, metric, flags, sim, L, stream);
+    if (rc) return rc;
+    if (sumL || argmax || maxL) return fwi_mc_reduce(L, N, sumL, argmax, maxL, stream);
+    return FWI_OK;
+}
+
+int fwi_mc_normalise(const float* L, int64_t N, double sumL, float* MTp, void* stream) {
+    FWI_REQUIRE(L && MTp && N >= 0, "fwi_mc_normalise: bad arguments");
+    if (!(sumL > 0.0)) { set_error("fwi_mc_normalise: sum of likelihoods is %g - no adequate solution (FWI:1206-1208)", sumL); return FWI_EZEROPROB; }
+    if (N == 0) return FWI_OK;
+    // MTp = L * p_model / p_data with p_model = 1/N and p_data = sum(p_model * L)  ==  L / sum(L)
+    mc_normalise_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(L, N, 1.0 / sumL, MTp);
+    FWI_CUDA(cudaGetLastError());
+    return FWI_OK;
+}
+
+__global__ void mc_stage_kernel(const double* __restrict__ Mh, int64_t N, int C, int n_comp, float* __restrict__ M) {
+    // (N, n_comp) float64 sample-major -> (C, N) fp32, missing trailing components zero (FWI:262)
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * C) return;
+    const int c = (int)(i / N);
+    const int64_t n = i % N;
+    M[i] = (c < n_comp) ? (float)Mh[n * n_comp + c] : 0.f;
+}
+__global__ void mc_unstage_kernel(const float* __restrict__ s, int64_t N, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) out[i] = (double)s[i];
+}
+
+int fwi_mc_eval_host(fwi_mc_ctx* c, const double* M_host, int64_t N, int n_comp, const double* frac_host, int nfrac,
+                     int metric, int flags, double* sim_host) {
+    FWI_REQUIRE(c && c->uploaded, "fwi_mc_eval_host: context has no data (call fwi_mc_upload)");
+    FWI_REQUIRE(M_host && sim_host && N >= 1, "fwi_mc_eval_host: bad arguments");
+    FWI_REQUIRE(n_comp >= 1 && n_comp <= c->C, "fwi_mc_eval_host: n_comp=%d exceeds C=%d", n_comp, c->C);
+    DeviceGuard g(c->device);
+    if (c->stage_cap < N) {
+        if (c->stage_M) cudaFree(c->stage_M);
+        if (c->stage_sim) cudaFree(c->stage_sim);
+        if (c->stage_frac) cudaFree(c->stage_frac);
+        c->stage_M = c->stage_sim = c->stage_frac = nullptr;
+        FWI_CUDA(cudaMalloc(&c->stage_M, (size_t)N * c->C * sizeof(float)));
+        FWI_CUDA(cudaMalloc(&c->stage_sim, (size_t)N * sizeof(float)));
+        FWI_CUDA(cudaMalloc(&c->stage_frac, (size_t)N * 3 * sizeof(float)));
+        c->stage_cap = N;
+    }
+    const int64_t need = (int64_t)N * (n_comp + 3) * sizeof(double);
+    double* dbuf = nullptr;
+    FWI_CUDA(cudaMalloc(&dbuf, (size_t)need));
+    int rc = FWI_OK;
+    do {
+        if (cudaMemcpy(dbuf, M_host, (size_t)N * n_comp * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { rc = FWI_ECUDA; break; }
+        mc_stage_kernel<<<(unsigned)ceil_div(N * c->C, 256), 256>>>(dbuf, N, c->C, n_comp, c->stage_M);
+        const float* frac = nullptr;
+        if (frac_host && nfrac > 0) {
+            double* fb = dbuf + (size_t)N * n_comp;
+            if (cudaMemcpy(fb, frac_host, (size_t)N * nfrac * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { rc = FWI_ECUDA; break; }
+            mc_stage_kernel<<<(unsigned)ceil_div(N * nfrac, 256), 256>>>(fb, N, nfrac, nfrac, c->stage_frac);
+            frac = c->stage_frac;
+        }
+        rc = fwi_mc_eval(c, c->stage_M, N, frac, frac ? nfrac : 0, N, metric, flags, c->stage_sim, nullptr, nullptr);
+        if (rc) break;
+        mc_unstage_kernel<<<(unsigned)ceil_div(N, 256), 256>>>(c->stage_sim, N, dbuf);
+        if (cudaMemcpy(sim_host, dbuf, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = FWI_ECUDA; break; }
+    } while (0);
+    cudaFree(dbuf);
+    if (rc == FWI_ECUDA) set_error("fwi_mc_eval_host: CUDA copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,410 @@
+"""Drop-in mirror of the reference module ``full_waveform_inversion.py`` for its hot path.
+
+Same function names, positional order, defaults and return shapes as the reference
+(cited FWI:<line>; UNP = unnormallised_probability_retrieval_from_full_waveform_soln.py), but the
+work runs in hand-written sm_100a CUDA behind the C ABI of include/fwi_b200.h.  NumPy float64
+arrays in, NumPy float64 arrays out; torch tensors are only the device-buffer carrier.
+
+Differences a user can see:
+  q1  per-trace 'gau' returns the intended mean; pass ``strict_reference=True`` to get the reference's 0.
+  q2  the single-ratio two-media path works past the first sample.
+  q3  ``num_samples`` not divisible by ``num_processors``: the remainder is distributed, not dropped.
+  q4  random streams are counter based (Philox keyed by the global sample index): no duplicated
+      samples across workers and results independent of the GPU count.
+  q9  a zero likelihood sum raises ZeroProbabilityError instead of print + sys.exit().
+``num_processors`` means "number of GPUs".
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_double, c_float, c_int64, c_void_p
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FwiError, ZeroProbabilityError, check, current_stream, ptr  # noqa: F401
+
+INVERSION_TYPES = ("full_mt", "DC", "single_force", "DC_single_force_couple", "DC_single_force_no_coupling",
+                   "DC_crack_couple", "single_force_crack_no_coupling")          # FWI:52
+METRICS = ("VR", "CC", "PCC", "CC-shift", "gau")                                  # FWI:56
+_COMBINED = INVERSION_TYPES[3:]                                                   # FWI:797
+_PHASES = ("P", "S", "surface")                                                   # FWI:719-721
+FLAG_NORMALISED, FLAG_SIMULTANEOUS, FLAG_STRICT_REF = 1, 2, 4
+
+
+def _metric_id(comparison_metric):
+    try:
+        return METRICS.index(comparison_metric)
+    except ValueError:
+        raise ValueError("comparison_metric must be one of %s, got %r" % (METRICS, comparison_metric))
+
+
+def _type_id(inversion_type):
+    try:
+        return INVERSION_TYPES.index(inversion_type)
+    except ValueError:
+        raise ValueError("inversion_type must be one of %s, got %r" % (INVERSION_TYPES, inversion_type))
+
+
+def _flags(norm, simul, strict=False):
+    return (FLAG_NORMALISED if norm else 0) | (FLAG_SIMULTANEOUS if simul else 0) | (FLAG_STRICT_REF if strict else 0)
+
+
+class SourceInversion:
+    """Device-resident problem: Green's functions + data on one GPU (wraps ``fwi_mc_ctx``)."""
+
+    def __init__(self, real_data_array, green_func_array, green_func_phase_labels=(), device=0):
+        lib = _lib.require_gpu()
+        d = np.ascontiguousarray(real_data_array, dtype=np.float64)
+        G = np.ascontiguousarray(green_func_array, dtype=np.float64)
+        if d.ndim != 2 or G.ndim not in (3, 4):
+            raise ValueError("real_data_array must be (K,T) and green_func_array (K,C,T) or (K,C,T,2)")
+        if G.shape[0] != d.shape[0] or G.shape[2] != d.shape[1]:
+            raise ValueError("green_func_array %s does not match real_data_array %s" % (G.shape, d.shape))
+        self.K, self.C, self.T = G.shape[:3]
+        self.n_media = 1 if G.ndim == 3 else G.shape[3]
+        self.device = int(device)
+        phase = None
+        if len(green_func_phase_labels) > 0:
+            if len(green_func_phase_labels) != self.K:
+                raise ValueError("green_func_phase_labels must have one entry per trace (FWI:1044-1047)")
+            phase = np.array([_PHASES.index(x) for x in green_func_phase_labels], dtype=np.int32)
+        self._h = c_void_p()
+        check(lib.fwi_mc_create(self.device, self.K, self.C, self.T, self.n_media, ctypes.byref(self._h)))
+        check(lib.fwi_mc_upload(self._h, G.ctypes.data_as(c_void_p), d.ctypes.data_as(c_void_p),
+                                None if phase is None else phase.ctypes.data_as(c_void_p)))
+        self.has_phase = phase is not None
+        self._lib = lib
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.fwi_mc_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def torch_device(self):
+        return torch.device("cuda", self.device)
+
+    # ---- device-level calls (tensors are (rows, N) fp32, the reference's MTs layout) ----------
+    def _frac_arg(self, frac_dev):
+        if frac_dev is None:
+            return None, 0
+        return ptr(frac_dev), int(frac_dev.shape[0])
+
+    def forward_dev(self, M_dev, n_comp=None, frac_dev=None):
+        N = M_dev.shape[1]
+        out = torch.empty((N, self.K, self.T), dtype=torch.float32, device=self.torch_device)
+        fp, nf = self._frac_arg(frac_dev)
+        with torch.cuda.device(self.device):
+            check(self._lib.fwi_mc_forward(self._h, ptr(M_dev), M_dev.stride(0), self.C if n_comp is None else n_comp,
+                                           fp, nf, N, ptr(out), current_stream()))
+        return out
+
+    def eval_dev(self, M_dev, metric, flags, frac_dev=None, want_likelihood=False):
+        N = M_dev.shape[1]
+        sim = torch.empty(N, dtype=torch.float32, device=self.torch_device)
+        like = torch.empty(N, dtype=torch.float32, device=self.torch_device) if want_likelihood else None
+        fp, nf = self._frac_arg(frac_dev)
+        with torch.cuda.device(self.device):
+            check(self._lib.fwi_mc_eval(self._h, ptr(M_dev), M_dev.stride(0), fp, nf, N, metric, flags,
+                                        ptr(sim), ptr(like), current_stream()))
+        return (sim, like) if want_likelihood else sim
+
+    def sample_eval_dev(self, type_id, seed, first, N, amplitude, metric, flags, nfrac=0, reduce=True):
+        rows = self._lib.fwi_mc_type_rows(type_id) + nfrac
+        dev = self.torch_device
+        MTs = torch.empty((rows, N), dtype=torch.float32, device=dev)
+        sim = torch.empty(N, dtype=torch.float32, device=dev)
+        L = torch.empty(N, dtype=torch.float32, device=dev)
+        s, a, m = c_double(0.0), c_int64(-1), c_float(0.0)
+        with torch.cuda.device(self.device):
+            check(self._lib.fwi_mc_sample_eval(self._h, type_id, seed, first, N, amplitude, metric, flags, nfrac,
+                                               ptr(MTs), N, ptr(sim), ptr(L),
+                                               ctypes.byref(s) if reduce else None,
+                                               ctypes.byref(a) if reduce else None,
+                                               ctypes.byref(m) if reduce else None, current_stream()))
+        return MTs, sim, L, (s.value, a.value, m.value)
+
+    # ---- host-array conveniences ----------------------------------------------------------------
+    def similarity(self, M, comparison_metric, perform_normallised_waveform_inversion=True,
+                   compare_all_waveforms_simultaneously=True, media_frac=None, strict_reference=False):
+        """Similarity of each source vector in M ((C,), (C,1) or (N,C)) -> float64 (N,).  Host in, host out
+        through ``fwi_mc_eval_host`` (copies inside the call)."""
+        M = np.asarray(M, dtype=np.float64)
+        if M.ndim == 1 or (M.ndim == 2 and M.shape[1] == 1):
+            M = M.reshape(1, -1)                      # one source vector, (C,) or the reference's (C,1)
+        M = np.ascontiguousarray(M)
+        N, nc = M.shape
+        out = np.empty(N, dtype=np.float64)
+        fr, nf = None, 0
+        if media_frac is not None:
+            fr = np.ascontiguousarray(np.asarray(media_frac, dtype=np.float64).reshape(N, -1))
+            nf = fr.shape[1]
+        check(self._lib.fwi_mc_eval_host(self._h, M.ctypes.data_as(c_void_p), N, nc,
+                                         None if fr is None else fr.ctypes.data_as(c_void_p), nf,
+                                         _metric_id(comparison_metric),
+                                         _flags(perform_normallised_waveform_inversion,
+                                                compare_all_waveforms_simultaneously, strict_reference),
+                                         out.ctypes.data_as(c_void_p)))
+        return out
+
+
+def _as_M_dev(M, C, device):
+    """(C,), (C,1), (n<C,...) host vector -> (C,1) fp32 device tensor, returning n_comp (FWI:262)."""
+    m = np.asarray(M, dtype=np.float64)
+    m = m.reshape(len(m), -1)[:, 0]
+    if len(m) > C:
+        raise IndexError("M has %d components but the Green's functions only %d (FWI:263)" % (len(m), C))
+    buf = np.zeros((C, 1), dtype=np.float32)
+    buf[: len(m), 0] = m
+    return torch.from_numpy(buf).to(device), len(m)
+
+
+# ------------------------------------------------------------------------------------------------ reference names
+def forward_model(green_func_array, M):
+    """synth[k,t] = sum_c G[k,c,t] M[c] -> (K,T) float64                    (FWI:253-264)"""
+    G = np.asarray(green_func_array, dtype=np.float64)
+    prob = SourceInversion(np.zeros((G.shape[0], G.shape[2])), G)
+    try:
+        M_dev, n_comp = _as_M_dev(M, prob.C, prob.torch_device)
+        out = prob.forward_dev(M_dev, n_comp=n_comp)
+        return out[0].double().cpu().numpy()
+    finally:
+        prob.close()
+
+
+def compare_synth_to_real_waveforms(real_data_array, synth_waveforms_array, comparison_metric,
+                                    perform_normallised_waveform_inversion=True,
+                                    compare_all_waveforms_simultaneously=True, strict_reference=False):
+    """Similarity of one synthetic array to the data -> float              (FWI:584-684)
+
+    The synthetic is presented to the device path as a one-component Green's function with M = 1.
+    """
+    d = np.asarray(real_data_array, dtype=np.float64)
+    s = np.asarray(synth_waveforms_array, dtype=np.float64)
+    if d.shape != s.shape or d.ndim != 2:
+        raise ValueError("real and synthetic arrays must both be (K,T); got %s and %s" % (d.shape, s.shape))
+    G = np.zeros((d.shape[0], 3, d.shape[1]))
+    G[:, 0, :] = s
+    prob = SourceInversion(d, G)
+    try:
+        return float(prob.similarity(np.array([[1.0, 0.0, 0.0]]), comparison_metric,
+                                     perform_normallised_waveform_inversion,
+                                     compare_all_waveforms_simultaneously, strict_reference=strict_reference)[0])
+    finally:
+        prob.close()
+
+
+def get_unnormallised_prob_for_specific_soln(real_data_array, green_func_array, MT_specific_soln, comparison_metric,
+                                             perform_normallised_waveform_inversion=True,
+                                             compare_all_waveforms_simultaneously=True):
+    """forward_model + compare for one solution; returns the raw similarity   (UNP:222-232)"""
+    prob = SourceInversion(real_data_array, green_func_array)
+    try:
+        m = np.asarray(MT_specific_soln, dtype=np.float64)
+        m = m.reshape(len(m), -1)[:, 0]
+        return float(prob.similarity(m[None, :], comparison_metric, perform_normallised_waveform_inversion,
+                                     compare_all_waveforms_simultaneously)[0])
+    finally:
+        prob.close()
+
+
+def perform_inversion(real_data_array, green_func_array):
+    """Stacked least squares for the amplitude scale -> (C,1)                 (FWI:242-250)
+
+    Runs once per inversion on a (K*T) x C system; stays on the host."""
+    d = np.asarray(real_data_array, dtype=np.float64)
+    G = np.asarray(green_func_array, dtype=np.float64)
+    A = G.transpose(0, 2, 1).reshape(-1, G.shape[1])
+    m, *_ = np.linalg.lstsq(A, d.reshape(-1, 1), rcond=None)
+    return m
+
+
+def _shard(num_samples, parts):
+    """Contiguous index ranges, remainder spread over the first ranks (q3; order of FWI:833-834)."""
+    base, rem = divmod(int(num_samples), int(parts))
+    out, start = [], 0
+    for r in range(parts):
+        n = base + (1 if r < rem else 0)
+        out.append((start, n))
+        start += n
+    return out
+
+
+def perform_monte_carlo_sampled_waveform_inversion(real_data_array, green_func_array, num_samples=1000, M_amplitude=1.,
+                                                   inversion_type="full_mt", comparison_metric="CC",
+                                                   perform_normallised_waveform_inversion=True,
+                                                   compare_all_waveforms_simultaneously=True, num_processors=1,
+                                                   return_absolute_similarity_values_switch=False,
+                                                   invert_for_ratio_of_multiple_media_greens_func_switch=False,
+                                                   green_func_phase_labels=[], num_phase_types_for_media_ratios=0,
+                                                   seed=0, strict_reference=False, return_device_tensors=False):
+    """Monte-Carlo sampling of the source -> (MTs, MTp, MTp_absolute)        (FWI:786-870)
+
+    Row order of MTs as in the reference: C source rows, amp-frac row for combined types
+    (FWI:851-852), media-ratio row(s) (FWI:853-862).  Work is sharded in contiguous sample ranges
+    over ``num_processors`` GPUs of this process, or - when torch.distributed is initialised -
+    over the ranks of the default group (one GPU per rank, sum of L all-reduced over NCCL).
+    """
+    type_id = _type_id(inversion_type)
+    metric = _metric_id(comparison_metric)
+    flags = _flags(perform_normallised_waveform_inversion, compare_all_waveforms_simultaneously, strict_reference)
+    G = np.asarray(green_func_array, dtype=np.float64)
+    media = bool(invert_for_ratio_of_multiple_media_greens_func_switch)
+    if media and G.ndim != 4:
+        raise ValueError("two-media inversion needs green_func_array of shape (K,C,T,2) (FWI:133)")
+    if not media and G.ndim != 3:
+        raise ValueError("green_func_array must be (K,C,T)")
+    nfrac = (3 if num_phase_types_for_media_ratios > 0 else 1) if media else 0
+    labels = green_func_phase_labels if nfrac == 3 else ()
+    N = int(num_samples)
+    if N < 1:
+        raise ValueError("num_samples must be >= 1")
+
+    import torch.distributed as dist
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if distributed:
+        world, rank = dist.get_world_size(), dist.get_rank()
+        dev = torch.cuda.current_device()
+        first, n_loc = _shard(N, world)[rank]
+        prob = SourceInversion(real_data_array, G, labels, device=dev)
+        try:
+            MTs, sim, L, (sumL, _, _) = prob.sample_eval_dev(type_id, seed, first, n_loc, float(M_amplitude), metric,
+                                                             flags, nfrac)
+            tot = torch.tensor([sumL], dtype=torch.float64, device=prob.torch_device)
+            dist.all_reduce(tot)                                                  # p_data = sum over all ranks (FWI:847)
+            sumL = float(tot.item())
+            counts = [n for _, n in _shard(N, world)]
+            nmax = max(counts)
+            pad = torch.zeros((MTs.shape[0] + 1, nmax), dtype=torch.float32, device=prob.torch_device)
+            pad[:-1, :n_loc] = MTs
+            pad[-1, :n_loc] = L
+            gathered = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(gathered, pad)
+            MTs = torch.cat([g[:-1, :c] for g, c in zip(gathered, counts)], dim=1)
+            L = torch.cat([g[-1, :c] for g, c in zip(gathered, counts)])
+        finally:
+            prob.close()
+    else:
+        ndev = max(1, min(int(num_processors), torch.cuda.device_count()))
+        parts = _shard(N, ndev)
+        probs, outs = [], []
+        try:
+            for dev, (first, n_loc) in enumerate(parts):
+                prob = SourceInversion(real_data_array, G, labels, device=dev)
+                probs.append(prob)
+                outs.append(prob.sample_eval_dev(type_id, seed, first, n_loc, float(M_amplitude), metric, flags, nfrac,
+                                                 reduce=False))
+            MTs = torch.cat([o[0].to("cuda:0") for o in outs], dim=1)
+            L = torch.cat([o[2].to("cuda:0") for o in outs])
+        finally:
+            for prob in probs:
+                prob.close()
+        lib = _lib.load()
+        s, a, m = c_double(0.0), c_int64(-1), c_float(0.0)
+        with torch.cuda.device(L.device):
+            check(lib.fwi_mc_reduce(ptr(L), N, ctypes.byref(s), ctypes.byref(a), ctypes.byref(m), current_stream()))
+        sumL = s.value
+
+    lib = _lib.load()
+    MTp = torch.empty_like(L)
+    with torch.cuda.device(L.device):
+        check(lib.fwi_mc_normalise(ptr(L), N, sumL, ptr(MTp), current_stream()))       # FWI:847-848
+    if return_device_tensors:
+        return MTs, MTp, (L if return_absolute_similarity_values_switch else [])
+    MTs_h = MTs.double().cpu().numpy()
+    MTp_h = MTp.double().cpu().numpy()
+    MTp_abs = L.double().cpu().numpy() if return_absolute_similarity_values_switch else []   # FWI:865-868
+    return MTs_h, MTp_h, MTp_abs
+
+
+def _one_sample(type_id, seed):
+    lib = _lib.require_gpu()
+    rows = lib.fwi_mc_type_rows(type_id)
+    nd = lib.fwi_mc_type_draws(type_id)
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    pat = ("nnnnnn", "nnn", "nnn", "nnnr", "nnnnnnr", "urrrnnn", "nnnurrnnnr")[type_id]
+    draws = torch.empty((nd, 1), dtype=torch.float32)
+    for j, ch in enumerate(pat):
+        draws[j, 0] = torch.randn(1, generator=g).item() if ch == "n" else \
+            (torch.rand(1, generator=g).item() * 2 - 1 if ch == "u" else torch.rand(1, generator=g).item())
+    return transform_draws(INVERSION_TYPES[type_id], draws.numpy().T)[0], rows
+
+
+def transform_draws(inversion_type, draws, amplitude=1.0):
+    """Raw draws (N, n_draws) in the reference's consumption order -> (N, rows) float64: the deterministic
+    arithmetic of the seven generators (FWI:282-510) evaluated on the GPU."""
+    lib = _lib.require_gpu()
+    type_id = _type_id(inversion_type)
+    q = np.ascontiguousarray(np.asarray(draws, dtype=np.float32).T)                # (n_draws, N)
+    if q.shape[0] != lib.fwi_mc_type_draws(type_id):
+        raise ValueError("%s consumes %d draws per sample, got %d" % (inversion_type, lib.fwi_mc_type_draws(type_id), q.shape[0]))
+    N = q.shape[1]
+    qd = torch.from_numpy(q).cuda()
+    out = torch.empty((lib.fwi_mc_type_rows(type_id), N), dtype=torch.float32, device="cuda")
+    check(lib.fwi_mc_transform_draws(type_id, ptr(qd), N, N, float(amplitude), ptr(out), N, current_stream()))
+    return out.double().cpu().numpy().T
+
+
+_draw_counter = [0]
+
+
+def _gen(type_id):
+    _draw_counter[0] += 1
+    v, rows = _one_sample(type_id, 0x5EED0000 + _draw_counter[0])
+    nc = _lib.load().fwi_mc_type_components(type_id)
+    tensor = v[:nc].reshape(nc, 1)
+    return (tensor, float(v[nc])) if rows > nc else tensor
+
+
+def generate_random_MT():                                   # FWI:282-293
+    return _gen(0)
+
+
+def generate_random_DC_MT():                                # FWI:295-317
+    return _gen(1)
+
+
+def generate_random_single_force_vector():                  # FWI:320-331
+    return _gen(2)
+
+
+def generate_random_DC_single_force_coupled_tensor():       # FWI:333-367
+    return _gen(3)
+
+
+def generate_random_DC_single_force_uncoupled_tensor():     # FWI:369-382
+    return _gen(4)
+
+
+def generate_random_DC_crack_coupled_tensor():              # FWI:384-446
+    return _gen(5)
+
+
+def generate_random_single_force_crack_uncoupled_tensor():  # FWI:448-510
+    return _gen(6)
+
+
+def get_synth_forward_model_most_likely_result(MTs, MTp, green_func_array, inversion_type,
+                                               invert_for_ratio_of_multiple_media_greens_func_switch=False,
+                                               green_func_phase_labels=[], num_phase_types_for_media_ratios=0):
+    """Re-synthesise the most likely sample (FWI:974-1020): argmax of MTp, strip the appended rows, re-mix the
+    two media with that sample's ratio(s), forward model."""
+    MTs = np.asarray(MTs, dtype=np.float64)
+    j = int(np.argmax(MTp))
+    C = int(np.asarray(green_func_array).shape[1])
+    col = MTs[:, j]
+    G = np.asarray(green_func_array, dtype=np.float64)
+    if invert_for_ratio_of_multiple_media_greens_func_switch:
+        if num_phase_types_for_media_ratios > 0:
+            fr = col[-3:]
+            idx = np.array([_PHASES.index(x) for x in green_func_phase_labels])
+            f = fr[idx][:, None, None]
+        else:
+            f = col[-1]
+        G = (1.0 - f) * G[..., 0] + f * G[..., 1]
+    return forward_model(G, col[:C])

@@ -1,0 +1,90 @@
+"""Keeps the Track B self-oracle honest (the reference has no propagator to pin it to):
+the adjoint-state gradient must equal finite differences of the misfit, and the stencil must
+propagate at the model velocity."""
+import numpy as np
+import pytest
+
+from oracle import fd_oracle as fo
+
+
+def _small_problem(ndim=2):
+    rng = np.random.default_rng(0)
+    shape = (26, 30) if ndim == 2 else (14, 13, 15)
+    v = 2000.0 + 300.0 * rng.random(shape)
+    h = 10.0
+    dt = fo.stable_dt(v.max(), h, ndim)
+    if ndim == 2:
+        src = [(5, 7), (6, 20)]
+        rec = [(4, x) for x in range(3, 28, 3)] + [(20, 15)]
+    else:
+        src = [(4, 5, 6)]
+        rec = [(3, 6, x) for x in range(2, 14, 2)]
+    nt = 60
+    wav = np.stack([fo.ricker(nt, dt, 25.0), 0.5 * fo.ricker(nt, dt, 18.0)], 1)[:, : len(src)]
+    return v, h, dt, src, rec, wav
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_gradient_matches_finite_differences(ndim):
+    v, h, dt, src, rec, wav = _small_problem(ndim)
+    true = fo.Problem(v * 1.03, h, dt, src, rec, nabs=5, alpha=0.3)
+    obs = true.forward(wav)
+    p = fo.Problem(v, h, dt, src, rec, nabs=5, alpha=0.3)
+    J, grad, _ = p.misfit_and_gradient(wav, obs)
+    rng = np.random.default_rng(1)
+    pts = [tuple(rng.integers(0, n) for n in v.shape) for _ in range(6)] + [src[0], rec[0]]
+    for pt in pts:
+        eps = 1e-3
+        vp, vm = v.copy(), v.copy()
+        vp[pt] += eps
+        vm[pt] -= eps
+        Jp = fo.misfit(fo.Problem(vp, h, dt, src, rec, nabs=5, alpha=0.3).forward(wav), obs)
+        Jm = fo.misfit(fo.Problem(vm, h, dt, src, rec, nabs=5, alpha=0.3).forward(wav), obs)
+        fd = (Jp - Jm) / (2 * eps)
+        assert abs(fd - grad[pt]) <= 1e-6 * max(abs(fd), np.abs(grad).max() * 1e-3), (pt, fd, grad[pt])
+
+
+def test_directional_derivative():
+    v, h, dt, src, rec, wav = _small_problem(2)
+    obs = fo.Problem(v * 0.97, h, dt, src, rec, nabs=5).forward(wav)
+    J, grad, _ = fo.Problem(v, h, dt, src, rec, nabs=5).misfit_and_gradient(wav, obs)
+    dv = np.random.default_rng(3).standard_normal(v.shape)
+    eps = 1e-4
+    Jp = fo.misfit(fo.Problem(v + eps * dv, h, dt, src, rec, nabs=5).forward(wav), obs)
+    Jm = fo.misfit(fo.Problem(v - eps * dv, h, dt, src, rec, nabs=5).forward(wav), obs)
+    assert abs((Jp - Jm) / (2 * eps) - float(np.sum(grad * dv))) <= 1e-7 * abs(float(np.sum(grad * dv)))
+
+
+def test_arrival_time_in_homogeneous_medium():
+    n, h, v0, f0 = 121, 10.0, 2000.0, 20.0
+    v = np.full((n, n), v0)
+    dt = fo.stable_dt(v0, h, 2)
+    nt = 260
+    p = fo.Problem(v, h, dt, [(60, 30)], [(60, 90)], nabs=20)
+    tr = p.forward(fo.ricker(nt, dt, f0)[:, None])[:, 0]
+    t_peak = np.argmax(np.abs(tr)) * dt
+    expect = 600.0 / v0 + 1.2 / f0
+    assert abs(t_peak - expect) < 0.02          # 2-D far-field phase shift moves the peak slightly
+
+
+def test_sponge_absorbs_and_is_stable():
+    v = np.full((80, 80), 2500.0)
+    dt = fo.stable_dt(2500.0, 10.0, 2)
+    p = fo.Problem(v, 10.0, dt, [(40, 40)], [(40, 41)], nabs=20)
+    tr, ws, (cur, old) = p.forward(fo.ricker(900, dt, 20.0)[:, None], save=False, return_state=True)
+    assert np.isfinite(cur).all()
+    assert np.abs(cur).max() < 0.02 * np.abs(tr).max()
+
+
+def test_update_and_fwi_reduce_misfit():
+    v_true = fo.layered_model((30, 40), 1800.0, 2600.0, 3)
+    v0 = np.full_like(v_true, 2100.0)
+    h = 10.0
+    dt = fo.stable_dt(v_true.max(), h, 2)
+    nt = 120
+    wav = fo.ricker(nt, dt, 20.0)[:, None]
+    shots = [([(3, sx)], [(3, x) for x in range(2, 38, 2)]) for sx in (8, 30)]
+    observed = [fo.Problem(v_true, h, dt, s, r, nabs=6).forward(wav) for s, r in shots]
+    v1, hist = fo.fwi(v0, h, dt, shots, wav, observed, 3, 1500.0, 3000.0, nabs=6)
+    assert hist[-1] < hist[0]
+    assert v1.min() >= 1500.0 and v1.max() <= 3000.0
