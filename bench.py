@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--nt", type=int, default=5000)
     ap.add_argument("--grid", default="1000x3000")
     ap.add_argument("--tile", default="")
+    ap.add_argument("--stream", default="")
     ap.add_argument("--no-track-a", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -226,7 +227,8 @@ def run_b200(args):
     w = workload(args)
     nz, nx, nt = w["nz"], w["nx"], w["nt"]
     tile = tuple(int(x) for x in args.tile.split(",")) if args.tile else None
-    prop = ac.Propagator2D((nz, nx), w["h"], w["dt"], nabs=w["nabs"], alpha=w["alpha"], device=local, tile=tile)
+    stream = tuple(int(x) for x in args.stream.split(",")) if args.stream else None
+    prop = ac.Propagator2D((nz, nx), w["h"], w["dt"], nabs=w["nabs"], alpha=w["alpha"], device=local, tile=tile, stream=stream)
     v_dev = torch.from_numpy(w["v"]).to(dev)
     prop.set_model(v_dev)
     wav_dev = torch.from_numpy(w["wav"]).to(dev)
@@ -322,7 +324,7 @@ def run_b200(args):
                     "misfit_last_step": J_last},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "kernel": "fd2d_step_kernel (forward-save and adjoint-image variants, averaged)",
+                         "kernel": "fd2d_stream_kernel (forward-save and adjoint-image variants, averaged)" if not tile else "fd2d_step_kernel (tiled; forward-save and adjoint-image variants, averaged)",
                          "algorithmic_bytes_per_launch": 16 * nz * nx,
                          "avg_launch_us": avg_launch_s * 1e6,
                          "note": "16 B per point-update (SURVEY 8d) over the mean step-kernel time incl. launch gaps; the snapshot stream adds 4 B/pt of real HBM traffic per step on top"},

@@ -27,6 +27,7 @@ _lib.register({
     "fwi_fd2d_create": (c_int, [c_int, c_int, c_int, c_float, c_float, c_int, c_float, POINTER(c_void_p)]),
     "fwi_fd2d_destroy": (c_int, [c_void_p]),
     "fwi_fd2d_set_tile": (c_int, [c_void_p, c_int, c_int]),
+    "fwi_fd2d_set_stream": (c_int, [c_void_p, c_int, c_int]),
     "fwi_fd2d_set_memory_limit": (c_int, [c_void_p, c_uint64]),
     "fwi_fd2d_set_model": (c_int, [c_void_p, c_void_p, c_void_p]),
     "fwi_fd2d_set_geometry": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
@@ -71,7 +72,7 @@ class Propagator2D:
 
     ndim = 2
 
-    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=0, tile=None, memory_limit=0):
+    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=0, tile=None, memory_limit=0, stream=None):
         self._lib = _lib.require_gpu()
         self.nz, self.nx = int(shape[0]), int(shape[1])
         self.h, self.dt = float(h), float(dt)
@@ -81,6 +82,8 @@ class Propagator2D:
                                         ctypes.byref(self._h)))
         if tile is not None:
             check(self._lib.fwi_fd2d_set_tile(self._h, int(tile[0]), int(tile[1])))
+        if stream is not None:
+            check(self._lib.fwi_fd2d_set_stream(self._h, int(stream[0]), int(stream[1])))
         if memory_limit:
             check(self._lib.fwi_fd2d_set_memory_limit(self._h, int(memory_limit)))
         self.nsrc = self.nrec = 0

@@ -23,6 +23,9 @@
 namespace fwi {
 
 enum { STEP_FWD = 0, STEP_FWD_SAVE = 1, STEP_ADJ = 2 };
+}  // namespace fwi
+#include "fd2d_stream.cuh"
+namespace fwi {
 
 struct Step2DArgs {
     float* oldnew;        // u_{n-1} in, u_{n+1} out (in place)
@@ -244,8 +247,14 @@ constexpr int kBX = 128;
 struct fwi_fd2d {
     int device = 0, nz = 0, nx = 0, px = 0, nabs = 0;
     float h = 0, dt = 0, alpha = 0;
-    int bz = 32, nw = 4;              // tile rows / warps per CTA (tunable)
+    int bz = 32, nw = 4;              // tiled variant: tile rows / warps per CTA (tunable)
     int tiles_x = 0, tiles_z = 0;
+    int variant = 1;                  // 1 = persistent streaming kernel (default), 0 = one-tile-per-CTA kernel
+    int sm_count = 148, snw = 8, snc = 4;   // streaming variant: warps per CTA, pipeline slots
+    int nstrips = 0, W = 0;
+    int* d_u0 = nullptr;
+    std::vector<int> h_u0;
+    CUtensorMap tm_cur_s[4], tm_old_s[4], tm_m_s;
     float *m = nullptr, *vp = nullptr, *gx = nullptr, *gz = nullptr;
     float* fld[4] = {nullptr, nullptr, nullptr, nullptr};   // forward pair 0/1, adjoint pair 2/3
     CUtensorMap tmap[4];
@@ -265,6 +274,29 @@ struct fwi_fd2d {
     size_t plane() const { return (size_t)nz * px; }
 };
 
+static int make_stream_partition(fwi_fd2d* p) {
+    p->nstrips = (p->nx + 127) / 128;
+    p->W = p->sm_count * p->snw;
+    const int64_t U = (int64_t)p->nstrips * p->nz;
+    p->h_u0.resize(p->W + 1);
+    for (int w = 0; w <= p->W; ++w) p->h_u0[w] = (int)(U * w / p->W);
+    if (p->d_u0) cudaFree(p->d_u0);
+    p->d_u0 = nullptr;
+    FWI_CUDA(cudaMalloc(&p->d_u0, (p->W + 1) * sizeof(int)));
+    FWI_CUDA(cudaMemcpy(p->d_u0, p->h_u0.data(), (p->W + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    const uint64_t dims[2] = {(uint64_t)p->nx, (uint64_t)p->nz};
+    const uint64_t dims_p[2] = {(uint64_t)p->px, (uint64_t)p->nz};
+    const uint64_t strides[1] = {(uint64_t)p->px * sizeof(float)};
+    const uint32_t box_c[2] = {(uint32_t)kSCW, (uint32_t)kSR}, box_r[2] = {128u, (uint32_t)kSR};
+    for (int i = 0; i < 4; ++i) {
+        int rc = encode_tiled_f32(&p->tm_cur_s[i], p->fld[i], 2, dims, strides, box_c);
+        if (rc) return rc;
+        rc = encode_tiled_f32(&p->tm_old_s[i], p->fld[i], 2, dims_p, strides, box_r);
+        if (rc) return rc;
+    }
+    return encode_tiled_f32(&p->tm_m_s, p->m, 2, dims_p, strides, box_r);
+}
+
 static int make_tmaps(fwi_fd2d* p) {
     for (int i = 0; i < 4; ++i) {
         const uint64_t dims[2] = {(uint64_t)p->nx, (uint64_t)p->nz};
@@ -276,18 +308,25 @@ static int make_tmaps(fwi_fd2d* p) {
     return FWI_OK;
 }
 
+// bin that owns grid point (z, x): the CTA tile (tiled variant) or the warp whose row-unit range holds it
+static int owner_bin(const fwi_fd2d* p, int z, int x) {
+    if (p->variant == 0) return (z / p->bz) * p->tiles_x + x / kBX;
+    const int u = (x / 128) * p->nz + z;
+    return (int)(std::upper_bound(p->h_u0.begin(), p->h_u0.end(), u) - p->h_u0.begin()) - 1;
+}
+
 static int build_point_list(fwi_fd2d* p, PointList& pl, int n, const int* iz, const int* ix, const char* what) {
     pl.release();
-    const int ntiles = p->tiles_x * p->tiles_z;
+    const int ntiles = (p->variant == 0) ? p->tiles_x * p->tiles_z : p->W;
     std::vector<int> tile_ptr(ntiles + 1, 0), off(std::max(n, 1)), id(std::max(n, 1));
     for (int i = 0; i < n; ++i) {
         FWI_REQUIRE(iz[i] >= 0 && iz[i] < p->nz && ix[i] >= 0 && ix[i] < p->nx, "%s %d at (z=%d, x=%d) is outside the %d x %d grid", what, i, iz[i], ix[i], p->nz, p->nx);
-        tile_ptr[(iz[i] / p->bz) * p->tiles_x + ix[i] / kBX + 1]++;
+        tile_ptr[owner_bin(p, iz[i], ix[i]) + 1]++;
     }
     for (int t = 0; t < ntiles; ++t) tile_ptr[t + 1] += tile_ptr[t];
     std::vector<int> fill(tile_ptr.begin(), tile_ptr.end() - 1);
     for (int i = 0; i < n; ++i) {
-        const int t = (iz[i] / p->bz) * p->tiles_x + ix[i] / kBX;
+        const int t = owner_bin(p, iz[i], ix[i]);
         const int e = fill[t]++;
         off[e] = iz[i] * p->px + ix[i];
         id[e] = i;
@@ -321,8 +360,45 @@ static int launch_step_cfg(fwi_fd2d* p, int mode, int cur, float* oldnew, const 
     return FWI_OK;
 }
 
+template <int NW, int NC>
+static int launch_stream_cfg(fwi_fd2d* p, int mode, int cur, int oldidx, const PointList* inj, const float* inj_vals,
+                             const PointList* rec, float* rec_out, float* snap, cudaStream_t st) {
+    Stream2DArgs a{};
+    a.oldnew = p->fld[oldidx]; a.gx = p->gx; a.gz = p->gz; a.m = p->m; a.snap = snap; a.acc = p->acc;
+    a.nx = p->nx; a.nz = p->nz; a.px = p->px; a.nstrips = p->nstrips; a.warp_u0 = p->d_u0;
+    a.inj = (inj && inj->n) ? inj->dev() : PointListDev{nullptr, nullptr, nullptr};
+    a.inj_vals = inj_vals;
+    a.rec = (rec && rec->n) ? rec->dev() : PointListDev{nullptr, nullptr, nullptr};
+    a.rec_out = rec_out;
+    const size_t smem = (size_t)NW * NC * (kStageBytes + 8);
+    static bool attr_done = false;
+    if (!attr_done) {
+        FWI_CUDA(cudaFuncSetAttribute(fd2d_stream_kernel<NW, NC, STEP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FWI_CUDA(cudaFuncSetAttribute(fd2d_stream_kernel<NW, NC, STEP_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FWI_CUDA(cudaFuncSetAttribute(fd2d_stream_kernel<NW, NC, STEP_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const dim3 grid(p->sm_count), block(NW * 32);
+    if (mode == STEP_FWD) fd2d_stream_kernel<NW, NC, STEP_FWD><<<grid, block, smem, st>>>(p->tm_cur_s[cur], p->tm_old_s[oldidx], p->tm_m_s, a);
+    else if (mode == STEP_FWD_SAVE) fd2d_stream_kernel<NW, NC, STEP_FWD_SAVE><<<grid, block, smem, st>>>(p->tm_cur_s[cur], p->tm_old_s[oldidx], p->tm_m_s, a);
+    else fd2d_stream_kernel<NW, NC, STEP_ADJ><<<grid, block, smem, st>>>(p->tm_cur_s[cur], p->tm_old_s[oldidx], p->tm_m_s, a);
+    p->launches++;
+    return FWI_OK;
+}
+
 static int launch_step(fwi_fd2d* p, int mode, int cur, float* oldnew, const PointList* inj, const float* inj_vals,
                        const PointList* rec, float* rec_out, float* snap, cudaStream_t st) {
+    if (p->variant == 1) {
+        int oldidx = -1;
+        for (int i = 0; i < 4; ++i) if (p->fld[i] == oldnew) oldidx = i;
+        if (p->snw == 8 && p->snc == 4) return launch_stream_cfg<8, 4>(p, mode, cur, oldidx, inj, inj_vals, rec, rec_out, snap, st);
+        if (p->snw == 4 && p->snc == 8) return launch_stream_cfg<4, 8>(p, mode, cur, oldidx, inj, inj_vals, rec, rec_out, snap, st);
+        if (p->snw == 6 && p->snc == 5) return launch_stream_cfg<6, 5>(p, mode, cur, oldidx, inj, inj_vals, rec, rec_out, snap, st);
+        if (p->snw == 8 && p->snc == 3) return launch_stream_cfg<8, 3>(p, mode, cur, oldidx, inj, inj_vals, rec, rec_out, snap, st);
+        if (p->snw == 12 && p->snc == 3) return launch_stream_cfg<12, 3>(p, mode, cur, oldidx, inj, inj_vals, rec, rec_out, snap, st);
+        set_error("fd2d: unsupported streaming configuration nw=%d nc=%d", p->snw, p->snc);
+        return FWI_EINVAL;
+    }
 #define CFG(BZV, NWV) if (p->bz == BZV && p->nw == NWV) return launch_step_cfg<BZV, NWV>(p, mode, cur, oldnew, inj, inj_vals, rec, rec_out, snap, st)
     CFG(32, 4); CFG(32, 8); CFG(16, 4); CFG(64, 8); CFG(16, 2); CFG(64, 4);
 #undef CFG
@@ -404,7 +480,10 @@ int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, flo
     std::vector<float> gxh = profile(nx, p->px), gzh = profile(nz, nz);
     FWI_CUDA(cudaMemcpy(p->gx, gxh.data(), p->px * sizeof(float), cudaMemcpyHostToDevice));
     FWI_CUDA(cudaMemcpy(p->gz, gzh.data(), nz * sizeof(float), cudaMemcpyHostToDevice));
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
     int rc = make_tmaps(p);
+    if (rc) return rc;
+    rc = make_stream_partition(p);
     if (rc) return rc;
     *out = p;
     return FWI_OK;
@@ -420,8 +499,19 @@ int fwi_fd2d_destroy(fwi_fd2d* p) {
     if (p->resid) cudaFree(p->resid);
     if (p->syn) cudaFree(p->syn);
     p->src.release(); p->rec.release();
+    if (p->d_u0) cudaFree(p->d_u0);
     delete p;
     return FWI_OK;
+}
+
+int fwi_fd2d_set_stream(fwi_fd2d* p, int nw, int nc) {
+    FWI_REQUIRE(p, "fwi_fd2d_set_stream: NULL plan");
+    const bool ok = (nw == 8 && nc == 4) || (nw == 4 && nc == 8) || (nw == 6 && nc == 5) || (nw == 8 && nc == 3) || (nw == 12 && nc == 3);
+    FWI_REQUIRE(ok, "fwi_fd2d_set_stream: unsupported (nw=%d, nc=%d)", nw, nc);
+    DeviceGuard g(p->device);
+    p->variant = 1; p->snw = nw; p->snc = nc;
+    p->src.release(); p->rec.release(); p->nsrc = p->nrec = 0;
+    return make_stream_partition(p);
 }
 
 int fwi_fd2d_set_tile(fwi_fd2d* p, int bz, int nw) {
@@ -429,7 +519,7 @@ int fwi_fd2d_set_tile(fwi_fd2d* p, int bz, int nw) {
     const bool ok = (bz == 32 && (nw == 4 || nw == 8)) || (bz == 16 && (nw == 4 || nw == 2)) || (bz == 64 && (nw == 8 || nw == 4));
     FWI_REQUIRE(ok, "fwi_fd2d_set_tile: unsupported (bz=%d, nw=%d)", bz, nw);
     DeviceGuard g(p->device);
-    p->bz = bz; p->nw = nw;
+    p->variant = 0; p->bz = bz; p->nw = nw;
     p->tiles_z = (p->nz + bz - 1) / bz;
     p->src.release(); p->rec.release(); p->nsrc = p->nrec = 0;      // tile binning changed
     return make_tmaps(p);

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(384) mc_eval_kernel(EvalParams p) {
     constexpr int NST = nstat(MODE);
     constexpr int SPB = 32 * S;
     constexpr int CHUNK = 64;
-    extern __shared__ float stats[];          // [K][NST][SPB]
+    extern __shared__ double stats[];         // [K][NST][SPB] (float64: the fold below cancels terms)
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -158,10 +158,10 @@ __global__ void __launch_bounds__(384) mc_eval_kernel(EvalParams p) {
         }
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            float* st = stats + (size_t)k * NST * SPB + s * 32 + lane;
-            st[0] = (float)t0[s];
-            if (MODE != MODE_SSE) { st[SPB] = (float)t1[s]; st[2 * SPB] = mu[s]; }
-            if (MODE == MODE_MOM_MAX) st[3 * SPB] = fmaxf(fabsf(vmax[s] + mu[s]), fabsf(vmin[s] + mu[s]));
+            double* st = stats + (size_t)k * NST * SPB + s * 32 + lane;
+            st[0] = t0[s];
+            if (MODE != MODE_SSE) { st[SPB] = t1[s]; st[2 * SPB] = (double)mu[s]; }
+            if (MODE == MODE_MOM_MAX) st[3 * SPB] = fmax(fabs((double)vmax[s] + (double)mu[s]), fabs((double)vmin[s] + (double)mu[s]));
         }
     }
     __syncthreads();
@@ -173,13 +173,13 @@ __global__ void __launch_bounds__(384) mc_eval_kernel(EvalParams p) {
         const bool norm = p.flags & FWI_FLAG_NORMALISED;
         const bool simul = p.flags & FWI_FLAG_SIMULTANEOUS;
         const double Tn = (double)p.Tv;
-        const float* st = stats + i;
+        const double* st = stats + i;
         double result;
         if (p.metric == FWI_METRIC_VR || p.metric == FWI_METRIC_GAU) {
             double acc = 0.0, tot_sse = 0.0, tot_dd = 0.0;
             for (int k = 0; k < p.K; ++k) {
                 const TraceConst tc = p.tc[k];
-                const float* q = st + (size_t)k * NST * SPB;
+                const double* q = st + (size_t)k * NST * SPB;
                 double sse, dd, sig = tc.sigma;
                 if (MODE == MODE_SSE) {
                     sse = q[0];
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(384) mc_eval_kernel(EvalParams p) {
             if (!simul) {
                 double acc = 0.0;
                 for (int k = 0; k < p.K; ++k) {
-                    const float* q = st + (size_t)k * NST * SPB;
+                    const double* q = st + (size_t)k * NST * SPB;
                     const double pcc = (double)q[SPB] / sqrt((double)q[0] * p.tc[k].ssd);   // FWI:572-573
                     acc += (pcc < 0.0) ? 0.0 : pcc;                                          // FWI:574-575
                 }
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(384) mc_eval_kernel(EvalParams p) {
                 double A1 = 0.0, A2 = 0.0, A3 = 0.0;
                 for (int k = 0; k < p.K; ++k) {
                     const TraceConst tc = p.tc[k];
-                    const float* q = st + (size_t)k * NST * SPB;
+                    const double* q = st + (size_t)k * NST * SPB;
                     const double s2 = q[0], sd = q[SPB], mu = q[2 * SPB];
                     double a = 1.0, b = 1.0;
                     if (MODE == MODE_MOM_MAX) { a = 1.0 / (double)q[3 * SPB]; b = 1.0 / tc.maxd; }
@@ -683,7 +683,7 @@ static int build_rowset(fwi_mc_ctx* c, RowSet& rs, int variant) {
 template <int C, int NM, int S, int MODE>
 static int launch_eval_t(const EvalParams& p, int nwarps, cudaStream_t st) {
     constexpr int SPB = 32 * S;
-    const size_t smem = (size_t)p.K * nstat(MODE) * SPB * sizeof(float);
+    const size_t smem = (size_t)p.K * nstat(MODE) * SPB * sizeof(double);
     auto kern = mc_eval_kernel<C, NM, S, MODE>;
     if (smem > 48 * 1024) FWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t blocks = ceil_div(p.N, SPB);
@@ -856,9 +856,9 @@ int fwi_mc_eval(fwi_mc_ctx* c, const float* M, int64_t ldm, const float* frac, i
     const int64_t full = (int64_t)c->sm_count * 2 * 128;
     if (N < full) S = 2;
     if (N < full / 4) S = 1;
-    while (S > 1 && (size_t)c->K * nstat(mode) * 32 * (c->NM == 1 ? S : std::max(1, S / 2)) * 4 > 200 * 1024) S >>= 1;
+    while (S > 1 && (size_t)c->K * nstat(mode) * 32 * (c->NM == 1 ? S : std::max(1, S / 2)) * 8 > 200 * 1024) S >>= 1;
     const int Seff = (c->NM == 1) ? S : std::max(1, S / 2);
-    FWI_REQUIRE((size_t)c->K * nstat(mode) * 32 * Seff * 4 <= 220 * 1024, "fwi_mc_eval: K=%d traces exceed the shared-memory statistics buffer", c->K);
+    FWI_REQUIRE((size_t)c->K * nstat(mode) * 32 * Seff * 8 <= 220 * 1024, "fwi_mc_eval: K=%d traces exceed the shared-memory statistics buffer", c->K);
     const int nw = pick_warps(c->K);
     cudaStream_t st = (cudaStream_t)stream;
     if (c->NM == 1) {
