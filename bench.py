@@ -12,7 +12,7 @@ the NCCL all-reduce of the gradient.  `value` counts wavefield point-updates (2 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nt 5000] [--grid 1000x3000]
 
 `--impl reference`: the reference repository has no propagator, so the CPU arm is the self-oracle port
-(oracle/fd_oracle_c.c, OpenMP over all host cores; NumPy fallback) on a bounded sample of the same workload.
+(oracle/fd_oracle_c.c, POSIX threads over all host cores; NumPy fallback) on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -133,7 +133,7 @@ def cpu_stencil_rate(w, seconds_target=12.0):
         n_steps = min(n_steps, 400)
         t = foc.time_forward_adjoint(w["v"], w["h"], w["dt"], w["nabs"], w["alpha"], n_steps)
         rate = 2.0 * n_steps * nz * nx / t
-        return rate, cores, "port", "oracle/fd_oracle_c.c (OpenMP): %d forward-with-save + %d adjoint steps on the full %dx%d grid, %.1f s" % (n_steps, n_steps, nz, nx, t)
+        return rate, cores, "port", "oracle/fd_oracle_c.c (pthreads): %d forward-with-save + %d adjoint steps on the full %dx%d grid, %.1f s" % (n_steps, n_steps, nz, nx, t)
     p = fo.Problem(w["v"].astype(np.float64), w["h"], w["dt"], w["shots"][0][0], w["shots"][0][1][::8], nabs=w["nabs"], alpha=w["alpha"])
     cur = np.zeros((nz, nx)); old = np.zeros((nz, nx))
     n_steps, t0 = 0, time.perf_counter()

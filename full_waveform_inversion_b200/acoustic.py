@@ -28,6 +28,7 @@ _lib.register({
     "fwi_fd2d_destroy": (c_int, [c_void_p]),
     "fwi_fd2d_set_tile": (c_int, [c_void_p, c_int, c_int]),
     "fwi_fd2d_set_stream": (c_int, [c_void_p, c_int, c_int]),
+    "fwi_fd2d_set_graphs": (c_int, [c_void_p, c_int]),
     "fwi_fd2d_set_memory_limit": (c_int, [c_void_p, c_uint64]),
     "fwi_fd2d_set_model": (c_int, [c_void_p, c_void_p, c_void_p]),
     "fwi_fd2d_set_geometry": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
@@ -72,7 +73,7 @@ class Propagator2D:
 
     ndim = 2
 
-    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=0, tile=None, memory_limit=0, stream=None):
+    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=0, tile=None, memory_limit=0, stream=None, graphs=True):
         self._lib = _lib.require_gpu()
         self.nz, self.nx = int(shape[0]), int(shape[1])
         self.h, self.dt = float(h), float(dt)
@@ -86,6 +87,8 @@ class Propagator2D:
             check(self._lib.fwi_fd2d_set_stream(self._h, int(stream[0]), int(stream[1])))
         if memory_limit:
             check(self._lib.fwi_fd2d_set_memory_limit(self._h, int(memory_limit)))
+        if not graphs:
+            check(self._lib.fwi_fd2d_set_graphs(self._h, 0))
         self.nsrc = self.nrec = 0
 
     @property

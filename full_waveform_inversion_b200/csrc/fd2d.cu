@@ -226,30 +226,44 @@ int encode_tiled_f32(CUtensorMap* out, void* base, int rank, const uint64_t* dim
 using namespace fwi;
 
 // =============================================================================================== host plan
+//
+// Time loops are replayed as CUDA graphs: a 1000 x 3000 step kernel runs for ~6 us, about what one
+// cudaLaunchKernel costs the host, so a stream of individual launches is launch-bound.  The whole forward
+// pass (nt step nodes) and the whole gradient (forward with snapshots, residual, adjoint with imaging, and the
+// checkpoint copies when they are needed) are each captured ONCE per (nt, geometry size) on the plan's private
+// stream and re-launched for every shot.  That requires every pointer inside the graph to be stable, so the
+// graph only touches plan-owned buffers: wavelet / observed data are copied into staging buffers before the
+// launch, synthetics are copied out after it, and the sparse source / receiver lists keep their allocations
+// (set_geometry rewrites their contents in place).
 namespace {
 
 struct PointList {
-    int n = 0;
+    int n = 0, cap = 0, nbins = 0;
     int* d_tile_ptr = nullptr; int* d_off = nullptr; int* d_id = nullptr;
     void release() {
         if (d_tile_ptr) cudaFree(d_tile_ptr);
         if (d_off) cudaFree(d_off);
         if (d_id) cudaFree(d_id);
-        d_tile_ptr = d_off = d_id = nullptr; n = 0;
+        d_tile_ptr = d_off = d_id = nullptr; n = cap = nbins = 0;
     }
     PointListDev dev() const { return PointListDev{d_tile_ptr, d_off, d_id}; }
 };
 
 constexpr int kBX = 128;
 
+struct GraphEntry {
+    int kind, nt, nsrc, nrec, seg, nseg;
+    cudaGraphExec_t exec;
+};
+
 }  // namespace
 
 struct fwi_fd2d {
     int device = 0, nz = 0, nx = 0, px = 0, nabs = 0;
     float h = 0, dt = 0, alpha = 0;
-    int bz = 32, nw = 4;              // tiled variant: tile rows / warps per CTA (tunable)
+    int bz = 16, nw = 2;              // tiled variant: tile rows / warps per CTA (tunable)
     int tiles_x = 0, tiles_z = 0;
-    int variant = 1;                  // 1 = persistent streaming kernel (default), 0 = one-tile-per-CTA kernel
+    int variant = 0;                  // 0 = one-tile-per-CTA kernel (default), 1 = persistent streaming kernel
     int sm_count = 148, snw = 8, snc = 4;   // streaming variant: warps per CTA, pipeline slots
     int nstrips = 0, W = 0;
     int* d_u0 = nullptr;
@@ -263,16 +277,26 @@ struct fwi_fd2d {
     float* ckpt = nullptr; size_t ckpt_slots = 0;
     float* resid = nullptr; size_t resid_cap = 0;
     float* syn = nullptr; size_t syn_cap = 0;
+    float* obs = nullptr; size_t obs_cap = 0;
+    float* wav = nullptr; size_t wav_cap = 0;
     double* d_J = nullptr;
-    unsigned int* d_absmax = nullptr;
     PointList src, rec;
     int nsrc = 0, nrec = 0;
     size_t mem_limit = 0;             // 0 = automatic (fraction of free memory)
     int fwd_cur = 0;                  // which of fld[0/1] holds u_n after the last forward
     bool model_set = false;
+    bool use_graphs = true;
     int64_t launches = 0;
+    cudaStream_t work = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    std::vector<GraphEntry> graphs;
     size_t plane() const { return (size_t)nz * px; }
 };
+
+static void drop_graphs(fwi_fd2d* p) {
+    for (auto& g : p->graphs) cudaGraphExecDestroy(g.exec);
+    p->graphs.clear();
+}
 
 static int make_stream_partition(fwi_fd2d* p) {
     p->nstrips = (p->nx + 127) / 128;
@@ -316,27 +340,33 @@ static int owner_bin(const fwi_fd2d* p, int z, int x) {
 }
 
 static int build_point_list(fwi_fd2d* p, PointList& pl, int n, const int* iz, const int* ix, const char* what) {
-    pl.release();
-    const int ntiles = (p->variant == 0) ? p->tiles_x * p->tiles_z : p->W;
-    std::vector<int> tile_ptr(ntiles + 1, 0), off(std::max(n, 1)), id(std::max(n, 1));
+    const int nbins = (p->variant == 0) ? p->tiles_x * p->tiles_z : p->W;
+    std::vector<int> tile_ptr(nbins + 1, 0), off(std::max(n, 1)), id(std::max(n, 1));
     for (int i = 0; i < n; ++i) {
         FWI_REQUIRE(iz[i] >= 0 && iz[i] < p->nz && ix[i] >= 0 && ix[i] < p->nx, "%s %d at (z=%d, x=%d) is outside the %d x %d grid", what, i, iz[i], ix[i], p->nz, p->nx);
         tile_ptr[owner_bin(p, iz[i], ix[i]) + 1]++;
     }
-    for (int t = 0; t < ntiles; ++t) tile_ptr[t + 1] += tile_ptr[t];
+    for (int t = 0; t < nbins; ++t) tile_ptr[t + 1] += tile_ptr[t];
     std::vector<int> fill(tile_ptr.begin(), tile_ptr.end() - 1);
     for (int i = 0; i < n; ++i) {
-        const int t = owner_bin(p, iz[i], ix[i]);
-        const int e = fill[t]++;
+        const int e = fill[owner_bin(p, iz[i], ix[i])]++;
         off[e] = iz[i] * p->px + ix[i];
         id[e] = i;
     }
-    FWI_CUDA(cudaMalloc(&pl.d_tile_ptr, (ntiles + 1) * sizeof(int)));
-    FWI_CUDA(cudaMalloc(&pl.d_off, std::max(n, 1) * sizeof(int)));
-    FWI_CUDA(cudaMalloc(&pl.d_id, std::max(n, 1) * sizeof(int)));
-    FWI_CUDA(cudaMemcpy(pl.d_tile_ptr, tile_ptr.data(), (ntiles + 1) * sizeof(int), cudaMemcpyHostToDevice));
-    FWI_CUDA(cudaMemcpy(pl.d_off, off.data(), std::max(n, 1) * sizeof(int), cudaMemcpyHostToDevice));
-    FWI_CUDA(cudaMemcpy(pl.d_id, id.data(), std::max(n, 1) * sizeof(int), cudaMemcpyHostToDevice));
+    if (pl.nbins != nbins || pl.cap < std::max(n, 1)) {     // allocations change -> cached graphs hold stale pointers
+        pl.release();
+        drop_graphs(p);
+        const int cap = std::max(n, 1);
+        FWI_CUDA(cudaMalloc(&pl.d_tile_ptr, (nbins + 1) * sizeof(int)));
+        FWI_CUDA(cudaMalloc(&pl.d_off, cap * sizeof(int)));
+        FWI_CUDA(cudaMalloc(&pl.d_id, cap * sizeof(int)));
+        pl.cap = cap; pl.nbins = nbins;
+    }
+    // contents are rewritten in place on the work stream, ordered after the previous shot's graph
+    FWI_CUDA(cudaMemcpyAsync(pl.d_tile_ptr, tile_ptr.data(), (nbins + 1) * sizeof(int), cudaMemcpyHostToDevice, p->work));
+    FWI_CUDA(cudaMemcpyAsync(pl.d_off, off.data(), std::max(n, 1) * sizeof(int), cudaMemcpyHostToDevice, p->work));
+    FWI_CUDA(cudaMemcpyAsync(pl.d_id, id.data(), std::max(n, 1) * sizeof(int), cudaMemcpyHostToDevice, p->work));
+    FWI_CUDA(cudaStreamSynchronize(p->work));       // the host vectors go out of scope
     pl.n = n;
     return FWI_OK;
 }
@@ -356,7 +386,15 @@ static int launch_step_cfg(fwi_fd2d* p, int mode, int cur, float* oldnew, const 
     if (mode == STEP_FWD) fd2d_step_kernel<BZ, NW, STEP_FWD><<<grid, block, smem, st>>>(p->tmap[cur], a);
     else if (mode == STEP_FWD_SAVE) fd2d_step_kernel<BZ, NW, STEP_FWD_SAVE><<<grid, block, smem, st>>>(p->tmap[cur], a);
     else fd2d_step_kernel<BZ, NW, STEP_ADJ><<<grid, block, smem, st>>>(p->tmap[cur], a);
-    p->launches++;
+    return FWI_OK;
+}
+
+template <int NW, int NC>
+static int stream_attrs() {
+    const size_t smem = (size_t)NW * NC * (kStageBytes + 8);
+    FWI_CUDA(cudaFuncSetAttribute(fd2d_stream_kernel<NW, NC, STEP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FWI_CUDA(cudaFuncSetAttribute(fd2d_stream_kernel<NW, NC, STEP_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FWI_CUDA(cudaFuncSetAttribute(fd2d_stream_kernel<NW, NC, STEP_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return FWI_OK;
 }
 
@@ -371,23 +409,16 @@ static int launch_stream_cfg(fwi_fd2d* p, int mode, int cur, int oldidx, const P
     a.rec = (rec && rec->n) ? rec->dev() : PointListDev{nullptr, nullptr, nullptr};
     a.rec_out = rec_out;
     const size_t smem = (size_t)NW * NC * (kStageBytes + 8);
-    static bool attr_done = false;
-    if (!attr_done) {
-        FWI_CUDA(cudaFuncSetAttribute(fd2d_stream_kernel<NW, NC, STEP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FWI_CUDA(cudaFuncSetAttribute(fd2d_stream_kernel<NW, NC, STEP_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FWI_CUDA(cudaFuncSetAttribute(fd2d_stream_kernel<NW, NC, STEP_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
     const dim3 grid(p->sm_count), block(NW * 32);
     if (mode == STEP_FWD) fd2d_stream_kernel<NW, NC, STEP_FWD><<<grid, block, smem, st>>>(p->tm_cur_s[cur], p->tm_old_s[oldidx], p->tm_m_s, a);
     else if (mode == STEP_FWD_SAVE) fd2d_stream_kernel<NW, NC, STEP_FWD_SAVE><<<grid, block, smem, st>>>(p->tm_cur_s[cur], p->tm_old_s[oldidx], p->tm_m_s, a);
     else fd2d_stream_kernel<NW, NC, STEP_ADJ><<<grid, block, smem, st>>>(p->tm_cur_s[cur], p->tm_old_s[oldidx], p->tm_m_s, a);
-    p->launches++;
     return FWI_OK;
 }
 
 static int launch_step(fwi_fd2d* p, int mode, int cur, float* oldnew, const PointList* inj, const float* inj_vals,
                        const PointList* rec, float* rec_out, float* snap, cudaStream_t st) {
+    p->launches++;
     if (p->variant == 1) {
         int oldidx = -1;
         for (int i = 0; i < 4; ++i) if (p->fld[i] == oldnew) oldidx = i;
@@ -400,17 +431,18 @@ static int launch_step(fwi_fd2d* p, int mode, int cur, float* oldnew, const Poin
         return FWI_EINVAL;
     }
 #define CFG(BZV, NWV) if (p->bz == BZV && p->nw == NWV) return launch_step_cfg<BZV, NWV>(p, mode, cur, oldnew, inj, inj_vals, rec, rec_out, snap, st)
-    CFG(32, 4); CFG(32, 8); CFG(16, 4); CFG(64, 8); CFG(16, 2); CFG(64, 4);
+    CFG(16, 2); CFG(32, 4); CFG(32, 8); CFG(16, 4); CFG(64, 8); CFG(64, 4);
 #undef CFG
     set_error("fd2d: unsupported tile configuration bz=%d nw=%d", p->bz, p->nw);
     return FWI_EINVAL;
 }
 
-static int ensure_bytes(float** ptr, size_t* cap, size_t need_floats) {
-    if (*cap >= need_floats) return FWI_OK;
+static int ensure_floats(fwi_fd2d* p, float** ptr, size_t* cap, size_t need_floats) {
+    if (*cap >= need_floats && *ptr) return FWI_OK;
     if (*ptr) cudaFree(*ptr);
     *ptr = nullptr; *cap = 0;
-    FWI_CUDA(cudaMalloc(ptr, need_floats * sizeof(float)));
+    drop_graphs(p);
+    FWI_CUDA(cudaMalloc(ptr, std::max<size_t>(need_floats, 1) * sizeof(float)));
     *cap = need_floats;
     return FWI_OK;
 }
@@ -441,6 +473,102 @@ static int run_adjoint(fwi_fd2d* p, const float* resid, int n0, int n1, size_t s
     return FWI_OK;
 }
 
+// The forward pass as a sequence of stream operations on `st` (captured into a graph or run directly).
+static int record_forward(fwi_fd2d* p, int nt, cudaStream_t st) {
+    const size_t pl = p->plane();
+    FWI_CUDA(cudaMemsetAsync(p->fld[0], 0, pl * sizeof(float), st));
+    FWI_CUDA(cudaMemsetAsync(p->fld[1], 0, pl * sizeof(float), st));
+    int cur = 0;
+    return run_forward(p, p->wav, 0, nt, p->nrec ? p->syn : nullptr, false, 0, cur, st);
+}
+
+// The gradient of one shot as a sequence of stream operations on `st`: forward (+ snapshots or checkpoints),
+// residual, adjoint with imaging.  Reads p->wav / p->obs, leaves synthetics in p->syn, I in p->acc, J in p->d_J.
+static int record_gradient(fwi_fd2d* p, int nt, int seg, int nseg, cudaStream_t st) {
+    const size_t pl = p->plane();
+    const size_t ntr = (size_t)nt * p->nrec;
+    FWI_CUDA(cudaMemsetAsync(p->fld[0], 0, pl * sizeof(float), st));
+    FWI_CUDA(cudaMemsetAsync(p->fld[1], 0, pl * sizeof(float), st));
+    int cur = 0, rc;
+    std::vector<int> seg_cur(nseg, 0);
+    if (nseg == 1) {
+        rc = run_forward(p, p->wav, 0, nt, p->syn, true, 0, cur, st);
+        if (rc) return rc;
+    } else {
+        for (int s = 0; s < nseg; ++s) {
+            FWI_CUDA(cudaMemcpyAsync(p->ckpt + (size_t)(2 * s) * pl, p->fld[cur], pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            FWI_CUDA(cudaMemcpyAsync(p->ckpt + (size_t)(2 * s + 1) * pl, p->fld[cur ^ 1], pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            seg_cur[s] = cur;
+            rc = run_forward(p, p->wav, s * seg, std::min(nt, (s + 1) * seg), p->syn, false, 0, cur, st);
+            if (rc) return rc;
+        }
+    }
+    FWI_CUDA(cudaMemsetAsync(p->d_J, 0, sizeof(double), st));
+    fd_residual_kernel<<<(unsigned)std::min<size_t>(1024, (ntr + 255) / 256), 256, 0, st>>>(p->syn, p->obs, (int64_t)ntr, p->resid, p->d_J);
+    FWI_CUDA(cudaGetLastError());
+    p->launches += 1;
+    FWI_CUDA(cudaMemsetAsync(p->fld[2], 0, pl * sizeof(float), st));
+    FWI_CUDA(cudaMemsetAsync(p->fld[3], 0, pl * sizeof(float), st));
+    FWI_CUDA(cudaMemsetAsync(p->acc, 0, pl * sizeof(float), st));
+    int acur = 0;
+    if (nseg == 1) {
+        rc = run_adjoint(p, p->resid, 0, nt, 0, acur, st);
+        if (rc) return rc;
+    } else {
+        for (int s = nseg - 1; s >= 0; --s) {
+            const int n0 = s * seg, n1 = std::min(nt, (s + 1) * seg);
+            int c = seg_cur[s];
+            FWI_CUDA(cudaMemcpyAsync(p->fld[c], p->ckpt + (size_t)(2 * s) * pl, pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            FWI_CUDA(cudaMemcpyAsync(p->fld[c ^ 1], p->ckpt + (size_t)(2 * s + 1) * pl, pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            rc = run_forward(p, p->wav, n0, n1, nullptr, true, n0, c, st);     // recompute w_n for this segment
+            if (rc) return rc;
+            rc = run_adjoint(p, p->resid, n0, n1, n0, acur, st);
+            if (rc) return rc;
+        }
+    }
+    return FWI_OK;
+}
+
+// Run `record` either directly on the work stream or as a cached graph keyed by (kind, nt, nsrc, nrec, seg, nseg).
+template <typename F>
+static int run_cached(fwi_fd2d* p, int kind, int nt, int seg, int nseg, F&& record) {
+    if (!p->use_graphs) return record(p->work);
+    for (auto& g : p->graphs)
+        if (g.kind == kind && g.nt == nt && g.nsrc == p->nsrc && g.nrec == p->nrec && g.seg == seg && g.nseg == nseg) {
+            FWI_CUDA(cudaGraphLaunch(g.exec, p->work));
+            p->launches += (kind == 0) ? nt : (int64_t)(nseg == 1 ? 2 : 3) * nt + 1;
+            return FWI_OK;
+        }
+    cudaGraph_t graph = nullptr;
+    FWI_CUDA(cudaStreamBeginCapture(p->work, cudaStreamCaptureModeThreadLocal));
+    const int64_t l0 = p->launches;
+    int rc = record(p->work);
+    cudaError_t e = cudaStreamEndCapture(p->work, &graph);
+    p->launches = l0;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) { set_error("stream capture failed: %s", cudaGetErrorString(e)); return FWI_ECUDA; }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return FWI_ECUDA; }
+    if (p->graphs.size() >= 6) { cudaGraphExecDestroy(p->graphs.front().exec); p->graphs.erase(p->graphs.begin()); }
+    p->graphs.push_back(GraphEntry{kind, nt, p->nsrc, p->nrec, seg, nseg, exec});
+    FWI_CUDA(cudaGraphLaunch(exec, p->work));
+    p->launches += (kind == 0) ? nt : (int64_t)(nseg == 1 ? 2 : 3) * nt + 1;
+    return FWI_OK;
+}
+
+static int enter(fwi_fd2d* p, cudaStream_t user) {       // work stream waits for everything queued on the caller's
+    FWI_CUDA(cudaEventRecord(p->ev_in, user));
+    FWI_CUDA(cudaStreamWaitEvent(p->work, p->ev_in, 0));
+    return FWI_OK;
+}
+static int leave(fwi_fd2d* p, cudaStream_t user) {       // ... and the caller's stream waits for the work stream
+    FWI_CUDA(cudaEventRecord(p->ev_out, p->work));
+    FWI_CUDA(cudaStreamWaitEvent(user, p->ev_out, 0));
+    return FWI_OK;
+}
+
 extern "C" {
 
 int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, float alpha, fwi_fd2d** out) {
@@ -458,6 +586,9 @@ int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, flo
     p->tiles_x = (nx + kBX - 1) / kBX;
     p->tiles_z = (nz + p->bz - 1) / p->bz;
     const size_t pl = p->plane();
+    FWI_CUDA(cudaStreamCreateWithFlags(&p->work, cudaStreamNonBlocking));
+    FWI_CUDA(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
+    FWI_CUDA(cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming));
     FWI_CUDA(cudaMalloc(&p->m, pl * sizeof(float)));
     FWI_CUDA(cudaMalloc(&p->vp, pl * sizeof(float)));
     FWI_CUDA(cudaMalloc(&p->acc, pl * sizeof(float)));
@@ -465,7 +596,6 @@ int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, flo
     FWI_CUDA(cudaMalloc(&p->gx, p->px * sizeof(float)));
     FWI_CUDA(cudaMalloc(&p->gz, nz * sizeof(float)));
     FWI_CUDA(cudaMalloc(&p->d_J, sizeof(double)));
-    FWI_CUDA(cudaMalloc(&p->d_absmax, sizeof(unsigned int)));
     // sponge profiles (oracle/fd_oracle.py sponge_profile), float64 on the host then rounded once
     auto profile = [&](int n, int padded) {
         std::vector<float> prof(padded, 1.0f);
@@ -485,6 +615,7 @@ int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, flo
     if (rc) return rc;
     rc = make_stream_partition(p);
     if (rc) return rc;
+    if ((rc = stream_attrs<8, 4>()) || (rc = stream_attrs<4, 8>()) || (rc = stream_attrs<6, 5>()) || (rc = stream_attrs<8, 3>()) || (rc = stream_attrs<12, 3>())) return rc;
     *out = p;
     return FWI_OK;
 }
@@ -492,14 +623,21 @@ int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, flo
 int fwi_fd2d_destroy(fwi_fd2d* p) {
     if (!p) return FWI_OK;
     DeviceGuard g(p->device);
-    cudaFree(p->m); cudaFree(p->vp); cudaFree(p->acc); cudaFree(p->gx); cudaFree(p->gz); cudaFree(p->d_J); cudaFree(p->d_absmax);
+    if (p->work) cudaStreamSynchronize(p->work);
+    drop_graphs(p);
+    cudaFree(p->m); cudaFree(p->vp); cudaFree(p->acc); cudaFree(p->gx); cudaFree(p->gz); cudaFree(p->d_J);
     for (int i = 0; i < 4; ++i) cudaFree(p->fld[i]);
     if (p->snap) cudaFree(p->snap);
     if (p->ckpt) cudaFree(p->ckpt);
     if (p->resid) cudaFree(p->resid);
     if (p->syn) cudaFree(p->syn);
+    if (p->obs) cudaFree(p->obs);
+    if (p->wav) cudaFree(p->wav);
     p->src.release(); p->rec.release();
     if (p->d_u0) cudaFree(p->d_u0);
+    if (p->ev_in) cudaEventDestroy(p->ev_in);
+    if (p->ev_out) cudaEventDestroy(p->ev_out);
+    if (p->work) cudaStreamDestroy(p->work);
     delete p;
     return FWI_OK;
 }
@@ -509,6 +647,8 @@ int fwi_fd2d_set_stream(fwi_fd2d* p, int nw, int nc) {
     const bool ok = (nw == 8 && nc == 4) || (nw == 4 && nc == 8) || (nw == 6 && nc == 5) || (nw == 8 && nc == 3) || (nw == 12 && nc == 3);
     FWI_REQUIRE(ok, "fwi_fd2d_set_stream: unsupported (nw=%d, nc=%d)", nw, nc);
     DeviceGuard g(p->device);
+    FWI_CUDA(cudaStreamSynchronize(p->work));
+    drop_graphs(p);
     p->variant = 1; p->snw = nw; p->snc = nc;
     p->src.release(); p->rec.release(); p->nsrc = p->nrec = 0;
     return make_stream_partition(p);
@@ -519,10 +659,18 @@ int fwi_fd2d_set_tile(fwi_fd2d* p, int bz, int nw) {
     const bool ok = (bz == 32 && (nw == 4 || nw == 8)) || (bz == 16 && (nw == 4 || nw == 2)) || (bz == 64 && (nw == 8 || nw == 4));
     FWI_REQUIRE(ok, "fwi_fd2d_set_tile: unsupported (bz=%d, nw=%d)", bz, nw);
     DeviceGuard g(p->device);
+    FWI_CUDA(cudaStreamSynchronize(p->work));
+    drop_graphs(p);
     p->variant = 0; p->bz = bz; p->nw = nw;
     p->tiles_z = (p->nz + bz - 1) / bz;
     p->src.release(); p->rec.release(); p->nsrc = p->nrec = 0;      // tile binning changed
     return make_tmaps(p);
+}
+
+int fwi_fd2d_set_graphs(fwi_fd2d* p, int enable) {
+    FWI_REQUIRE(p, "fwi_fd2d_set_graphs: NULL plan");
+    p->use_graphs = enable != 0;
+    return FWI_OK;
 }
 
 int fwi_fd2d_set_memory_limit(fwi_fd2d* p, uint64_t bytes) {
@@ -534,11 +682,14 @@ int fwi_fd2d_set_memory_limit(fwi_fd2d* p, uint64_t bytes) {
 int fwi_fd2d_set_model(fwi_fd2d* p, const float* v_dev, void* stream) {
     FWI_REQUIRE(p && v_dev, "fwi_fd2d_set_model: NULL argument");
     DeviceGuard g(p->device);
+    cudaStream_t user = (cudaStream_t)stream;
+    int rc = enter(p, user);
+    if (rc) return rc;
     dim3 grid((p->px + 127) / 128, p->nz);
-    fd_model_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(v_dev, p->nz, p->nx, p->px, p->dt / p->h, p->m, p->vp);
+    fd_model_kernel<<<grid, 128, 0, p->work>>>(v_dev, p->nz, p->nx, p->px, p->dt / p->h, p->m, p->vp);
     FWI_CUDA(cudaGetLastError());
     p->model_set = true;
-    return FWI_OK;
+    return leave(p, user);
 }
 
 int fwi_fd2d_set_geometry(fwi_fd2d* p, int nsrc, const int* src_z, const int* src_x, int nrec, const int* rec_z,
@@ -559,23 +710,30 @@ int fwi_fd2d_forward(fwi_fd2d* p, const float* wavelet_dev, int nt, float* trace
     FWI_REQUIRE(nt >= 0 && (p->nsrc == 0 || wavelet_dev), "fwi_fd2d_forward: bad wavelet / nt");
     FWI_REQUIRE(p->nrec == 0 || traces_dev, "fwi_fd2d_forward: traces_dev is NULL but receivers are set");
     DeviceGuard g(p->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    FWI_CUDA(cudaMemsetAsync(p->fld[0], 0, p->plane() * sizeof(float), st));
-    FWI_CUDA(cudaMemsetAsync(p->fld[1], 0, p->plane() * sizeof(float), st));
-    int cur = 0;
-    int rc = run_forward(p, wavelet_dev, 0, nt, p->nrec ? traces_dev : nullptr, false, 0, cur, st);
-    p->fwd_cur = cur;
-    return rc;
+    cudaStream_t user = (cudaStream_t)stream;
+    int rc;
+    if ((rc = ensure_floats(p, &p->wav, &p->wav_cap, (size_t)nt * p->nsrc))) return rc;
+    if ((rc = ensure_floats(p, &p->syn, &p->syn_cap, (size_t)nt * p->nrec))) return rc;
+    if ((rc = enter(p, user))) return rc;
+    if (nt * p->nsrc) FWI_CUDA(cudaMemcpyAsync(p->wav, wavelet_dev, (size_t)nt * p->nsrc * sizeof(float), cudaMemcpyDeviceToDevice, p->work));
+    rc = run_cached(p, 0, nt, 0, 0, [&](cudaStream_t st) { return record_forward(p, nt, st); });
+    if (rc) return rc;
+    if (nt * p->nrec) FWI_CUDA(cudaMemcpyAsync(traces_dev, p->syn, (size_t)nt * p->nrec * sizeof(float), cudaMemcpyDeviceToDevice, p->work));
+    p->fwd_cur = nt & 1;
+    return leave(p, user);
 }
 
 int fwi_fd2d_wavefield(fwi_fd2d* p, int which, float* out_dev, void* stream) {
     FWI_REQUIRE(p && out_dev && which >= 0 && which <= 2, "fwi_fd2d_wavefield: bad arguments");
     DeviceGuard g(p->device);
+    cudaStream_t user = (cudaStream_t)stream;
+    int rc = enter(p, user);
+    if (rc) return rc;
     const float* src = (which == 0) ? p->fld[p->fwd_cur] : (which == 1 ? p->fld[p->fwd_cur ^ 1] : p->acc);
     dim3 grid((p->nx + 127) / 128, p->nz);
-    fd_unpitch_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(src, p->nz, p->nx, p->px, out_dev);
+    fd_unpitch_kernel<<<grid, 128, 0, p->work>>>(src, p->nz, p->nx, p->px, out_dev);
     FWI_CUDA(cudaGetLastError());
-    return FWI_OK;
+    return leave(p, user);
 }
 
 int fwi_fd2d_gradient(fwi_fd2d* p, const float* wavelet_dev, const float* obs_dev, int nt, float* grad_dev,
@@ -584,14 +742,14 @@ int fwi_fd2d_gradient(fwi_fd2d* p, const float* wavelet_dev, const float* obs_de
     FWI_REQUIRE(wavelet_dev && obs_dev && grad_dev && nt >= 1, "fwi_fd2d_gradient: NULL argument or nt < 1");
     FWI_REQUIRE(p->nsrc >= 1 && p->nrec >= 1, "fwi_fd2d_gradient: geometry needs at least one source and one receiver");
     DeviceGuard g(p->device);
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t user = (cudaStream_t)stream;
     const size_t pl = p->plane();
     // ---- choose between holding every w_n in HBM and two-level checkpointing --------------------------
     size_t budget = p->mem_limit;
     if (!budget) {
         size_t fr = 0, tot = 0;
         FWI_CUDA(cudaMemGetInfo(&fr, &tot));
-        budget = (size_t)((fr + (p->snap_steps + 2 * p->ckpt_slots) * pl * sizeof(float)) * 0.85);
+        budget = (size_t)((fr + (p->snap_steps + p->ckpt_slots) * sizeof(float)) * 0.85);   // both capacities are in floats
     }
     const size_t max_planes = budget / (pl * sizeof(float));
     int seg = nt, nseg = 1;
@@ -601,78 +759,34 @@ int fwi_fd2d_gradient(fwi_fd2d* p, const float* wavelet_dev, const float* obs_de
         nseg = (nt + seg - 1) / seg;
         FWI_REQUIRE((size_t)seg + 2 * (size_t)nseg <= max_planes, "fwi_fd2d_gradient: %zu bytes are not enough even with checkpointing (need %zu planes of %zu bytes)", budget, (size_t)seg + 2 * (size_t)nseg, pl * sizeof(float));
     }
-    if (p->snap_steps < (size_t)seg) {
-        if (p->snap) cudaFree(p->snap);
-        p->snap = nullptr; p->snap_steps = 0;
-        FWI_CUDA(cudaMalloc(&p->snap, (size_t)seg * pl * sizeof(float)));
-        p->snap_steps = seg;
-    }
-    if (nseg > 1 && p->ckpt_slots < (size_t)nseg) {
-        if (p->ckpt) cudaFree(p->ckpt);
-        p->ckpt = nullptr; p->ckpt_slots = 0;
-        FWI_CUDA(cudaMalloc(&p->ckpt, (size_t)nseg * 2 * pl * sizeof(float)));
-        p->ckpt_slots = nseg;
-    }
+    int rc;
+    if ((rc = ensure_floats(p, &p->snap, &p->snap_steps, (size_t)seg * pl))) return rc;     // snap_steps counts floats here
+    if (nseg > 1 && (rc = ensure_floats(p, &p->ckpt, &p->ckpt_slots, (size_t)nseg * 2 * pl))) return rc;
     const size_t ntr = (size_t)nt * p->nrec;
-    int rc = ensure_bytes(&p->resid, &p->resid_cap, ntr);
-    if (rc) return rc;
-    float* syn = traces_dev;
-    if (!syn) { rc = ensure_bytes(&p->syn, &p->syn_cap, ntr); if (rc) return rc; syn = p->syn; }
+    if ((rc = ensure_floats(p, &p->resid, &p->resid_cap, ntr))) return rc;
+    if ((rc = ensure_floats(p, &p->syn, &p->syn_cap, ntr))) return rc;
+    if ((rc = ensure_floats(p, &p->obs, &p->obs_cap, ntr))) return rc;
+    if ((rc = ensure_floats(p, &p->wav, &p->wav_cap, (size_t)nt * p->nsrc))) return rc;
 
-    // ---- forward -----------------------------------------------------------------------------------------
-    FWI_CUDA(cudaMemsetAsync(p->fld[0], 0, pl * sizeof(float), st));
-    FWI_CUDA(cudaMemsetAsync(p->fld[1], 0, pl * sizeof(float), st));
-    int cur = 0;
-    std::vector<int> seg_cur(nseg, 0);
-    if (nseg == 1) {
-        rc = run_forward(p, wavelet_dev, 0, nt, syn, true, 0, cur, st);
-        if (rc) return rc;
-    } else {
-        for (int s = 0; s < nseg; ++s) {
-            FWI_CUDA(cudaMemcpyAsync(p->ckpt + (size_t)(2 * s) * pl, p->fld[cur], pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            FWI_CUDA(cudaMemcpyAsync(p->ckpt + (size_t)(2 * s + 1) * pl, p->fld[cur ^ 1], pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            seg_cur[s] = cur;
-            rc = run_forward(p, wavelet_dev, s * seg, std::min(nt, (s + 1) * seg), syn, false, 0, cur, st);
-            if (rc) return rc;
-        }
-    }
-    p->fwd_cur = cur;
-    // ---- residual + misfit -----------------------------------------------------------------------------
-    FWI_CUDA(cudaMemsetAsync(p->d_J, 0, sizeof(double), st));
-    fd_residual_kernel<<<(unsigned)std::min<size_t>(1024, (ntr + 255) / 256), 256, 0, st>>>(syn, obs_dev, (int64_t)ntr, p->resid, p->d_J);
-    FWI_CUDA(cudaGetLastError());
-    p->launches += 2;      // residual + gradient finalize
-    // ---- adjoint + imaging -------------------------------------------------------------------------------
-    FWI_CUDA(cudaMemsetAsync(p->fld[2], 0, pl * sizeof(float), st));
-    FWI_CUDA(cudaMemsetAsync(p->fld[3], 0, pl * sizeof(float), st));
-    FWI_CUDA(cudaMemsetAsync(p->acc, 0, pl * sizeof(float), st));
-    int acur = 0;
-    if (nseg == 1) {
-        rc = run_adjoint(p, p->resid, 0, nt, 0, acur, st);
-        if (rc) return rc;
-    } else {
-        for (int s = nseg - 1; s >= 0; --s) {
-            const int n0 = s * seg, n1 = std::min(nt, (s + 1) * seg);
-            int c = seg_cur[s];
-            FWI_CUDA(cudaMemcpyAsync(p->fld[c], p->ckpt + (size_t)(2 * s) * pl, pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            FWI_CUDA(cudaMemcpyAsync(p->fld[c ^ 1], p->ckpt + (size_t)(2 * s + 1) * pl, pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            rc = run_forward(p, wavelet_dev, n0, n1, nullptr, true, n0, c, st);     // recompute w_n for this segment
-            if (rc) return rc;
-            rc = run_adjoint(p, p->resid, n0, n1, n0, acur, st);
-            if (rc) return rc;
-        }
-    }
+    if ((rc = enter(p, user))) return rc;
+    FWI_CUDA(cudaMemcpyAsync(p->wav, wavelet_dev, (size_t)nt * p->nsrc * sizeof(float), cudaMemcpyDeviceToDevice, p->work));
+    FWI_CUDA(cudaMemcpyAsync(p->obs, obs_dev, ntr * sizeof(float), cudaMemcpyDeviceToDevice, p->work));
+    rc = run_cached(p, 1, nt, seg, nseg, [&](cudaStream_t st) { return record_gradient(p, nt, seg, nseg, st); });
+    if (rc) return rc;
+    p->fwd_cur = nt & 1;
     dim3 grid((p->nx + 127) / 128, p->nz);
-    fd_grad_finalize_kernel<<<grid, 128, 0, st>>>(p->acc, p->vp, p->nz, p->nx, p->px, grad_dev);
+    fd_grad_finalize_kernel<<<grid, 128, 0, p->work>>>(p->acc, p->vp, p->nz, p->nx, p->px, grad_dev);
     FWI_CUDA(cudaGetLastError());
-    if (misfit_host) {
-        FWI_CUDA(cudaMemcpyAsync(misfit_host, p->d_J, sizeof(double), cudaMemcpyDeviceToHost, st));
-        FWI_CUDA(cudaStreamSynchronize(st));
-    }
+    p->launches += 1;
+    if (traces_dev) FWI_CUDA(cudaMemcpyAsync(traces_dev, p->syn, ntr * sizeof(float), cudaMemcpyDeviceToDevice, p->work));
+    if (misfit_host) FWI_CUDA(cudaMemcpyAsync(misfit_host, p->d_J, sizeof(double), cudaMemcpyDeviceToHost, p->work));
+    if ((rc = leave(p, user))) return rc;
+    if (misfit_host) FWI_CUDA(cudaStreamSynchronize(p->work));
     return FWI_OK;
 }
 
 int64_t fwi_fd2d_launch_count(fwi_fd2d* p) { return p ? p->launches : 0; }
+
 
 int fwi_fd_misfit(const float* syn_dev, const float* obs_dev, int64_t n, float* resid_dev, double* misfit_host, void* stream) {
     FWI_REQUIRE(syn_dev && obs_dev && resid_dev && misfit_host && n >= 0, "fwi_fd_misfit: bad arguments");

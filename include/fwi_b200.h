@@ -132,12 +132,14 @@ typedef struct fwi_fd2d fwi_fd2d;
  * accumulator and the TMA descriptors. */
 int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, float alpha, fwi_fd2d** out);
 int fwi_fd2d_destroy(fwi_fd2d* plan);
-/* Select the one-tile-per-CTA step kernel with bz tile rows and nw warps per CTA (cross-check / tuning
- * variant).  Clears the geometry. */
+/* Select the one-tile-per-CTA step kernel with bz tile rows and nw warps per CTA (default: 16 x 2).
+ * Clears the geometry. */
 int fwi_fd2d_set_tile(fwi_fd2d* plan, int bz, int nw);
-/* Select the persistent streaming step kernel (the default) with nw warps per SM and nc TMA pipeline slots
- * per warp.  Clears the geometry. */
+/* Select the persistent streaming step kernel with nw warps per SM and nc TMA pipeline slots per warp.
+ * Clears the geometry. */
 int fwi_fd2d_set_stream(fwi_fd2d* plan, int nw, int nc);
+/* Replay the time loops as cached CUDA graphs (default on) or as individual launches (0). */
+int fwi_fd2d_set_graphs(fwi_fd2d* plan, int enable);
 /* Cap (bytes) on the forward-field storage used by fwi_fd2d_gradient; 0 = 85 % of free HBM.  When all nt
  * snapshots do not fit, the gradient switches to two-level checkpointing (recompute per segment). */
 int fwi_fd2d_set_memory_limit(fwi_fd2d* plan, uint64_t bytes);

@@ -88,3 +88,22 @@ def test_update_and_fwi_reduce_misfit():
     v1, hist = fo.fwi(v0, h, dt, shots, wav, observed, 3, 1500.0, 3000.0, nabs=6)
     assert hist[-1] < hist[0]
     assert v1.min() >= 1500.0 and v1.max() <= 3000.0
+
+
+def test_c_port_matches_numpy_oracle():
+    """oracle/fd_oracle_c.c (the multi-threaded CPU-baseline port) against the NumPy self-oracle."""
+    from oracle import fd_oracle_c as foc
+    rng = np.random.default_rng(2)
+    nz, nx, nt = 40, 70, 90
+    v = (2000.0 + 400.0 * rng.random((nz, nx))).astype(np.float32)
+    h = 10.0
+    dt = fo.stable_dt(float(v.max()), h, 2)
+    src, rec = [(5, 20), (7, 50)], [(4, x) for x in range(2, nx - 2, 3)]
+    wav = np.stack([fo.ricker(nt, dt, 25.0), 0.7 * fo.ricker(nt, dt, 20.0)], 1).astype(np.float32)
+    obs = fo.Problem(v.astype(np.float64) * 1.03, h, dt, src, rec, nabs=8).forward(wav.astype(np.float64))
+    J0, g0, tr0 = fo.Problem(v.astype(np.float64), h, dt, src, rec, nabs=8).misfit_and_gradient(wav.astype(np.float64), obs)
+    J1, g1, tr1 = foc.misfit_and_gradient(v, h, dt, src, rec, wav, obs, nabs=8)
+    assert np.linalg.norm(tr1 - tr0) / np.linalg.norm(tr0) < 1e-5
+    assert np.linalg.norm(g1 - g0) / np.linalg.norm(g0) < 1e-4
+    assert abs(J1 - J0) < 1e-4 * J0
+    assert foc.num_threads() >= 1
