@@ -130,7 +130,7 @@ def cpu_stencil_rate(w, seconds_target=12.0):
         n_steps = 4
         t = foc.time_forward_adjoint(w["v"], w["h"], w["dt"], w["nabs"], w["alpha"], n_steps)
         n_steps = max(4, int(seconds_target / max(t / n_steps, 1e-6)))
-        n_steps = min(n_steps, 400)
+        n_steps = min(n_steps, 4000)
         t = foc.time_forward_adjoint(w["v"], w["h"], w["dt"], w["nabs"], w["alpha"], n_steps)
         rate = 2.0 * n_steps * nz * nx / t
         return rate, cores, "port", "oracle/fd_oracle_c.c (pthreads): %d forward-with-save + %d adjoint steps on the full %dx%d grid, %.1f s" % (n_steps, n_steps, nz, nx, t)
@@ -324,7 +324,7 @@ def run_b200(args):
                     "misfit_last_step": J_last},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "kernel": "fd2d_stream_kernel (forward-save and adjoint-image variants, averaged)" if not tile else "fd2d_step_kernel (tiled; forward-save and adjoint-image variants, averaged)",
+                         "kernel": ("fd2d_stream_kernel" if stream else "fd2d_step_kernel") + " (forward-save and adjoint-image variants, averaged)",
                          "algorithmic_bytes_per_launch": 16 * nz * nx,
                          "avg_launch_us": avg_launch_s * 1e6,
                          "note": "16 B per point-update (SURVEY 8d) over the mean step-kernel time incl. launch gaps; the snapshot stream adds 4 B/pt of real HBM traffic per step on top"},

@@ -161,8 +161,9 @@ def test_size_independent_properties_at_scale(ac):
     prop.set_geometry([a], [b, (500, 2500)])
     t1 = prop.forward(wav).cpu().numpy()
     t2 = prop.forward(2.0 * wav).cpu().numpy()
-    # linearity: exact for a power of two, except where the leading edge passes through the denormal range
-    assert np.max(np.abs(t2.astype(np.float64) - 2.0 * t1)) <= 1e-30
+    # linearity. Not bit-exact even for a power of two: the numerical precursor passes through the denormal range,
+    # where scaling is inexact, and from then on the two runs carry independent fp32 rounding noise.
+    assert rel_l2(t2, 2.0 * t1) <= 2e-5
     t2 = prop.forward(2.5 * wav).cpu().numpy()
     assert rel_l2(t2, 2.5 * t1) <= 2e-5                                    # linearity up to fp32 rounding noise
     assert np.all(t1[:, 1] == 0.0)                                         # causality: ~19 km away, not reached in 600 steps
