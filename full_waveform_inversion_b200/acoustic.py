@@ -36,6 +36,8 @@ _lib.register({
     "fwi_fd2d_wavefield": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "fwi_fd2d_gradient": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, POINTER(c_double), c_void_p]),
     "fwi_fd2d_launch_count": (c_int64, [c_void_p]),
+    "fwi_fd3d_create": (c_int, [c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_float, POINTER(c_void_p)]),
+    "fwi_fd3d_set_geometry": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "fwi_fd_misfit": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_double), c_void_p]),
     "fwi_fd_model_update": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_void_p]),
     "fwi_fd_absmax": (c_int, [c_void_p, c_int64, POINTER(c_float), c_void_p]),
@@ -68,19 +70,26 @@ def _points(pts, ndim):
     return [np.ascontiguousarray(a[:, k]) for k in range(ndim)]
 
 
-class Propagator2D:
-    """One GPU's 2-D propagator plan (wraps ``fwi_fd2d``): model, sponge, wavefields, TMA descriptors."""
-
-    ndim = 2
+class Propagator:
+    """One GPU's propagator plan (wraps ``fwi_fd2d``; 2-D or 3-D by the length of `shape`): model, sponge,
+    wavefields, TMA descriptors, cached CUDA graphs."""
 
     def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=0, tile=None, memory_limit=0, stream=None, graphs=True):
         self._lib = _lib.require_gpu()
-        self.nz, self.nx = int(shape[0]), int(shape[1])
+        self.shape = tuple(int(n) for n in shape)
+        self.ndim = len(self.shape)
+        if self.ndim not in (2, 3):
+            raise ValueError("grid must be 2-D (nz, nx) or 3-D (nz, ny, nx)")
+        self.nz, self.nx = self.shape[0], self.shape[-1]
         self.h, self.dt = float(h), float(dt)
         self.device = int(device)
         self._h = c_void_p()
-        check(self._lib.fwi_fd2d_create(self.device, self.nz, self.nx, self.h, self.dt, int(nabs), float(alpha),
-                                        ctypes.byref(self._h)))
+        if self.ndim == 2:
+            check(self._lib.fwi_fd2d_create(self.device, self.nz, self.nx, self.h, self.dt, int(nabs), float(alpha),
+                                            ctypes.byref(self._h)))
+        else:
+            check(self._lib.fwi_fd3d_create(self.device, self.nz, self.shape[1], self.nx, self.h, self.dt, int(nabs),
+                                            float(alpha), ctypes.byref(self._h)))
         if tile is not None:
             check(self._lib.fwi_fd2d_set_tile(self._h, int(tile[0]), int(tile[1])))
         if stream is not None:
@@ -107,18 +116,19 @@ class Propagator2D:
 
     def set_model(self, v):
         v = _dev_f32(v, self.torch_device)
-        if tuple(v.shape) != (self.nz, self.nx):
-            raise ValueError("velocity grid %s does not match the plan (%d, %d)" % (tuple(v.shape), self.nz, self.nx))
+        if tuple(v.shape) != self.shape:
+            raise ValueError("velocity grid %s does not match the plan %s" % (tuple(v.shape), self.shape))
         with torch.cuda.device(self.device):
             check(self._lib.fwi_fd2d_set_model(self._h, ptr(v), current_stream()))
         self._v = v
 
     def set_geometry(self, src, rec):
-        sz, sx = _points(src, 2)
-        rz, rx = _points(rec, 2)
-        check(self._lib.fwi_fd2d_set_geometry(self._h, len(sz), sz.ctypes.data_as(c_void_p), sx.ctypes.data_as(c_void_p),
-                                              len(rz), rz.ctypes.data_as(c_void_p), rx.ctypes.data_as(c_void_p)))
-        self.nsrc, self.nrec = len(sz), len(rz)
+        s_ = _points(src, self.ndim)
+        r_ = _points(rec, self.ndim)
+        fn = self._lib.fwi_fd2d_set_geometry if self.ndim == 2 else self._lib.fwi_fd3d_set_geometry
+        check(fn(self._h, len(s_[0]), *[a.ctypes.data_as(c_void_p) for a in s_],
+                 len(r_[0]), *[a.ctypes.data_as(c_void_p) for a in r_]))
+        self.nsrc, self.nrec = len(s_[0]), len(r_[0])
 
     def _wavelet(self, wavelet):
         w = _dev_f32(wavelet, self.torch_device)
@@ -138,7 +148,7 @@ class Propagator2D:
         return traces
 
     def wavefield(self, which=0):
-        out = torch.empty((self.nz, self.nx), dtype=torch.float32, device=self.torch_device)
+        out = torch.empty(self.shape, dtype=torch.float32, device=self.torch_device)
         with torch.cuda.device(self.device):
             check(self._lib.fwi_fd2d_wavefield(self._h, which, ptr(out), current_stream()))
         return out
@@ -151,7 +161,7 @@ class Propagator2D:
         if tuple(obs.shape) != (nt, self.nrec):
             raise ValueError("observed traces %s do not match (nt=%d, nrec=%d)" % (tuple(obs.shape), nt, self.nrec))
         if grad is None:
-            grad = torch.zeros((self.nz, self.nx), dtype=torch.float32, device=self.torch_device)
+            grad = torch.zeros(self.shape, dtype=torch.float32, device=self.torch_device)
         traces = torch.empty((nt, self.nrec), dtype=torch.float32, device=self.torch_device) if want_traces else None
         J = c_double(0.0)
         with torch.cuda.device(self.device):
@@ -163,11 +173,12 @@ class Propagator2D:
         return int(self._lib.fwi_fd2d_launch_count(self._h))
 
 
+Propagator2D = Propagator
+Propagator3D = Propagator
+
+
 def _make_propagator(shape, h, dt, nabs, alpha, device, **kw):
-    if len(shape) == 2:
-        return Propagator2D(shape, h, dt, nabs, alpha, device, **kw)
-    from .acoustic3d import Propagator3D
-    return Propagator3D(shape, h, dt, nabs, alpha, device, **kw)
+    return Propagator(shape, h, dt, nabs, alpha, device, **kw)
 
 
 # ------------------------------------------------------------------------------------------------ entry points

@@ -25,6 +25,7 @@ namespace fwi {
 enum { STEP_FWD = 0, STEP_FWD_SAVE = 1, STEP_ADJ = 2 };
 }  // namespace fwi
 #include "fd2d_stream.cuh"
+#include "fd3d.cuh"
 namespace fwi {
 
 struct Step2DArgs {
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constan
 // ------------------------------------------------------------------------------------------ small kernels
 __global__ void fd_model_kernel(const float* __restrict__ v, int nz, int nx, int px, float dt_over_h,
                                 float* __restrict__ m, float* __restrict__ vp) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+    const int x = blockIdx.y * blockDim.x + threadIdx.x, z = blockIdx.x;   // rows on grid.x (no 65535 limit)
     if (x >= px || z >= nz) return;
     float val = 0.f, vv = 0.f;
     if (x < nx) { vv = v[(size_t)z * nx + x]; const float c = vv * dt_over_h; val = c * c; }
@@ -154,14 +155,14 @@ __global__ void fd_model_kernel(const float* __restrict__ v, int nz, int nx, int
 
 __global__ void fd_grad_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ vp, int nz, int nx,
                                         int px, float* __restrict__ grad) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+    const int x = blockIdx.y * blockDim.x + threadIdx.x, z = blockIdx.x;   // rows on grid.x (no 65535 limit)
     if (x >= nx || z >= nz) return;
     const size_t o = (size_t)z * px + x;
     grad[(size_t)z * nx + x] += 2.0f * acc[o] / vp[o];                 // dJ/dv = (2/v) I
 }
 
 __global__ void fd_unpitch_kernel(const float* __restrict__ src, int nz, int nx, int px, float* __restrict__ dst) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+    const int x = blockIdx.y * blockDim.x + threadIdx.x, z = blockIdx.x;   // rows on grid.x (no 65535 limit)
     if (x < nx && z < nz) dst[(size_t)z * nx + x] = src[(size_t)z * px + x];
 }
 
@@ -259,8 +260,11 @@ struct GraphEntry {
 }  // namespace
 
 struct fwi_fd2d {
-    int device = 0, nz = 0, nx = 0, px = 0, nabs = 0;
+    int device = 0, nz = 0, ny = 1, nx = 0, px = 0, nabs = 0;   // ny == 1: 2-D plan; rows() = nz * ny
     float h = 0, dt = 0, alpha = 0;
+    int tiles_y = 1, zchunk = 0, nzch = 1;                      // 3-D tiling: 128 x 16 columns, z chunks
+    float* gy = nullptr;
+    CUtensorMap tm3[4];
     int bz = 16, nw = 2;              // tiled variant: tile rows / warps per CTA (tunable)
     int tiles_x = 0, tiles_z = 0;
     int variant = 0;                  // 0 = one-tile-per-CTA kernel (default), 1 = persistent streaming kernel
@@ -290,7 +294,8 @@ struct fwi_fd2d {
     cudaStream_t work = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     std::vector<GraphEntry> graphs;
-    size_t plane() const { return (size_t)nz * px; }
+    int rows() const { return nz * ny; }
+    size_t plane() const { return (size_t)nz * ny * px; }
 };
 
 static void drop_graphs(fwi_fd2d* p) {
@@ -299,6 +304,7 @@ static void drop_graphs(fwi_fd2d* p) {
 }
 
 static int make_stream_partition(fwi_fd2d* p) {
+    if (p->ny > 1) return FWI_OK;
     p->nstrips = (p->nx + 127) / 128;
     p->W = p->sm_count * p->snw;
     const int64_t U = (int64_t)p->nstrips * p->nz;
@@ -321,7 +327,26 @@ static int make_stream_partition(fwi_fd2d* p) {
     return encode_tiled_f32(&p->tm_m_s, p->m, 2, dims_p, strides, box_r);
 }
 
+static int make_tmaps3(fwi_fd2d* p) {
+    p->tiles_x = (p->nx + k3BX - 1) / k3BX;
+    p->tiles_y = (p->ny + k3BY - 1) / k3BY;
+    const int target = 6 * p->sm_count;                         // ~3 waves of 2 resident CTAs per SM
+    int nzch = (target + p->tiles_x * p->tiles_y - 1) / (p->tiles_x * p->tiles_y);
+    nzch = std::max(1, std::min(nzch, std::max(1, p->nz / 16)));
+    p->zchunk = (p->nz + nzch - 1) / nzch;
+    p->nzch = (p->nz + p->zchunk - 1) / p->zchunk;
+    for (int i = 0; i < 4; ++i) {
+        const uint64_t dims[3] = {(uint64_t)p->nx, (uint64_t)p->ny, (uint64_t)p->nz};
+        const uint64_t strides[2] = {(uint64_t)p->px * sizeof(float), (uint64_t)p->px * p->ny * sizeof(float)};
+        const uint32_t box[3] = {(uint32_t)k3SX, (uint32_t)k3SY, 1u};
+        int rc = encode_tiled_f32(&p->tm3[i], p->fld[i], 3, dims, strides, box);
+        if (rc) return rc;
+    }
+    return FWI_OK;
+}
+
 static int make_tmaps(fwi_fd2d* p) {
+    if (p->ny > 1) return make_tmaps3(p);
     for (int i = 0; i < 4; ++i) {
         const uint64_t dims[2] = {(uint64_t)p->nx, (uint64_t)p->nz};
         const uint64_t strides[1] = {(uint64_t)p->px * sizeof(float)};
@@ -333,24 +358,27 @@ static int make_tmaps(fwi_fd2d* p) {
 }
 
 // bin that owns grid point (z, x): the CTA tile (tiled variant) or the warp whose row-unit range holds it
-static int owner_bin(const fwi_fd2d* p, int z, int x) {
+static int owner_bin(const fwi_fd2d* p, int z, int y, int x) {
+    if (p->ny > 1) return ((z / p->zchunk) * p->tiles_y + y / k3BY) * p->tiles_x + x / k3BX;
     if (p->variant == 0) return (z / p->bz) * p->tiles_x + x / kBX;
     const int u = (x / 128) * p->nz + z;
     return (int)(std::upper_bound(p->h_u0.begin(), p->h_u0.end(), u) - p->h_u0.begin()) - 1;
 }
 
-static int build_point_list(fwi_fd2d* p, PointList& pl, int n, const int* iz, const int* ix, const char* what) {
-    const int nbins = (p->variant == 0) ? p->tiles_x * p->tiles_z : p->W;
+static int build_point_list(fwi_fd2d* p, PointList& pl, int n, const int* iz, const int* iy, const int* ix, const char* what) {
+    const int nbins = (p->ny > 1) ? p->tiles_x * p->tiles_y * p->nzch : ((p->variant == 0) ? p->tiles_x * p->tiles_z : p->W);
     std::vector<int> tile_ptr(nbins + 1, 0), off(std::max(n, 1)), id(std::max(n, 1));
     for (int i = 0; i < n; ++i) {
-        FWI_REQUIRE(iz[i] >= 0 && iz[i] < p->nz && ix[i] >= 0 && ix[i] < p->nx, "%s %d at (z=%d, x=%d) is outside the %d x %d grid", what, i, iz[i], ix[i], p->nz, p->nx);
-        tile_ptr[owner_bin(p, iz[i], ix[i]) + 1]++;
+        const int yy = iy ? iy[i] : 0;
+        FWI_REQUIRE(iz[i] >= 0 && iz[i] < p->nz && ix[i] >= 0 && ix[i] < p->nx && yy >= 0 && yy < p->ny, "%s %d at (z=%d, y=%d, x=%d) is outside the %d x %d x %d grid", what, i, iz[i], yy, ix[i], p->nz, p->ny, p->nx);
+        tile_ptr[owner_bin(p, iz[i], yy, ix[i]) + 1]++;
     }
     for (int t = 0; t < nbins; ++t) tile_ptr[t + 1] += tile_ptr[t];
     std::vector<int> fill(tile_ptr.begin(), tile_ptr.end() - 1);
     for (int i = 0; i < n; ++i) {
-        const int e = fill[owner_bin(p, iz[i], ix[i])]++;
-        off[e] = iz[i] * p->px + ix[i];
+        const int yy = iy ? iy[i] : 0;
+        const int e = fill[owner_bin(p, iz[i], yy, ix[i])]++;
+        off[e] = (iz[i] * p->ny + yy) * p->px + ix[i];
         id[e] = i;
     }
     if (pl.nbins != nbins || pl.cap < std::max(n, 1)) {     // allocations change -> cached graphs hold stale pointers
@@ -416,9 +444,27 @@ static int launch_stream_cfg(fwi_fd2d* p, int mode, int cur, int oldidx, const P
     return FWI_OK;
 }
 
+static int launch_step3(fwi_fd2d* p, int mode, int cur, float* oldnew, const PointList* inj, const float* inj_vals,
+                        const PointList* rec, float* rec_out, float* snap, cudaStream_t st) {
+    Step3DArgs a{};
+    a.oldnew = oldnew; a.m = p->m; a.gx = p->gx; a.gy = p->gy; a.gz = p->gz; a.snap = snap; a.acc = p->acc;
+    a.nx = p->nx; a.ny = p->ny; a.nz = p->nz; a.px = p->px; a.zchunk = p->zchunk;
+    a.inj = (inj && inj->n) ? inj->dev() : PointListDev{nullptr, nullptr, nullptr};
+    a.inj_vals = inj_vals;
+    a.rec = (rec && rec->n) ? rec->dev() : PointListDev{nullptr, nullptr, nullptr};
+    a.rec_out = rec_out;
+    const dim3 grid(p->tiles_x, p->tiles_y, p->nzch), block((k3CW + 1) * 32);
+    const size_t smem = (size_t)k3NP * k3PlaneFloats * sizeof(float);
+    if (mode == STEP_FWD) fd3d_step_kernel<STEP_FWD><<<grid, block, smem, st>>>(p->tm3[cur], a);
+    else if (mode == STEP_FWD_SAVE) fd3d_step_kernel<STEP_FWD_SAVE><<<grid, block, smem, st>>>(p->tm3[cur], a);
+    else fd3d_step_kernel<STEP_ADJ><<<grid, block, smem, st>>>(p->tm3[cur], a);
+    return FWI_OK;
+}
+
 static int launch_step(fwi_fd2d* p, int mode, int cur, float* oldnew, const PointList* inj, const float* inj_vals,
                        const PointList* rec, float* rec_out, float* snap, cudaStream_t st) {
     p->launches++;
+    if (p->ny > 1) return launch_step3(p, mode, cur, oldnew, inj, inj_vals, rec, rec_out, snap, st);
     if (p->variant == 1) {
         int oldidx = -1;
         for (int i = 0; i < 4; ++i) if (p->fld[i] == oldnew) oldidx = i;
@@ -571,9 +617,10 @@ static int leave(fwi_fd2d* p, cudaStream_t user) {       // ... and the caller's
 
 extern "C" {
 
-int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, float alpha, fwi_fd2d** out) {
-    FWI_REQUIRE(out != nullptr, "fwi_fd2d_create: out is NULL");
-    FWI_REQUIRE(nz >= 1 && nx >= 1, "fwi_fd2d_create: grid must be at least 1 x 1 (got %d x %d)", nz, nx);
+static int create_plan(int device, int nz, int ny, int nx, float h, float dt, int nabs, float alpha, fwi_fd2d** out) {
+    FWI_REQUIRE(out != nullptr, "fwi_fd_create: out is NULL");
+    FWI_REQUIRE(nz >= 1 && nx >= 1 && ny >= 1, "fwi_fd_create: grid must be at least 1 x 1 (got %d x %d x %d)", nz, ny, nx);
+    FWI_REQUIRE((int64_t)nz * ny * ((nx + 31) & ~31) < (int64_t)2147483647, "fwi_fd_create: grid too large for 32-bit point offsets");
     FWI_REQUIRE(h > 0.f && dt > 0.f, "fwi_fd2d_create: h and dt must be positive");
     FWI_REQUIRE(nabs >= 0 && alpha >= 0.f, "fwi_fd2d_create: nabs and alpha must be non-negative");
     int ndev = 0;
@@ -581,7 +628,7 @@ int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, flo
     FWI_REQUIRE(device >= 0 && device < ndev, "fwi_fd2d_create: device %d out of range (%d visible)", device, ndev);
     DeviceGuard g(device);
     auto* p = new fwi_fd2d();
-    p->device = device; p->nz = nz; p->nx = nx; p->h = h; p->dt = dt; p->nabs = nabs; p->alpha = alpha;
+    p->device = device; p->nz = nz; p->ny = ny; p->nx = nx; p->h = h; p->dt = dt; p->nabs = nabs; p->alpha = alpha;
     p->px = (nx + 31) & ~31;
     p->tiles_x = (nx + kBX - 1) / kBX;
     p->tiles_z = (nz + p->bz - 1) / p->bz;
@@ -595,6 +642,7 @@ int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, flo
     for (int i = 0; i < 4; ++i) { FWI_CUDA(cudaMalloc(&p->fld[i], pl * sizeof(float))); FWI_CUDA(cudaMemset(p->fld[i], 0, pl * sizeof(float))); }
     FWI_CUDA(cudaMalloc(&p->gx, p->px * sizeof(float)));
     FWI_CUDA(cudaMalloc(&p->gz, nz * sizeof(float)));
+    FWI_CUDA(cudaMalloc(&p->gy, ny * sizeof(float)));
     FWI_CUDA(cudaMalloc(&p->d_J, sizeof(double)));
     // sponge profiles (oracle/fd_oracle.py sponge_profile), float64 on the host then rounded once
     auto profile = [&](int n, int padded) {
@@ -607,7 +655,8 @@ int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, flo
         }
         return prof;
     };
-    std::vector<float> gxh = profile(nx, p->px), gzh = profile(nz, nz);
+    std::vector<float> gxh = profile(nx, p->px), gzh = profile(nz, nz), gyh = (ny > 1) ? profile(ny, ny) : std::vector<float>(1, 1.0f);
+    FWI_CUDA(cudaMemcpy(p->gy, gyh.data(), ny * sizeof(float), cudaMemcpyHostToDevice));
     FWI_CUDA(cudaMemcpy(p->gx, gxh.data(), p->px * sizeof(float), cudaMemcpyHostToDevice));
     FWI_CUDA(cudaMemcpy(p->gz, gzh.data(), nz * sizeof(float), cudaMemcpyHostToDevice));
     cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -616,8 +665,21 @@ int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, flo
     rc = make_stream_partition(p);
     if (rc) return rc;
     if ((rc = stream_attrs<8, 4>()) || (rc = stream_attrs<4, 8>()) || (rc = stream_attrs<6, 5>()) || (rc = stream_attrs<8, 3>()) || (rc = stream_attrs<12, 3>())) return rc;
+    const int smem3 = k3NP * k3PlaneFloats * (int)sizeof(float);
+    FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     *out = p;
     return FWI_OK;
+}
+
+int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, float alpha, fwi_fd2d** out) {
+    return create_plan(device, nz, 1, nx, h, dt, nabs, alpha, out);
+}
+
+int fwi_fd3d_create(int device, int nz, int ny, int nx, float h, float dt, int nabs, float alpha, fwi_fd2d** out) {
+    FWI_REQUIRE(ny >= 2, "fwi_fd3d_create: ny must be >= 2 (use fwi_fd2d_create for 2-D grids)");
+    return create_plan(device, nz, ny, nx, h, dt, nabs, alpha, out);
 }
 
 int fwi_fd2d_destroy(fwi_fd2d* p) {
@@ -625,7 +687,7 @@ int fwi_fd2d_destroy(fwi_fd2d* p) {
     DeviceGuard g(p->device);
     if (p->work) cudaStreamSynchronize(p->work);
     drop_graphs(p);
-    cudaFree(p->m); cudaFree(p->vp); cudaFree(p->acc); cudaFree(p->gx); cudaFree(p->gz); cudaFree(p->d_J);
+    cudaFree(p->m); cudaFree(p->vp); cudaFree(p->acc); cudaFree(p->gx); cudaFree(p->gz); cudaFree(p->gy); cudaFree(p->d_J);
     for (int i = 0; i < 4; ++i) cudaFree(p->fld[i]);
     if (p->snap) cudaFree(p->snap);
     if (p->ckpt) cudaFree(p->ckpt);
@@ -646,6 +708,7 @@ int fwi_fd2d_set_stream(fwi_fd2d* p, int nw, int nc) {
     FWI_REQUIRE(p, "fwi_fd2d_set_stream: NULL plan");
     const bool ok = (nw == 8 && nc == 4) || (nw == 4 && nc == 8) || (nw == 6 && nc == 5) || (nw == 8 && nc == 3) || (nw == 12 && nc == 3);
     FWI_REQUIRE(ok, "fwi_fd2d_set_stream: unsupported (nw=%d, nc=%d)", nw, nc);
+    FWI_REQUIRE(p->ny == 1, "fwi_fd2d_set_stream: 2-D plans only");
     DeviceGuard g(p->device);
     FWI_CUDA(cudaStreamSynchronize(p->work));
     drop_graphs(p);
@@ -658,6 +721,7 @@ int fwi_fd2d_set_tile(fwi_fd2d* p, int bz, int nw) {
     FWI_REQUIRE(p, "fwi_fd2d_set_tile: NULL plan");
     const bool ok = (bz == 32 && (nw == 4 || nw == 8)) || (bz == 16 && (nw == 4 || nw == 2)) || (bz == 64 && (nw == 8 || nw == 4));
     FWI_REQUIRE(ok, "fwi_fd2d_set_tile: unsupported (bz=%d, nw=%d)", bz, nw);
+    FWI_REQUIRE(p->ny == 1, "fwi_fd2d_set_tile: 2-D plans only");
     DeviceGuard g(p->device);
     FWI_CUDA(cudaStreamSynchronize(p->work));
     drop_graphs(p);
@@ -685,24 +749,38 @@ int fwi_fd2d_set_model(fwi_fd2d* p, const float* v_dev, void* stream) {
     cudaStream_t user = (cudaStream_t)stream;
     int rc = enter(p, user);
     if (rc) return rc;
-    dim3 grid((p->px + 127) / 128, p->nz);
-    fd_model_kernel<<<grid, 128, 0, p->work>>>(v_dev, p->nz, p->nx, p->px, p->dt / p->h, p->m, p->vp);
+    dim3 grid(p->rows(), (p->px + 127) / 128);
+    fd_model_kernel<<<grid, 128, 0, p->work>>>(v_dev, p->rows(), p->nx, p->px, p->dt / p->h, p->m, p->vp);
     FWI_CUDA(cudaGetLastError());
     p->model_set = true;
     return leave(p, user);
 }
 
-int fwi_fd2d_set_geometry(fwi_fd2d* p, int nsrc, const int* src_z, const int* src_x, int nrec, const int* rec_z,
-                          const int* rec_x) {
-    FWI_REQUIRE(p, "fwi_fd2d_set_geometry: NULL plan");
-    FWI_REQUIRE(nsrc >= 0 && nrec >= 0 && (nsrc == 0 || (src_z && src_x)) && (nrec == 0 || (rec_z && rec_x)), "fwi_fd2d_set_geometry: bad arguments");
+static int set_geometry(fwi_fd2d* p, int nsrc, const int* src_z, const int* src_y, const int* src_x, int nrec,
+                        const int* rec_z, const int* rec_y, const int* rec_x) {
+    FWI_REQUIRE(p, "fwi_fd_set_geometry: NULL plan");
+    FWI_REQUIRE(nsrc >= 0 && nrec >= 0 && (nsrc == 0 || (src_z && src_x)) && (nrec == 0 || (rec_z && rec_x)), "fwi_fd_set_geometry: bad arguments");
     DeviceGuard g(p->device);
-    int rc = build_point_list(p, p->src, nsrc, src_z, src_x, "source");
+    if (nsrc != p->nsrc || nrec != p->nrec) drop_graphs(p);
+    int rc = build_point_list(p, p->src, nsrc, src_z, src_y, src_x, "source");
     if (rc) return rc;
-    rc = build_point_list(p, p->rec, nrec, rec_z, rec_x, "receiver");
+    rc = build_point_list(p, p->rec, nrec, rec_z, rec_y, rec_x, "receiver");
     if (rc) return rc;
     p->nsrc = nsrc; p->nrec = nrec;
     return FWI_OK;
+}
+
+int fwi_fd2d_set_geometry(fwi_fd2d* p, int nsrc, const int* src_z, const int* src_x, int nrec, const int* rec_z,
+                          const int* rec_x) {
+    FWI_REQUIRE(p && p->ny == 1, "fwi_fd2d_set_geometry: needs a 2-D plan");
+    return set_geometry(p, nsrc, src_z, nullptr, src_x, nrec, rec_z, nullptr, rec_x);
+}
+
+int fwi_fd3d_set_geometry(fwi_fd2d* p, int nsrc, const int* src_z, const int* src_y, const int* src_x, int nrec,
+                          const int* rec_z, const int* rec_y, const int* rec_x) {
+    FWI_REQUIRE(p && p->ny > 1, "fwi_fd3d_set_geometry: needs a 3-D plan");
+    FWI_REQUIRE((nsrc == 0 || src_y) && (nrec == 0 || rec_y), "fwi_fd3d_set_geometry: y indices missing");
+    return set_geometry(p, nsrc, src_z, src_y, src_x, nrec, rec_z, rec_y, rec_x);
 }
 
 int fwi_fd2d_forward(fwi_fd2d* p, const float* wavelet_dev, int nt, float* traces_dev, void* stream) {
@@ -730,8 +808,8 @@ int fwi_fd2d_wavefield(fwi_fd2d* p, int which, float* out_dev, void* stream) {
     int rc = enter(p, user);
     if (rc) return rc;
     const float* src = (which == 0) ? p->fld[p->fwd_cur] : (which == 1 ? p->fld[p->fwd_cur ^ 1] : p->acc);
-    dim3 grid((p->nx + 127) / 128, p->nz);
-    fd_unpitch_kernel<<<grid, 128, 0, p->work>>>(src, p->nz, p->nx, p->px, out_dev);
+    dim3 grid(p->rows(), (p->nx + 127) / 128);
+    fd_unpitch_kernel<<<grid, 128, 0, p->work>>>(src, p->rows(), p->nx, p->px, out_dev);
     FWI_CUDA(cudaGetLastError());
     return leave(p, user);
 }
@@ -774,8 +852,8 @@ int fwi_fd2d_gradient(fwi_fd2d* p, const float* wavelet_dev, const float* obs_de
     rc = run_cached(p, 1, nt, seg, nseg, [&](cudaStream_t st) { return record_gradient(p, nt, seg, nseg, st); });
     if (rc) return rc;
     p->fwd_cur = nt & 1;
-    dim3 grid((p->nx + 127) / 128, p->nz);
-    fd_grad_finalize_kernel<<<grid, 128, 0, p->work>>>(p->acc, p->vp, p->nz, p->nx, p->px, grad_dev);
+    dim3 grid(p->rows(), (p->nx + 127) / 128);
+    fd_grad_finalize_kernel<<<grid, 128, 0, p->work>>>(p->acc, p->vp, p->rows(), p->nx, p->px, grad_dev);
     FWI_CUDA(cudaGetLastError());
     p->launches += 1;
     if (traces_dev) FWI_CUDA(cudaMemcpyAsync(traces_dev, p->syn, ntr * sizeof(float), cudaMemcpyDeviceToDevice, p->work));

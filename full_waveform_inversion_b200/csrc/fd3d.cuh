@@ -1,0 +1,183 @@
+// Track B, 3-D: 25-point (8th-order) leapfrog step, marching along z with a TMA plane pipeline.
+//
+// Layout [nz][ny][px] fp32, x contiguous.  A CTA owns a 128 (x) x 16 (y) column of the grid over a chunk of z and
+// marches through it plane by plane:
+//   * a dedicated producer warp keeps a ring of NP = 8 shared-memory planes filled: one 3-D TMA box
+//     (136 x 24 x 1, halo included, out-of-grid zero-filled = Dirichlet) per z plane, full/empty mbarrier pairs;
+//   * 8 consumer warps own two y rows each, a lane owns a float4 of x.  The nine z-neighbours of every output live
+//     in a register window that rotates as the march advances (one LDS.128 per new plane); the x and y neighbours
+//     come from the centre plane, which is still in the ring four planes behind the newest one;
+//   * u_{n-1} and m are read once per point from global, u_{n+1} overwrites u_{n-1} in place; snapshot write /
+//     snapshot read + imaging are fused exactly as in 2-D; the CTA applies its own source / receiver points at the end.
+// Algorithmic traffic: 16 B per point update (+ halo re-reads that hit L2).
+#pragma once
+#include "fd_common.cuh"
+
+namespace fwi {
+
+constexpr int k3BX = 128, k3BY = 16, k3NP = 8, k3CW = 8;            // tile, ring depth, consumer warps
+constexpr int k3SX = k3BX + 2 * kHalo, k3SY = k3BY + 2 * kHalo;     // 136 x 24
+constexpr int k3PlaneFloats = k3SX * k3SY;                          // 3264 floats = 13056 B (102 * 128)
+
+struct Step3DArgs {
+    float* oldnew;
+    const float* m;
+    const float* gx;
+    const float* gy;
+    const float* gz;
+    float* snap;
+    float* acc;
+    int nx, ny, nz, px, zchunk;
+    PointListDev inj;
+    const float* inj_vals;
+    PointListDev rec;
+    float* rec_out;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __grid_constant__ CUtensorMap tm_cur, Step3DArgs a) {
+    extern __shared__ __align__(128) float ring[];                   // [NP][SY][SX]
+    __shared__ __align__(8) uint64_t full_bar[k3NP], empty_bar[k3NP];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * k3BX, y0 = blockIdx.y * k3BY;
+    const int zc0 = blockIdx.z * a.zchunk, zc1 = min(a.nz, zc0 + a.zchunk);
+    const int nout = zc1 - zc0;                   // output planes of this CTA
+    const int nplanes = nout + 2 * kHalo;         // planes zc0-4 .. zc1+3
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < k3NP; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], k3CW); }
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    if (warp == k3CW) {
+        // ---------------- producer warp: one lane feeds the plane ring
+        if (lane == 0) {
+            for (int p = 0; p < nplanes; ++p) {
+                const int slot = p % k3NP;
+                if (p >= k3NP) mbar_wait(&empty_bar[slot], ((p / k3NP) - 1) & 1);
+                mbar_expect_tx(&full_bar[slot], k3PlaneFloats * (uint32_t)sizeof(float));
+                tma_load_3d(ring + (size_t)slot * k3PlaneFloats, &tm_cur, x0 - kHalo, y0 - kHalo, zc0 - kHalo + p, &full_bar[slot]);
+            }
+        }
+    } else {
+        // ---------------- consumer warps
+        const int x = x0 + 4 * lane;
+        const int yl = 2 * warp;                       // first of this warp's two rows inside the tile
+        const bool col_ok = x < a.px;
+        float4 gx4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (col_ok) gx4 = ld4(a.gx + x);
+        float gyv[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) gyv[r] = (y0 + yl + r < a.ny) ? __ldg(a.gy + y0 + yl + r) : 1.f;
+
+        float4 win[2][9];
+        auto own = [&](int p, int r) {                 // this lane's element of row r in ring plane p
+            return ld4(ring + (size_t)(p % k3NP) * k3PlaneFloats + (yl + r + kHalo) * k3SX + kHalo + 4 * lane);
+        };
+        // prime with planes 0..7 (z = zc0-4 .. zc0+3); planes 0..3 are never centre planes -> release them
+        for (int p = 0; p < 2 * kHalo; ++p) {
+            mbar_wait(&full_bar[p % k3NP], (p / k3NP) & 1);
+            win[0][p + 1] = own(p, 0);
+            win[1][p + 1] = own(p, 1);
+            if (p < kHalo) {
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[p % k3NP])) : "memory");
+            }
+        }
+        for (int iz = 0; iz < nout; ++iz) {
+            const int z = zc0 + iz;
+            const int ptop = iz + 2 * kHalo, pmid = iz + kHalo;
+            // global operands first: their latency overlaps the barrier wait and the shared-memory reads
+            float4 o4[2], m4[2], s4[2], c4[2];
+            size_t off[2];
+            bool ok[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int y = y0 + yl + r;
+                ok[r] = col_ok && y < a.ny;
+                off[r] = ((size_t)z * a.ny + y) * a.px + x;
+                if (ok[r]) {
+                    o4[r] = ld4(a.oldnew + off[r]);
+                    m4[r] = ld4(a.m + off[r]);
+                    if (MODE == STEP_ADJ) { s4[r] = ld4_stream(a.snap + off[r]); c4[r] = ld4(a.acc + off[r]); }
+                }
+            }
+            const float gzv = __ldg(a.gz + z);
+            mbar_wait(&full_bar[ptop % k3NP], (ptop / k3NP) & 1);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) win[r][k] = win[r][k + 1];
+                win[r][8] = own(ptop, r);
+            }
+            const float* mid = ring + (size_t)(pmid % k3NP) * k3PlaneFloats;
+            float4 yc[10];                               // rows yl-4 .. yl+5 of the centre plane, this lane's float4
+#pragma unroll
+            for (int k = 0; k < 10; ++k) yc[k] = ld4(mid + (yl + k) * k3SX + kHalo + 4 * lane);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const float* row = mid + (yl + r + kHalo) * k3SX + 4 * lane;
+                const float4 L = ld4(row), R = ld4(row + 8);
+                const float4 C = yc[r + 4];
+                const float ax[12] = {L.x, L.y, L.z, L.w, C.x, C.y, C.z, C.w, R.x, R.y, R.z, R.w};
+                const float gg = gyv[r] * gzv;
+                const float gv[4] = {gx4.x * gg, gx4.y * gg, gx4.z * gg, gx4.w * gg};
+                const float ov[4] = {o4[r].x, o4[r].y, o4[r].z, o4[r].w}, mv[4] = {m4[r].x, m4[r].y, m4[r].z, m4[r].w};
+                float wv[4], nv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float c = ax[4 + q];
+                    auto comp = [&](const float4& v) { return q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w)); };
+                    float lap = (3.0f * kC0) * c;
+                    lap = fmaf(kC1, ((ax[3 + q] + ax[5 + q]) + (comp(yc[r + 3]) + comp(yc[r + 5]))) + (comp(win[r][3]) + comp(win[r][5])), lap);
+                    lap = fmaf(kC2, ((ax[2 + q] + ax[6 + q]) + (comp(yc[r + 2]) + comp(yc[r + 6]))) + (comp(win[r][2]) + comp(win[r][6])), lap);
+                    lap = fmaf(kC3, ((ax[1 + q] + ax[7 + q]) + (comp(yc[r + 1]) + comp(yc[r + 7]))) + (comp(win[r][1]) + comp(win[r][7])), lap);
+                    lap = fmaf(kC4, ((ax[0 + q] + ax[8 + q]) + (comp(yc[r + 0]) + comp(yc[r + 8]))) + (comp(win[r][0]) + comp(win[r][8])), lap);
+                    wv[q] = lap;
+                    nv[q] = gv[q] * fmaf(mv[q], lap, fmaf(-gv[q], ov[q], 2.0f * c));
+                }
+                if (ok[r]) {
+                    st4(a.oldnew + off[r], make_float4(nv[0], nv[1], nv[2], nv[3]));
+                    if (MODE == STEP_FWD_SAVE) st4_stream(a.snap + off[r], make_float4(wv[0], wv[1], wv[2], wv[3]));
+                    if (MODE == STEP_ADJ) {
+                        float4 c = c4[r];
+                        c.x = fmaf(nv[0], s4[r].x, c.x); c.y = fmaf(nv[1], s4[r].y, c.y);
+                        c.z = fmaf(nv[2], s4[r].z, c.z); c.w = fmaf(nv[3], s4[r].w, c.w);
+                        st4(a.acc + off[r], c);
+                    }
+                }
+            }
+            // the centre plane is dead now (later outputs see it only through the register windows)
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[pmid % k3NP])) : "memory");
+        }
+    }
+
+    // ---- sparse fix-ups for the points this CTA owns: injection, then receiver sampling -------------------
+    const int tid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const int i0 = a.inj.tile_ptr ? a.inj.tile_ptr[tid] : 0, i1 = a.inj.tile_ptr ? a.inj.tile_ptr[tid + 1] : 0;
+    const int r0 = a.rec.tile_ptr ? a.rec.tile_ptr[tid] : 0, r1 = a.rec.tile_ptr ? a.rec.tile_ptr[tid + 1] : 0;
+    if (i1 > i0 || r1 > r0) {
+        __syncthreads();
+        for (int e = i0 + threadIdx.x; e < i1; e += blockDim.x) {
+            const int off = a.inj.off[e];
+            const int zy = off / a.px, xx = off - zy * a.px;
+            const int z = zy / a.ny, y = zy - z * a.ny;
+            const float val = a.inj_vals[a.inj.id[e]];
+            const float gm = a.gx[xx] * a.gy[y] * a.gz[z] * a.m[off];
+            atomicAdd(a.oldnew + off, gm * val);
+            if (MODE == STEP_FWD_SAVE) atomicAdd(a.snap + off, val);
+            if (MODE == STEP_ADJ) atomicAdd(a.acc + off, gm * val * a.snap[off]);
+        }
+        if (r1 > r0) {
+            __syncthreads();
+            for (int e = r0 + threadIdx.x; e < r1; e += blockDim.x) a.rec_out[a.rec.id[e]] = __ldcg(a.oldnew + a.rec.off[e]);
+        }
+    }
+}
+
+}  // namespace fwi

@@ -161,7 +161,14 @@ int fwi_fd2d_wavefield(fwi_fd2d* plan, int which, float* out_dev, void* stream);
  * (requesting it synchronises the stream). */
 int fwi_fd2d_gradient(fwi_fd2d* plan, const float* wavelet_dev, const float* obs_dev, int nt, float* grad_dev,
                       float* traces_dev, double* misfit_host, void* stream);
-int64_t fwi_fd2d_launch_count(fwi_fd2d* plan);     /* step-kernel launches so far (bench bookkeeping) */
+int64_t fwi_fd2d_launch_count(fwi_fd2d* plan);
+
+/* 3-D plans (nz x ny x nx, x contiguous; fd_oracle works in any dimension).  A 3-D plan is used with the same
+ * fwi_fd2d_set_model / _forward / _gradient / _wavefield / _set_memory_limit / _set_graphs / _destroy entry points
+ * (dense arrays are then (nz, ny, nx)); only creation and geometry differ. */
+int fwi_fd3d_create(int device, int nz, int ny, int nx, float h, float dt, int nabs, float alpha, fwi_fd2d** out);
+int fwi_fd3d_set_geometry(fwi_fd2d* plan, int nsrc, const int* src_z_host, const int* src_y_host, const int* src_x_host,
+                          int nrec, const int* rec_z_host, const int* rec_y_host, const int* rec_x_host);     /* step-kernel launches so far (bench bookkeeping) */
 
 /* residual = syn - obs, J = 1/2 sum residual^2 (fd_oracle.misfit). Synchronises. */
 int fwi_fd_misfit(const float* syn_dev, const float* obs_dev, int64_t n, float* resid_dev, double* misfit_host,
