@@ -38,6 +38,13 @@ _lib.register({
     "fwi_fd2d_launch_count": (c_int64, [c_void_p]),
     "fwi_fd3d_create": (c_int, [c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_float, POINTER(c_void_p)]),
     "fwi_fd3d_set_geometry": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "fwi_fd_set_profiles": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fwi_fd_field_ptr": (c_void_p, [c_void_p, c_int]),
+    "fwi_fd_pitch": (c_int, [c_void_p]),
+    "fwi_fd_reserve_snapshots": (c_int, [c_void_p, c_int]),
+    "fwi_fd_reset": (c_int, [c_void_p, c_int, c_void_p]),
+    "fwi_fd_step": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "fwi_fd_finalize_gradient": (c_int, [c_void_p, c_void_p, c_void_p]),
     "fwi_fd_misfit": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_double), c_void_p]),
     "fwi_fd_model_update": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_void_p]),
     "fwi_fd_absmax": (c_int, [c_void_p, c_int64, POINTER(c_float), c_void_p]),
@@ -74,7 +81,7 @@ class Propagator:
     """One GPU's propagator plan (wraps ``fwi_fd2d``; 2-D or 3-D by the length of `shape`): model, sponge,
     wavefields, TMA descriptors, cached CUDA graphs."""
 
-    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=0, tile=None, memory_limit=0, stream=None, graphs=True):
+    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=None, tile=None, memory_limit=0, stream=None, graphs=True):
         self._lib = _lib.require_gpu()
         self.shape = tuple(int(n) for n in shape)
         self.ndim = len(self.shape)
@@ -82,7 +89,7 @@ class Propagator:
             raise ValueError("grid must be 2-D (nz, nx) or 3-D (nz, ny, nx)")
         self.nz, self.nx = self.shape[0], self.shape[-1]
         self.h, self.dt = float(h), float(dt)
-        self.device = int(device)
+        self.device = torch.cuda.current_device() if device is None else int(device)
         self._h = c_void_p()
         if self.ndim == 2:
             check(self._lib.fwi_fd2d_create(self.device, self.nz, self.nx, self.h, self.dt, int(nabs), float(alpha),
@@ -169,6 +176,40 @@ class Propagator:
                                               ctypes.byref(J) if want_misfit else None, current_stream()))
         return (J.value if want_misfit else None), grad, traces
 
+    # ---- low-level stepping (the caller drives the time loop; used by SlabPropagator) --------------------------
+    def set_profiles(self, gz=None, gy=None, gx=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float32) for a in (gz, gy, gx)]
+        check(self._lib.fwi_fd_set_profiles(self._h, *[None if a is None else a.ctypes.data_as(c_void_p) for a in arrs]))
+
+    def field_view(self, idx):
+        """Zero-copy torch view (rows..., pitch) of wavefield buffer idx (0/1 forward pair, 2/3 adjoint pair)."""
+        px = int(self._lib.fwi_fd_pitch(self._h))
+        shape = self.shape[:-1] + (px,)
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "version": 3,
+                                        "data": (int(self._lib.fwi_fd_field_ptr(self._h, idx)), False)}
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(raw, device=self.torch_device)
+
+    def reserve_snapshots(self, nsteps):
+        check(self._lib.fwi_fd_reserve_snapshots(self._h, int(nsteps)))
+
+    def reset(self, pair):
+        with torch.cuda.device(self.device):
+            check(self._lib.fwi_fd_reset(self._h, int(pair), current_stream()))
+
+    def step(self, mode, cur, inj_row_ptr, rec_row_ptr=None, snap_index=-1):
+        with torch.cuda.device(self.device):
+            check(self._lib.fwi_fd_step(self._h, int(mode), int(cur), c_void_p(inj_row_ptr),
+                                        None if rec_row_ptr is None else c_void_p(rec_row_ptr), int(snap_index), current_stream()))
+
+    def finalize_gradient(self, grad):
+        with torch.cuda.device(self.device):
+            check(self._lib.fwi_fd_finalize_gradient(self._h, ptr(grad), current_stream()))
+
     def launch_count(self):
         return int(self._lib.fwi_fd2d_launch_count(self._h))
 
@@ -179,6 +220,143 @@ Propagator3D = Propagator
 
 def _make_propagator(shape, h, dt, nabs, alpha, device, **kw):
     return Propagator(shape, h, dt, nabs, alpha, device, **kw)
+
+
+def sponge_profile(n, nabs, alpha):
+    """1-D Cerjan profile (fd_oracle.sponge_profile)."""
+    prof = np.ones(n, dtype=np.float64)
+    for i in range(min(nabs, n)):
+        val = math.exp(-((alpha * (nabs - i) / nabs) ** 2))
+        prof[i] = min(prof[i], val)
+        prof[n - 1 - i] = min(prof[n - 1 - i], val)
+    return prof.astype(np.float32)
+
+
+class SlabPropagator:
+    """Large grids split into z slabs over the ranks of the default process group (BASELINE config 4).
+
+    Every rank owns a contiguous range of z planes plus a 4-plane ghost zone towards each neighbour and runs the
+    ordinary step kernel on its local grid; after every step the freshly computed boundary planes are exchanged
+    with the neighbours (NCCL send/recv on the compute stream - NVLink peer traffic, stream ordered, no host
+    barrier).  Values in the ghost planes are overwritten by the neighbour's, so the owned planes are bit-identical
+    to a single-GPU run.  The time loop is driven from Python, one `fwi_fd_step` per step."""
+
+    HALO = 4
+
+    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=None):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("SlabPropagator needs an initialised torch.distributed process group")
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.shape = tuple(int(n) for n in shape)
+        nz = self.shape[0]
+        if nz < self.world * 2 * self.HALO:
+            raise ValueError("grid has too few z planes (%d) for %d slabs" % (nz, self.world))
+        base, rem = divmod(nz, self.world)
+        counts = [base + (1 if r < rem else 0) for r in range(self.world)]
+        self.z0 = sum(counts[: self.rank])
+        self.n_own = counts[self.rank]
+        self.up = self.HALO if self.rank > 0 else 0
+        self.down = self.HALO if self.rank < self.world - 1 else 0
+        self.local_shape = (self.n_own + self.up + self.down,) + self.shape[1:]
+        device = torch.cuda.current_device() if device is None else device
+        self.prop = Propagator(self.local_shape, h, dt, nabs, alpha, device, graphs=False)
+        gz = sponge_profile(nz, nabs, alpha)[self.z0 - self.up: self.z0 + self.n_own + self.down]
+        self.prop.set_profiles(gz=gz)
+        self.fields = [self.prop.field_view(i) for i in range(4)]
+        self.nsrc = self.nrec = 0
+
+    def close(self):
+        self.prop.close()
+
+    @property
+    def own(self):
+        return slice(self.up, self.up + self.n_own)
+
+    def set_model(self, v):
+        """v: the GLOBAL velocity grid (host or device); every rank keeps its slab (+ ghosts)."""
+        lo, hi = self.z0 - self.up, self.z0 + self.n_own + self.down
+        self.prop.set_model(v[lo:hi])
+
+    def set_geometry(self, src, rec):
+        ndim = len(self.shape)
+        src = np.asarray(src, dtype=np.int64).reshape(-1, ndim)
+        rec = np.asarray(rec, dtype=np.int64).reshape(-1, ndim)
+
+        def mine(p):
+            keep = np.nonzero((p[:, 0] >= self.z0) & (p[:, 0] < self.z0 + self.n_own))[0]
+            loc = p[keep].copy()
+            loc[:, 0] += self.up - self.z0
+            return keep, loc
+        self.src_ids, s_loc = mine(src)
+        self.rec_ids, r_loc = mine(rec)
+        self.nsrc_global, self.nrec_global = len(src), len(rec)
+        self.prop.set_geometry(s_loc, r_loc)
+
+    def _exchange(self, idx):
+        """Refresh the ghost planes of wavefield buffer idx from the neighbours' boundary planes."""
+        f, H, ops = self.fields[idx], self.HALO, []
+        n = f.shape[0]
+        P2P = self.dist.P2POp
+        if self.up:
+            ops += [P2P(self.dist.isend, f[H:2 * H], self.rank - 1), P2P(self.dist.irecv, f[0:H], self.rank - 1)]
+        if self.down:
+            ops += [P2P(self.dist.isend, f[n - 2 * H: n - H], self.rank + 1), P2P(self.dist.irecv, f[n - H: n], self.rank + 1)]
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def _wavelet_local(self, wavelet):
+        w = _dev_f32(wavelet, self.prop.torch_device)
+        if w.ndim == 1:
+            w = w[:, None].expand(-1, self.nsrc_global)
+        return w[:, torch.as_tensor(self.src_ids, device=w.device)].contiguous() if len(self.src_ids) else \
+            torch.zeros((w.shape[0], 1), dtype=torch.float32, device=w.device)
+
+    def _run(self, nt, mode, pair, inj, out, snap_offset=0, reverse=False):
+        self.prop.reset(pair)
+        cur = 0
+        for k in range(nt):
+            n = nt - 1 - k if reverse else k
+            self.prop.step(mode, cur, inj.data_ptr() + n * inj.shape[1] * 4,
+                           None if out is None or out.shape[1] == 0 else out.data_ptr() + n * out.shape[1] * 4,
+                           snap_index=n + snap_offset if mode else -1)
+            cur ^= 1
+            self._exchange(2 * pair + cur)
+
+    def _gather_traces(self, local, nt):
+        full = torch.zeros((nt, self.nrec_global), dtype=torch.float32, device=local.device)
+        if len(self.rec_ids):
+            full[:, torch.as_tensor(self.rec_ids, device=local.device)] = local
+        self.dist.all_reduce(full)
+        return full
+
+    def forward(self, wavelet):
+        """Traces (nt, nrec) of the whole survey on every rank."""
+        w = self._wavelet_local(wavelet)
+        nt = w.shape[0]
+        local = torch.zeros((nt, len(self.rec_ids)), dtype=torch.float32, device=w.device)
+        self._run(nt, 0, 0, w, local)
+        return self._gather_traces(local, nt)
+
+    def gradient(self, wavelet, observed):
+        """(J, gradient of this rank's own planes (n_own, ...), traces) - every w_n of the slab is held in HBM."""
+        w = self._wavelet_local(wavelet)
+        nt = w.shape[0]
+        dev = w.device
+        self.prop.reserve_snapshots(nt)
+        local = torch.zeros((nt, max(1, len(self.rec_ids))), dtype=torch.float32, device=dev)[:, : len(self.rec_ids)].contiguous()
+        self._run(nt, 1, 0, w, local)
+        obs = _dev_f32(observed, dev)
+        res = (local - obs[:, torch.as_tensor(self.rec_ids, device=dev)]).contiguous() if len(self.rec_ids) else \
+            torch.zeros((nt, 1), dtype=torch.float32, device=dev)
+        J = 0.5 * (res.double() ** 2).sum()
+        self.dist.all_reduce(J)
+        self._run(nt, 2, 1, res, None, reverse=True)
+        grad = torch.zeros(self.local_shape, dtype=torch.float32, device=dev)
+        self.prop.finalize_gradient(grad)
+        return float(J.item()), grad[self.own], self._gather_traces(local, nt)
 
 
 # ------------------------------------------------------------------------------------------------ entry points

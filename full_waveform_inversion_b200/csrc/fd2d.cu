@@ -865,6 +865,69 @@ int fwi_fd2d_gradient(fwi_fd2d* p, const float* wavelet_dev, const float* obs_de
 
 int64_t fwi_fd2d_launch_count(fwi_fd2d* p) { return p ? p->launches : 0; }
 
+// ---- low-level stepping API: the caller drives the time loop (used by the slab-decomposed multi-GPU path, which
+// interleaves halo exchanges with single steps on the caller's stream) -----------------------------------------
+int fwi_fd_set_profiles(fwi_fd2d* p, const float* gz_host, const float* gy_host, const float* gx_host) {
+    FWI_REQUIRE(p, "fwi_fd_set_profiles: NULL plan");
+    DeviceGuard g(p->device);
+    FWI_CUDA(cudaStreamSynchronize(p->work));
+    if (gz_host) FWI_CUDA(cudaMemcpy(p->gz, gz_host, p->nz * sizeof(float), cudaMemcpyHostToDevice));
+    if (gy_host) FWI_CUDA(cudaMemcpy(p->gy, gy_host, p->ny * sizeof(float), cudaMemcpyHostToDevice));
+    if (gx_host) FWI_CUDA(cudaMemcpy(p->gx, gx_host, p->nx * sizeof(float), cudaMemcpyHostToDevice));
+    return FWI_OK;
+}
+
+void* fwi_fd_field_ptr(fwi_fd2d* p, int idx) { return (p && idx >= 0 && idx < 4) ? (void*)p->fld[idx] : nullptr; }
+int fwi_fd_pitch(fwi_fd2d* p) { return p ? p->px : 0; }
+
+int fwi_fd_reserve_snapshots(fwi_fd2d* p, int nsteps) {
+    FWI_REQUIRE(p && nsteps >= 0, "fwi_fd_reserve_snapshots: bad arguments");
+    DeviceGuard g(p->device);
+    FWI_CUDA(cudaStreamSynchronize(p->work));
+    return ensure_floats(p, &p->snap, &p->snap_steps, (size_t)nsteps * p->plane());
+}
+
+// Zero the wavefield pair (0 = forward, 1 = adjoint; the adjoint pair also clears the imaging accumulator).
+int fwi_fd_reset(fwi_fd2d* p, int pair, void* stream) {
+    FWI_REQUIRE(p && (pair == 0 || pair == 1), "fwi_fd_reset: bad arguments");
+    DeviceGuard g(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t pl = p->plane();
+    FWI_CUDA(cudaMemsetAsync(p->fld[2 * pair], 0, pl * sizeof(float), st));
+    FWI_CUDA(cudaMemsetAsync(p->fld[2 * pair + 1], 0, pl * sizeof(float), st));
+    if (pair == 1) FWI_CUDA(cudaMemsetAsync(p->acc, 0, pl * sizeof(float), st));
+    return FWI_OK;
+}
+
+// One leapfrog step on `stream`.  mode: 0 forward, 1 forward + snapshot[snap_index], 2 adjoint + imaging with
+// snapshot[snap_index].  `cur` (0/1) says which buffer of the pair holds u_n; u_{n+1} lands in the other one.
+// inj_vals_dev: this step's injected values (sources for modes 0/1, receiver residuals for mode 2);
+// rec_out_dev: this step's trace row (modes 0/1, nullable).
+int fwi_fd_step(fwi_fd2d* p, int mode, int cur, const float* inj_vals_dev, float* rec_out_dev, int64_t snap_index, void* stream) {
+    FWI_REQUIRE(p && p->model_set, "fwi_fd_step: set the model first");
+    FWI_REQUIRE(mode >= 0 && mode <= 2 && (cur == 0 || cur == 1), "fwi_fd_step: bad mode / cur");
+    FWI_REQUIRE(mode == 0 || (snap_index >= 0 && (size_t)(snap_index + 1) * p->plane() <= p->snap_steps), "fwi_fd_step: snapshot %lld not reserved", (long long)snap_index);
+    DeviceGuard g(p->device);
+    const int base = (mode == STEP_ADJ) ? 2 : 0;
+    float* snap = (mode == 0) ? nullptr : p->snap + (size_t)snap_index * p->plane();
+    int rc = launch_step(p, mode, base + cur, p->fld[base + (cur ^ 1)], mode == STEP_ADJ ? &p->rec : &p->src, inj_vals_dev,
+                         (mode != STEP_ADJ && rec_out_dev) ? &p->rec : nullptr, rec_out_dev, snap, (cudaStream_t)stream);
+    if (rc) return rc;
+    FWI_CUDA(cudaGetLastError());
+    if (mode != STEP_ADJ) p->fwd_cur = cur ^ 1;
+    return FWI_OK;
+}
+
+// grad_dev (dense grid) += (2 / v) * imaging accumulator
+int fwi_fd_finalize_gradient(fwi_fd2d* p, float* grad_dev, void* stream) {
+    FWI_REQUIRE(p && grad_dev, "fwi_fd_finalize_gradient: bad arguments");
+    DeviceGuard g(p->device);
+    dim3 grid(p->rows(), (p->nx + 127) / 128);
+    fd_grad_finalize_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p->acc, p->vp, p->rows(), p->nx, p->px, grad_dev);
+    FWI_CUDA(cudaGetLastError());
+    return FWI_OK;
+}
+
 
 int fwi_fd_misfit(const float* syn_dev, const float* obs_dev, int64_t n, float* resid_dev, double* misfit_host, void* stream) {
     FWI_REQUIRE(syn_dev && obs_dev && resid_dev && misfit_host && n >= 0, "fwi_fd_misfit: bad arguments");

@@ -54,7 +54,7 @@ def _flags(norm, simul, strict=False):
 class SourceInversion:
     """Device-resident problem: Green's functions + data on one GPU (wraps ``fwi_mc_ctx``)."""
 
-    def __init__(self, real_data_array, green_func_array, green_func_phase_labels=(), device=0):
+    def __init__(self, real_data_array, green_func_array, green_func_phase_labels=(), device=None):
         lib = _lib.require_gpu()
         d = np.ascontiguousarray(real_data_array, dtype=np.float64)
         G = np.ascontiguousarray(green_func_array, dtype=np.float64)
@@ -64,7 +64,7 @@ class SourceInversion:
             raise ValueError("green_func_array %s does not match real_data_array %s" % (G.shape, d.shape))
         self.K, self.C, self.T = G.shape[:3]
         self.n_media = 1 if G.ndim == 3 else G.shape[3]
-        self.device = int(device)
+        self.device = torch.cuda.current_device() if device is None else int(device)
         phase = None
         if len(green_func_phase_labels) > 0:
             if len(green_func_phase_labels) != self.K:

@@ -170,6 +170,21 @@ int fwi_fd3d_create(int device, int nz, int ny, int nx, float h, float dt, int n
 int fwi_fd3d_set_geometry(fwi_fd2d* plan, int nsrc, const int* src_z_host, const int* src_y_host, const int* src_x_host,
                           int nrec, const int* rec_z_host, const int* rec_y_host, const int* rec_x_host);     /* step-kernel launches so far (bench bookkeeping) */
 
+/* Low-level stepping API: the caller drives the time loop, one leapfrog step per call on the caller's stream.
+ * Used by the slab-decomposed multi-GPU path (acoustic.SlabPropagator), which exchanges the 4-plane halos of the
+ * slab with its neighbours over NCCL/NVLink between steps. */
+int fwi_fd_set_profiles(fwi_fd2d* plan, const float* gz_host, const float* gy_host, const float* gx_host); /* override sponge profiles (nullable each) */
+void* fwi_fd_field_ptr(fwi_fd2d* plan, int idx);   /* wavefield buffer idx: 0/1 forward pair, 2/3 adjoint pair; layout [rows][pitch] */
+int fwi_fd_pitch(fwi_fd2d* plan);                  /* floats per row (nx rounded up to 32) */
+int fwi_fd_reserve_snapshots(fwi_fd2d* plan, int nsteps);
+int fwi_fd_reset(fwi_fd2d* plan, int pair, void* stream);   /* zero pair 0 (forward) or 1 (adjoint + imaging sum) */
+/* mode 0 forward, 1 forward + store w_n in snapshot[snap_index], 2 adjoint + imaging against snapshot[snap_index];
+ * cur (0/1) = buffer of the pair holding u_n; inj_vals_dev = this step's source values (or receiver residuals);
+ * rec_out_dev = this step's trace row (nullable). */
+int fwi_fd_step(fwi_fd2d* plan, int mode, int cur, const float* inj_vals_dev, float* rec_out_dev, int64_t snap_index,
+                void* stream);
+int fwi_fd_finalize_gradient(fwi_fd2d* plan, float* grad_dev, void* stream);   /* grad += (2/v) I */
+
 /* residual = syn - obs, J = 1/2 sum residual^2 (fd_oracle.misfit). Synchronises. */
 int fwi_fd_misfit(const float* syn_dev, const float* obs_dev, int64_t n, float* resid_dev, double* misfit_host,
                   void* stream);

@@ -1,0 +1,48 @@
+"""Run under torchrun: slab-decomposed 3-D forward + gradient (halo exchange over NCCL) vs a single-GPU run.
+  torchrun --nproc-per-node 2 tools/slab_check.py [n] [nt]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+from full_waveform_inversion_b200 import acoustic as ac
+from oracle import fd_oracle as fo
+
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank, world = dist.get_rank(), dist.get_world_size()
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 96
+nt = int(sys.argv[2]) if len(sys.argv) > 2 else 120
+shape = (n, n - 8, n + 32)
+v = (fo.layered_model(shape, 1700.0, 3000.0, 4) + 40.0 * np.random.default_rng(0).standard_normal(shape)).astype(np.float32)
+h = 10.0; dt = fo.stable_dt(float(v.max()), h, 3)
+wav = ac.ricker(nt, dt, 20.0)
+src = [(6, shape[1] // 2, shape[2] // 3), (n - 9, shape[1] // 3, shape[2] // 2)]
+rec = [(z, y, x) for z in (5, n // 2, n - 7) for y in range(3, shape[1] - 3, 9) for x in range(3, shape[2] - 3, 11)]
+vt = torch.from_numpy(v).cuda()
+
+slab = ac.SlabPropagator(shape, h, dt, nabs=10)
+slab.set_model(vt * 1.03)
+slab.set_geometry(src, rec)
+obs = slab.forward(wav)
+slab.set_model(vt)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+J, g_own, tr = slab.gradient(wav, obs)
+torch.cuda.synchronize(); t_slab = time.perf_counter() - t0
+
+single = ac.Propagator(shape, h, dt, nabs=10)
+single.set_model(vt * 1.03); single.set_geometry(src, rec)
+obs1 = single.forward(wav)
+single.set_model(vt)
+J1, g1, tr1 = single.gradient(wav, obs1, want_traces=True)
+e_obs = float((obs - obs1).abs().max() / obs1.abs().max())
+e_tr = float((tr - tr1).abs().max() / tr1.abs().max())
+g_ref = g1[slab.z0: slab.z0 + slab.n_own]
+e_g = float((g_own - g_ref).norm() / g1.norm())
+ok = torch.tensor([1.0 if (e_obs < 1e-6 and e_tr < 1e-6 and e_g < 1e-6 and abs(J - J1) < 1e-6 * J1) else 0.0], device="cuda")
+dist.all_reduce(ok)
+print("rank %d/%d slab z0=%d n_own=%d: obs diff %.2e traces diff %.2e grad diff %.2e J %.6e vs %.6e  (slab gradient %.2f s, %d steps)"
+      % (rank, world, slab.z0, slab.n_own, e_obs, e_tr, e_g, J, J1, t_slab, 2 * nt), flush=True)
+dist.barrier()
+if rank == 0:
+    print("SLAB_CHECK_OK" if ok.item() == world else "SLAB_CHECK_FAILED")
+dist.destroy_process_group()
