@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--grid", default="1000x3000")
     ap.add_argument("--tile", default="")
     ap.add_argument("--stream", default="")
+    ap.add_argument("--tb2", type=int, default=0)
     ap.add_argument("--no-track-a", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -228,7 +229,7 @@ def run_b200(args):
     nz, nx, nt = w["nz"], w["nx"], w["nt"]
     tile = tuple(int(x) for x in args.tile.split(",")) if args.tile else None
     stream = tuple(int(x) for x in args.stream.split(",")) if args.stream else None
-    prop = ac.Propagator2D((nz, nx), w["h"], w["dt"], nabs=w["nabs"], alpha=w["alpha"], device=local, tile=tile, stream=stream)
+    prop = ac.Propagator2D((nz, nx), w["h"], w["dt"], nabs=w["nabs"], alpha=w["alpha"], device=local, tile=tile, stream=stream, tb2=(args.tb2 or None))
     v_dev = torch.from_numpy(w["v"]).to(dev)
     prop.set_model(v_dev)
     wav_dev = torch.from_numpy(w["wav"]).to(dev)

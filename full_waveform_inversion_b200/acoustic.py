@@ -29,6 +29,7 @@ _lib.register({
     "fwi_fd2d_set_tile": (c_int, [c_void_p, c_int, c_int]),
     "fwi_fd2d_set_stream": (c_int, [c_void_p, c_int, c_int]),
     "fwi_fd2d_set_graphs": (c_int, [c_void_p, c_int]),
+    "fwi_fd2d_set_tb2": (c_int, [c_void_p, c_int]),
     "fwi_fd2d_set_memory_limit": (c_int, [c_void_p, c_uint64]),
     "fwi_fd2d_set_model": (c_int, [c_void_p, c_void_p, c_void_p]),
     "fwi_fd2d_set_geometry": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
@@ -81,7 +82,7 @@ class Propagator:
     """One GPU's propagator plan (wraps ``fwi_fd2d``; 2-D or 3-D by the length of `shape`): model, sponge,
     wavefields, TMA descriptors, cached CUDA graphs."""
 
-    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=None, tile=None, memory_limit=0, stream=None, graphs=True):
+    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=None, tile=None, memory_limit=0, stream=None, graphs=True, tb2=None):
         self._lib = _lib.require_gpu()
         self.shape = tuple(int(n) for n in shape)
         self.ndim = len(self.shape)
@@ -101,6 +102,8 @@ class Propagator:
             check(self._lib.fwi_fd2d_set_tile(self._h, int(tile[0]), int(tile[1])))
         if stream is not None:
             check(self._lib.fwi_fd2d_set_stream(self._h, int(stream[0]), int(stream[1])))
+        if tb2 is not None:
+            check(self._lib.fwi_fd2d_set_tb2(self._h, int(tb2)))
         if memory_limit:
             check(self._lib.fwi_fd2d_set_memory_limit(self._h, int(memory_limit)))
         if not graphs:
@@ -182,7 +185,7 @@ class Propagator:
         check(self._lib.fwi_fd_set_profiles(self._h, *[None if a is None else a.ctypes.data_as(c_void_p) for a in arrs]))
 
     def field_view(self, idx):
-        """Zero-copy torch view (rows..., pitch) of wavefield buffer idx (0/1 forward pair, 2/3 adjoint pair)."""
+        """Zero-copy torch view (rows..., pitch) of wavefield buffer idx (0/1 forward pair, 4/5 adjoint pair)."""
         px = int(self._lib.fwi_fd_pitch(self._h))
         shape = self.shape[:-1] + (px,)
 
@@ -264,7 +267,7 @@ class SlabPropagator:
         self.prop = Propagator(self.local_shape, h, dt, nabs, alpha, device, graphs=False)
         gz = sponge_profile(nz, nabs, alpha)[self.z0 - self.up: self.z0 + self.n_own + self.down]
         self.prop.set_profiles(gz=gz)
-        self.fields = [self.prop.field_view(i) for i in range(4)]
+        self.fields = [self.prop.field_view(i) for i in range(8)]
         self.nsrc = self.nrec = 0
 
     def close(self):
@@ -323,7 +326,7 @@ class SlabPropagator:
                            None if out is None or out.shape[1] == 0 else out.data_ptr() + n * out.shape[1] * 4,
                            snap_index=n + snap_offset if mode else -1)
             cur ^= 1
-            self._exchange(2 * pair + cur)
+            self._exchange(4 * pair + cur)
 
     def _gather_traces(self, local, nt):
         full = torch.zeros((nt, self.nrec_global), dtype=torch.float32, device=local.device)

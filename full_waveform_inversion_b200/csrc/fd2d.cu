@@ -26,6 +26,7 @@ enum { STEP_FWD = 0, STEP_FWD_SAVE = 1, STEP_ADJ = 2 };
 }  // namespace fwi
 #include "fd2d_stream.cuh"
 #include "fd3d.cuh"
+#include "fd2d_tb2.cuh"
 namespace fwi {
 
 struct Step2DArgs {
@@ -255,6 +256,7 @@ constexpr int kBX = 128;
 struct GraphEntry {
     int kind, nt, nsrc, nrec, seg, nseg;
     cudaGraphExec_t exec;
+    int64_t kernels;
 };
 
 }  // namespace
@@ -264,7 +266,7 @@ struct fwi_fd2d {
     float h = 0, dt = 0, alpha = 0;
     int tiles_y = 1, zchunk = 0, nzch = 1;                      // 3-D tiling: 128 x 16 columns, z chunks
     float* gy = nullptr;
-    CUtensorMap tm3[4];
+    CUtensorMap tm3[8];
     int bz = 16, nw = 2;              // tiled variant: tile rows / warps per CTA (tunable)
     int tiles_x = 0, tiles_z = 0;
     int variant = 0;                  // 0 = one-tile-per-CTA kernel (default), 1 = persistent streaming kernel
@@ -272,10 +274,12 @@ struct fwi_fd2d {
     int nstrips = 0, W = 0;
     int* d_u0 = nullptr;
     std::vector<int> h_u0;
-    CUtensorMap tm_cur_s[4], tm_old_s[4], tm_m_s;
+    CUtensorMap tm_cur_s[8], tm_old_s[8], tm_m_s;
+    CUtensorMap tb_cur[8], tb_old[8], tb_m;     // temporally blocked kernel (variant 2)
+    int cz = 32, tiles_x2 = 0, tiles_z2 = 0;
     float *m = nullptr, *vp = nullptr, *gx = nullptr, *gz = nullptr;
-    float* fld[4] = {nullptr, nullptr, nullptr, nullptr};   // forward pair 0/1, adjoint pair 2/3
-    CUtensorMap tmap[4];
+    float* fld[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // forward 0..3, adjoint 4..7 (one-step kernels use 0/1 and 4/5)
+    CUtensorMap tmap[8];
     float* acc = nullptr;
     float* snap = nullptr; size_t snap_steps = 0;
     float* ckpt = nullptr; size_t ckpt_slots = 0;
@@ -285,9 +289,10 @@ struct fwi_fd2d {
     float* wav = nullptr; size_t wav_cap = 0;
     double* d_J = nullptr;
     PointList src, rec;
+    PointList src_ext2, src_own2, rec_ext2, rec_own2;   // variant 2: binned by the 120 x cz core tiles (+-4 for *_ext2)
     int nsrc = 0, nrec = 0;
     size_t mem_limit = 0;             // 0 = automatic (fraction of free memory)
-    int fwd_cur = 0;                  // which of fld[0/1] holds u_n after the last forward
+    int fwd_c = 0, fwd_o = 1;         // fld[] indices of u_n and u_{n-1} after the last forward
     bool model_set = false;
     bool use_graphs = true;
     int64_t launches = 0;
@@ -318,7 +323,7 @@ static int make_stream_partition(fwi_fd2d* p) {
     const uint64_t dims_p[2] = {(uint64_t)p->px, (uint64_t)p->nz};
     const uint64_t strides[1] = {(uint64_t)p->px * sizeof(float)};
     const uint32_t box_c[2] = {(uint32_t)kSCW, (uint32_t)kSR}, box_r[2] = {128u, (uint32_t)kSR};
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
         int rc = encode_tiled_f32(&p->tm_cur_s[i], p->fld[i], 2, dims, strides, box_c);
         if (rc) return rc;
         rc = encode_tiled_f32(&p->tm_old_s[i], p->fld[i], 2, dims_p, strides, box_r);
@@ -335,7 +340,7 @@ static int make_tmaps3(fwi_fd2d* p) {
     nzch = std::max(1, std::min(nzch, std::max(1, p->nz / 16)));
     p->zchunk = (p->nz + nzch - 1) / nzch;
     p->nzch = (p->nz + p->zchunk - 1) / p->zchunk;
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
         const uint64_t dims[3] = {(uint64_t)p->nx, (uint64_t)p->ny, (uint64_t)p->nz};
         const uint64_t strides[2] = {(uint64_t)p->px * sizeof(float), (uint64_t)p->px * p->ny * sizeof(float)};
         const uint32_t box[3] = {(uint32_t)k3SX, (uint32_t)k3SY, 1u};
@@ -347,7 +352,23 @@ static int make_tmaps3(fwi_fd2d* p) {
 
 static int make_tmaps(fwi_fd2d* p) {
     if (p->ny > 1) return make_tmaps3(p);
-    for (int i = 0; i < 4; ++i) {
+    p->tiles_x2 = (p->nx + kT2CX - 1) / kT2CX;
+    p->tiles_z2 = (p->nz + p->cz - 1) / p->cz;
+    {
+        const uint64_t dims[2] = {(uint64_t)p->nx, (uint64_t)p->nz};
+        const uint64_t dims_p[2] = {(uint64_t)p->px, (uint64_t)p->nz};
+        const uint64_t strides[1] = {(uint64_t)p->px * sizeof(float)};
+        const uint32_t box_c[2] = {(uint32_t)kT2W0, (uint32_t)(p->cz + 16)}, box_o[2] = {(uint32_t)kT2W1, (uint32_t)(p->cz + 8)};
+        for (int i = 0; i < 8; ++i) {
+            int rc = encode_tiled_f32(&p->tb_cur[i], p->fld[i], 2, dims, strides, box_c);
+            if (rc) return rc;
+            rc = encode_tiled_f32(&p->tb_old[i], p->fld[i], 2, dims_p, strides, box_o);
+            if (rc) return rc;
+        }
+        int rc = encode_tiled_f32(&p->tb_m, p->m, 2, dims_p, strides, box_o);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < 8; ++i) {
         const uint64_t dims[2] = {(uint64_t)p->nx, (uint64_t)p->nz};
         const uint64_t strides[1] = {(uint64_t)p->px * sizeof(float)};
         const uint32_t box[2] = {(uint32_t)(kBX + 2 * kHalo), (uint32_t)(p->bz + 2 * kHalo)};
@@ -360,13 +381,13 @@ static int make_tmaps(fwi_fd2d* p) {
 // bin that owns grid point (z, x): the CTA tile (tiled variant) or the warp whose row-unit range holds it
 static int owner_bin(const fwi_fd2d* p, int z, int y, int x) {
     if (p->ny > 1) return ((z / p->zchunk) * p->tiles_y + y / k3BY) * p->tiles_x + x / k3BX;
-    if (p->variant == 0) return (z / p->bz) * p->tiles_x + x / kBX;
+    if (p->variant != 1) return (z / p->bz) * p->tiles_x + x / kBX;
     const int u = (x / 128) * p->nz + z;
     return (int)(std::upper_bound(p->h_u0.begin(), p->h_u0.end(), u) - p->h_u0.begin()) - 1;
 }
 
 static int build_point_list(fwi_fd2d* p, PointList& pl, int n, const int* iz, const int* iy, const int* ix, const char* what) {
-    const int nbins = (p->ny > 1) ? p->tiles_x * p->tiles_y * p->nzch : ((p->variant == 0) ? p->tiles_x * p->tiles_z : p->W);
+    const int nbins = (p->ny > 1) ? p->tiles_x * p->tiles_y * p->nzch : ((p->variant != 1) ? p->tiles_x * p->tiles_z : p->W);
     std::vector<int> tile_ptr(nbins + 1, 0), off(std::max(n, 1)), id(std::max(n, 1));
     for (int i = 0; i < n; ++i) {
         const int yy = iy ? iy[i] : 0;
@@ -396,6 +417,41 @@ static int build_point_list(fwi_fd2d* p, PointList& pl, int n, const int* iz, co
     FWI_CUDA(cudaMemcpyAsync(pl.d_id, id.data(), std::max(n, 1) * sizeof(int), cudaMemcpyHostToDevice, p->work));
     FWI_CUDA(cudaStreamSynchronize(p->work));       // the host vectors go out of scope
     pl.n = n;
+    return FWI_OK;
+}
+
+// variant 2: bin points by the 120 x cz core tiles; with `ext` a point is listed in every tile whose core +- 4 holds it
+static int build_point_list_tb2(fwi_fd2d* p, PointList& pl, int n, const int* iz, const int* ix, bool ext) {
+    const int nbins = p->tiles_x2 * p->tiles_z2;
+    std::vector<std::vector<std::pair<int, int>>> bins(nbins);
+    const int h = ext ? kHalo : 0;
+    for (int i = 0; i < n; ++i) {
+        const int tz0 = std::max(0, (iz[i] - h) / p->cz), tz1 = std::min(p->tiles_z2 - 1, (iz[i] + h) / p->cz);
+        const int tx0 = std::max(0, (ix[i] - h) / kT2CX), tx1 = std::min(p->tiles_x2 - 1, (ix[i] + h) / kT2CX);
+        for (int tz = tz0; tz <= tz1; ++tz)
+            for (int tx = tx0; tx <= tx1; ++tx) bins[tz * p->tiles_x2 + tx].push_back({iz[i] * p->px + ix[i], i});
+    }
+    std::vector<int> tile_ptr(nbins + 1, 0), off, id;
+    for (int t = 0; t < nbins; ++t) {
+        tile_ptr[t + 1] = tile_ptr[t] + (int)bins[t].size();
+        for (auto& e : bins[t]) { off.push_back(e.first); id.push_back(e.second); }
+    }
+    const int tot = std::max<int>(1, (int)off.size());
+    off.resize(tot); id.resize(tot);
+    if (pl.nbins != nbins || pl.cap < tot) {
+        pl.release();
+        drop_graphs(p);
+        const int cap = tot + tot / 2 + 16;          // extended lists vary a little from shot to shot
+        FWI_CUDA(cudaMalloc(&pl.d_tile_ptr, (nbins + 1) * sizeof(int)));
+        FWI_CUDA(cudaMalloc(&pl.d_off, cap * sizeof(int)));
+        FWI_CUDA(cudaMalloc(&pl.d_id, cap * sizeof(int)));
+        pl.cap = cap; pl.nbins = nbins;
+    }
+    FWI_CUDA(cudaMemcpyAsync(pl.d_tile_ptr, tile_ptr.data(), (nbins + 1) * sizeof(int), cudaMemcpyHostToDevice, p->work));
+    FWI_CUDA(cudaMemcpyAsync(pl.d_off, off.data(), tot * sizeof(int), cudaMemcpyHostToDevice, p->work));
+    FWI_CUDA(cudaMemcpyAsync(pl.d_id, id.data(), tot * sizeof(int), cudaMemcpyHostToDevice, p->work));
+    FWI_CUDA(cudaStreamSynchronize(p->work));
+    pl.n = tile_ptr[nbins];
     return FWI_OK;
 }
 
@@ -467,7 +523,7 @@ static int launch_step(fwi_fd2d* p, int mode, int cur, float* oldnew, const Poin
     if (p->ny > 1) return launch_step3(p, mode, cur, oldnew, inj, inj_vals, rec, rec_out, snap, st);
     if (p->variant == 1) {
         int oldidx = -1;
-        for (int i = 0; i < 4; ++i) if (p->fld[i] == oldnew) oldidx = i;
+        for (int i = 0; i < 8; ++i) if (p->fld[i] == oldnew) oldidx = i;
         if (p->snw == 8 && p->snc == 4) return launch_stream_cfg<8, 4>(p, mode, cur, oldidx, inj, inj_vals, rec, rec_out, snap, st);
         if (p->snw == 4 && p->snc == 8) return launch_stream_cfg<4, 8>(p, mode, cur, oldidx, inj, inj_vals, rec, rec_out, snap, st);
         if (p->snw == 6 && p->snc == 5) return launch_stream_cfg<6, 5>(p, mode, cur, oldidx, inj, inj_vals, rec, rec_out, snap, st);
@@ -493,27 +549,110 @@ static int ensure_floats(fwi_fd2d* p, float** ptr, size_t* cap, size_t need_floa
     return FWI_OK;
 }
 
-// forward time loop over steps [n0, n1); `cur` indexes fld[] holding u_n on entry, returns the new cur
+struct State { int c, o; };      // fld[] indices of u_n and u_{n-1}
+
+static void other_two(const State& s, int base, int& a, int& b) {
+    int f[2], k = 0;
+    for (int i = base; i < base + 4 && k < 2; ++i) if (i != s.c && i != s.o) f[k++] = i;
+    a = f[0]; b = f[1];
+}
+static State advance_state(const fwi_fd2d* p, State s, int base, int nsteps) {
+    if (p->variant == 2 && p->ny == 1) {
+        for (int k = 0; k + 1 < nsteps; k += 2) { int a, b; other_two(s, base, a, b); s = State{a, b}; }
+        if (nsteps & 1) s = State{s.o, s.c};
+        return s;
+    }
+    if (nsteps & 1) s = State{s.o, s.c};
+    return s;
+}
+
+template <int CZ, int NW>
+static int launch_tb2_cfg(fwi_fd2d* p, int mode, const State& s, int jc, int jd, const PointList* inj_ext, const PointList* inj_own,
+                          const float* inj1, const float* inj2, const PointList* rec, float* rec1, float* rec2, float* snap1,
+                          float* snap2, cudaStream_t st) {
+    Tb2Args a{};
+    a.out_new = p->fld[jc]; a.out_mid = p->fld[jd]; a.gx = p->gx; a.gz = p->gz; a.m = p->m; a.snap1 = snap1; a.snap2 = snap2; a.acc = p->acc;
+    a.nx = p->nx; a.nz = p->nz; a.px = p->px;
+    const PointListDev none{nullptr, nullptr, nullptr};
+    a.inj_ext = (inj_ext && inj_ext->n) ? inj_ext->dev() : none;
+    a.inj_own = (inj_own && inj_own->n) ? inj_own->dev() : none;
+    a.inj1 = inj1; a.inj2 = inj2;
+    a.rec = (rec && rec->n) ? rec->dev() : none;
+    a.rec1 = rec1; a.rec2 = rec2;
+    const dim3 grid(p->tiles_x2, p->tiles_z2), block(NW * 32);
+    const size_t smem = ((size_t)(CZ + 16) * kT2W0 + 2 * (size_t)(CZ + 8) * kT2W1) * sizeof(float);
+    if (mode == STEP_FWD) fd2d_tb2_kernel<CZ, NW, STEP_FWD><<<grid, block, smem, st>>>(p->tb_cur[s.c], p->tb_old[s.o], p->tb_m, a);
+    else if (mode == STEP_FWD_SAVE) fd2d_tb2_kernel<CZ, NW, STEP_FWD_SAVE><<<grid, block, smem, st>>>(p->tb_cur[s.c], p->tb_old[s.o], p->tb_m, a);
+    else fd2d_tb2_kernel<CZ, NW, STEP_ADJ><<<grid, block, smem, st>>>(p->tb_cur[s.c], p->tb_old[s.o], p->tb_m, a);
+    return FWI_OK;
+}
+template <int CZ, int NW>
+static int tb2_attrs() {
+    const int smem = (int)(((size_t)(CZ + 16) * kT2W0 + 2 * (size_t)(CZ + 8) * kT2W1) * sizeof(float));
+    FWI_CUDA(cudaFuncSetAttribute(fd2d_tb2_kernel<CZ, NW, STEP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FWI_CUDA(cudaFuncSetAttribute(fd2d_tb2_kernel<CZ, NW, STEP_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FWI_CUDA(cudaFuncSetAttribute(fd2d_tb2_kernel<CZ, NW, STEP_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return FWI_OK;
+}
+static int launch_tb2(fwi_fd2d* p, int mode, const State& s, int jc, int jd, const PointList* inj_ext, const PointList* inj_own,
+                      const float* inj1, const float* inj2, const PointList* rec, float* rec1, float* rec2, float* snap1, float* snap2,
+                      cudaStream_t st) {
+    p->launches++;
+#define TB(CZV) if (p->cz == CZV) return launch_tb2_cfg<CZV, 8>(p, mode, s, jc, jd, inj_ext, inj_own, inj1, inj2, rec, rec1, rec2, snap1, snap2, st)
+    TB(32); TB(24); TB(16); TB(56);
+#undef TB
+    set_error("fd2d: unsupported temporal-blocking tile cz=%d", p->cz);
+    return FWI_EINVAL;
+}
+
+// forward time loop over steps [n0, n1); `s` holds the fld[] indices of (u_n, u_{n-1}) on entry and on return
 static int run_forward(fwi_fd2d* p, const float* wavelet, int n0, int n1, float* traces, bool save, size_t snap_base,
-                       int& cur, cudaStream_t st) {
-    for (int n = n0; n < n1; ++n) {
-        float* snap = save ? p->snap + (size_t)(n - snap_base) * p->plane() : nullptr;
-        int rc = launch_step(p, save ? STEP_FWD_SAVE : STEP_FWD, cur, p->fld[cur ^ 1], &p->src, wavelet + (size_t)n * p->nsrc,
+                       State& s, cudaStream_t st) {
+    const size_t pl = p->plane();
+    int n = n0;
+    if (p->variant == 2 && p->ny == 1) {
+        for (; n + 1 < n1; n += 2) {
+            int jc, jd;
+            other_two(s, 0, jc, jd);
+            float* s1 = save ? p->snap + (size_t)(n - snap_base) * pl : nullptr;
+            int rc = launch_tb2(p, save ? STEP_FWD_SAVE : STEP_FWD, s, jc, jd, &p->src_ext2, &p->src_own2, wavelet + (size_t)n * p->nsrc,
+                                wavelet + (size_t)(n + 1) * p->nsrc, traces ? &p->rec_own2 : nullptr,
+                                traces ? traces + (size_t)n * p->nrec : nullptr, traces ? traces + (size_t)(n + 1) * p->nrec : nullptr,
+                                s1, save ? s1 + pl : nullptr, st);
+            if (rc) return rc;
+            s = State{jc, jd};
+        }
+    }
+    for (; n < n1; ++n) {
+        float* snap = save ? p->snap + (size_t)(n - snap_base) * pl : nullptr;
+        int rc = launch_step(p, save ? STEP_FWD_SAVE : STEP_FWD, s.c, p->fld[s.o], &p->src, wavelet + (size_t)n * p->nsrc,
                              traces ? &p->rec : nullptr, traces ? traces + (size_t)n * p->nrec : nullptr, snap, st);
         if (rc) return rc;
-        cur ^= 1;
+        s = State{s.o, s.c};
     }
     FWI_CUDA(cudaGetLastError());
     return FWI_OK;
 }
 
-// adjoint steps for trace rows n1-1 down to n0 (fields fld[2/3]); `acur` indexes the pair
-static int run_adjoint(fwi_fd2d* p, const float* resid, int n0, int n1, size_t snap_base, int& acur, cudaStream_t st) {
-    for (int n = n1 - 1; n >= n0; --n) {
-        int rc = launch_step(p, STEP_ADJ, 2 + acur, p->fld[2 + (acur ^ 1)], &p->rec, resid + (size_t)n * p->nrec, nullptr, nullptr,
-                             p->snap + (size_t)(n - snap_base) * p->plane(), st);
+// adjoint steps for trace rows n1-1 down to n0 (fields fld[4..7])
+static int run_adjoint(fwi_fd2d* p, const float* resid, int n0, int n1, size_t snap_base, State& s, cudaStream_t st) {
+    const size_t pl = p->plane();
+    int n = n1 - 1;
+    if (p->variant == 2 && p->ny == 1) {
+        for (; n - 1 >= n0; n -= 2) {
+            int jc, jd;
+            other_two(s, 4, jc, jd);
+            int rc = launch_tb2(p, STEP_ADJ, s, jc, jd, &p->rec_ext2, &p->rec_own2, resid + (size_t)n * p->nrec, resid + (size_t)(n - 1) * p->nrec,
+                                nullptr, nullptr, nullptr, p->snap + (size_t)(n - snap_base) * pl, p->snap + (size_t)(n - 1 - snap_base) * pl, st);
+            if (rc) return rc;
+            s = State{jc, jd};
+        }
+    }
+    for (; n >= n0; --n) {
+        int rc = launch_step(p, STEP_ADJ, s.c, p->fld[s.o], &p->rec, resid + (size_t)n * p->nrec, nullptr, nullptr,
+                             p->snap + (size_t)(n - snap_base) * pl, st);
         if (rc) return rc;
-        acur ^= 1;
+        s = State{s.o, s.c};
     }
     FWI_CUDA(cudaGetLastError());
     return FWI_OK;
@@ -524,8 +663,8 @@ static int record_forward(fwi_fd2d* p, int nt, cudaStream_t st) {
     const size_t pl = p->plane();
     FWI_CUDA(cudaMemsetAsync(p->fld[0], 0, pl * sizeof(float), st));
     FWI_CUDA(cudaMemsetAsync(p->fld[1], 0, pl * sizeof(float), st));
-    int cur = 0;
-    return run_forward(p, p->wav, 0, nt, p->nrec ? p->syn : nullptr, false, 0, cur, st);
+    State s{0, 1};
+    return run_forward(p, p->wav, 0, nt, p->nrec ? p->syn : nullptr, false, 0, s, st);
 }
 
 // The gradient of one shot as a sequence of stream operations on `st`: forward (+ snapshots or checkpoints),
@@ -535,17 +674,18 @@ static int record_gradient(fwi_fd2d* p, int nt, int seg, int nseg, cudaStream_t 
     const size_t ntr = (size_t)nt * p->nrec;
     FWI_CUDA(cudaMemsetAsync(p->fld[0], 0, pl * sizeof(float), st));
     FWI_CUDA(cudaMemsetAsync(p->fld[1], 0, pl * sizeof(float), st));
-    int cur = 0, rc;
-    std::vector<int> seg_cur(nseg, 0);
+    int rc;
+    State fs{0, 1};
+    std::vector<State> seg_state(nseg, fs);
     if (nseg == 1) {
-        rc = run_forward(p, p->wav, 0, nt, p->syn, true, 0, cur, st);
+        rc = run_forward(p, p->wav, 0, nt, p->syn, true, 0, fs, st);
         if (rc) return rc;
     } else {
         for (int s = 0; s < nseg; ++s) {
-            FWI_CUDA(cudaMemcpyAsync(p->ckpt + (size_t)(2 * s) * pl, p->fld[cur], pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            FWI_CUDA(cudaMemcpyAsync(p->ckpt + (size_t)(2 * s + 1) * pl, p->fld[cur ^ 1], pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            seg_cur[s] = cur;
-            rc = run_forward(p, p->wav, s * seg, std::min(nt, (s + 1) * seg), p->syn, false, 0, cur, st);
+            FWI_CUDA(cudaMemcpyAsync(p->ckpt + (size_t)(2 * s) * pl, p->fld[fs.c], pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            FWI_CUDA(cudaMemcpyAsync(p->ckpt + (size_t)(2 * s + 1) * pl, p->fld[fs.o], pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            seg_state[s] = fs;
+            rc = run_forward(p, p->wav, s * seg, std::min(nt, (s + 1) * seg), p->syn, false, 0, fs, st);
             if (rc) return rc;
         }
     }
@@ -553,22 +693,22 @@ static int record_gradient(fwi_fd2d* p, int nt, int seg, int nseg, cudaStream_t 
     fd_residual_kernel<<<(unsigned)std::min<size_t>(1024, (ntr + 255) / 256), 256, 0, st>>>(p->syn, p->obs, (int64_t)ntr, p->resid, p->d_J);
     FWI_CUDA(cudaGetLastError());
     p->launches += 1;
-    FWI_CUDA(cudaMemsetAsync(p->fld[2], 0, pl * sizeof(float), st));
-    FWI_CUDA(cudaMemsetAsync(p->fld[3], 0, pl * sizeof(float), st));
+    FWI_CUDA(cudaMemsetAsync(p->fld[4], 0, pl * sizeof(float), st));
+    FWI_CUDA(cudaMemsetAsync(p->fld[5], 0, pl * sizeof(float), st));
     FWI_CUDA(cudaMemsetAsync(p->acc, 0, pl * sizeof(float), st));
-    int acur = 0;
+    State as{4, 5};
     if (nseg == 1) {
-        rc = run_adjoint(p, p->resid, 0, nt, 0, acur, st);
+        rc = run_adjoint(p, p->resid, 0, nt, 0, as, st);
         if (rc) return rc;
     } else {
         for (int s = nseg - 1; s >= 0; --s) {
             const int n0 = s * seg, n1 = std::min(nt, (s + 1) * seg);
-            int c = seg_cur[s];
-            FWI_CUDA(cudaMemcpyAsync(p->fld[c], p->ckpt + (size_t)(2 * s) * pl, pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            FWI_CUDA(cudaMemcpyAsync(p->fld[c ^ 1], p->ckpt + (size_t)(2 * s + 1) * pl, pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            State c = seg_state[s];
+            FWI_CUDA(cudaMemcpyAsync(p->fld[c.c], p->ckpt + (size_t)(2 * s) * pl, pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            FWI_CUDA(cudaMemcpyAsync(p->fld[c.o], p->ckpt + (size_t)(2 * s + 1) * pl, pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
             rc = run_forward(p, p->wav, n0, n1, nullptr, true, n0, c, st);     // recompute w_n for this segment
             if (rc) return rc;
-            rc = run_adjoint(p, p->resid, n0, n1, n0, acur, st);
+            rc = run_adjoint(p, p->resid, n0, n1, n0, as, st);
             if (rc) return rc;
         }
     }
@@ -582,7 +722,7 @@ static int run_cached(fwi_fd2d* p, int kind, int nt, int seg, int nseg, F&& reco
     for (auto& g : p->graphs)
         if (g.kind == kind && g.nt == nt && g.nsrc == p->nsrc && g.nrec == p->nrec && g.seg == seg && g.nseg == nseg) {
             FWI_CUDA(cudaGraphLaunch(g.exec, p->work));
-            p->launches += (kind == 0) ? nt : (int64_t)(nseg == 1 ? 2 : 3) * nt + 1;
+            p->launches += g.kernels;
             return FWI_OK;
         }
     cudaGraph_t graph = nullptr;
@@ -590,6 +730,7 @@ static int run_cached(fwi_fd2d* p, int kind, int nt, int seg, int nseg, F&& reco
     const int64_t l0 = p->launches;
     int rc = record(p->work);
     cudaError_t e = cudaStreamEndCapture(p->work, &graph);
+    const int64_t kernels = p->launches - l0;
     p->launches = l0;
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) { set_error("stream capture failed: %s", cudaGetErrorString(e)); return FWI_ECUDA; }
@@ -598,9 +739,9 @@ static int run_cached(fwi_fd2d* p, int kind, int nt, int seg, int nseg, F&& reco
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return FWI_ECUDA; }
     if (p->graphs.size() >= 6) { cudaGraphExecDestroy(p->graphs.front().exec); p->graphs.erase(p->graphs.begin()); }
-    p->graphs.push_back(GraphEntry{kind, nt, p->nsrc, p->nrec, seg, nseg, exec});
+    p->graphs.push_back(GraphEntry{kind, nt, p->nsrc, p->nrec, seg, nseg, exec, kernels});
     FWI_CUDA(cudaGraphLaunch(exec, p->work));
-    p->launches += (kind == 0) ? nt : (int64_t)(nseg == 1 ? 2 : 3) * nt + 1;
+    p->launches += kernels;
     return FWI_OK;
 }
 
@@ -639,7 +780,7 @@ static int create_plan(int device, int nz, int ny, int nx, float h, float dt, in
     FWI_CUDA(cudaMalloc(&p->m, pl * sizeof(float)));
     FWI_CUDA(cudaMalloc(&p->vp, pl * sizeof(float)));
     FWI_CUDA(cudaMalloc(&p->acc, pl * sizeof(float)));
-    for (int i = 0; i < 4; ++i) { FWI_CUDA(cudaMalloc(&p->fld[i], pl * sizeof(float))); FWI_CUDA(cudaMemset(p->fld[i], 0, pl * sizeof(float))); }
+    for (int i = 0; i < 8; ++i) { FWI_CUDA(cudaMalloc(&p->fld[i], pl * sizeof(float))); FWI_CUDA(cudaMemset(p->fld[i], 0, pl * sizeof(float))); }
     FWI_CUDA(cudaMalloc(&p->gx, p->px * sizeof(float)));
     FWI_CUDA(cudaMalloc(&p->gz, nz * sizeof(float)));
     FWI_CUDA(cudaMalloc(&p->gy, ny * sizeof(float)));
@@ -665,6 +806,7 @@ static int create_plan(int device, int nz, int ny, int nx, float h, float dt, in
     rc = make_stream_partition(p);
     if (rc) return rc;
     if ((rc = stream_attrs<8, 4>()) || (rc = stream_attrs<4, 8>()) || (rc = stream_attrs<6, 5>()) || (rc = stream_attrs<8, 3>()) || (rc = stream_attrs<12, 3>())) return rc;
+    if ((rc = tb2_attrs<32, 8>()) || (rc = tb2_attrs<24, 8>()) || (rc = tb2_attrs<16, 8>()) || (rc = tb2_attrs<56, 8>())) return rc;
     const int smem3 = k3NP * k3PlaneFloats * (int)sizeof(float);
     FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
@@ -688,7 +830,7 @@ int fwi_fd2d_destroy(fwi_fd2d* p) {
     if (p->work) cudaStreamSynchronize(p->work);
     drop_graphs(p);
     cudaFree(p->m); cudaFree(p->vp); cudaFree(p->acc); cudaFree(p->gx); cudaFree(p->gz); cudaFree(p->gy); cudaFree(p->d_J);
-    for (int i = 0; i < 4; ++i) cudaFree(p->fld[i]);
+    for (int i = 0; i < 8; ++i) cudaFree(p->fld[i]);
     if (p->snap) cudaFree(p->snap);
     if (p->ckpt) cudaFree(p->ckpt);
     if (p->resid) cudaFree(p->resid);
@@ -696,6 +838,7 @@ int fwi_fd2d_destroy(fwi_fd2d* p) {
     if (p->obs) cudaFree(p->obs);
     if (p->wav) cudaFree(p->wav);
     p->src.release(); p->rec.release();
+    p->src_ext2.release(); p->src_own2.release(); p->rec_ext2.release(); p->rec_own2.release();
     if (p->d_u0) cudaFree(p->d_u0);
     if (p->ev_in) cudaEventDestroy(p->ev_in);
     if (p->ev_out) cudaEventDestroy(p->ev_out);
@@ -728,6 +871,19 @@ int fwi_fd2d_set_tile(fwi_fd2d* p, int bz, int nw) {
     p->variant = 0; p->bz = bz; p->nw = nw;
     p->tiles_z = (p->nz + bz - 1) / bz;
     p->src.release(); p->rec.release(); p->nsrc = p->nrec = 0;      // tile binning changed
+    return make_tmaps(p);
+}
+
+int fwi_fd2d_set_tb2(fwi_fd2d* p, int cz) {
+    FWI_REQUIRE(p, "fwi_fd2d_set_tb2: NULL plan");
+    FWI_REQUIRE(cz == 16 || cz == 24 || cz == 32 || cz == 56, "fwi_fd2d_set_tb2: unsupported core rows %d (16, 24, 32, 56)", cz);
+    FWI_REQUIRE(p->ny == 1, "fwi_fd2d_set_tb2: 2-D plans only");
+    DeviceGuard g(p->device);
+    FWI_CUDA(cudaStreamSynchronize(p->work));
+    drop_graphs(p);
+    p->variant = 2; p->cz = cz;
+    p->src.release(); p->rec.release(); p->nsrc = p->nrec = 0;
+    p->src_ext2.release(); p->src_own2.release(); p->rec_ext2.release(); p->rec_own2.release();
     return make_tmaps(p);
 }
 
@@ -766,6 +922,12 @@ static int set_geometry(fwi_fd2d* p, int nsrc, const int* src_z, const int* src_
     if (rc) return rc;
     rc = build_point_list(p, p->rec, nrec, rec_z, rec_y, rec_x, "receiver");
     if (rc) return rc;
+    if (p->variant == 2 && p->ny == 1) {
+        if ((rc = build_point_list_tb2(p, p->src_ext2, nsrc, src_z, src_x, true))) return rc;
+        if ((rc = build_point_list_tb2(p, p->src_own2, nsrc, src_z, src_x, false))) return rc;
+        if ((rc = build_point_list_tb2(p, p->rec_ext2, nrec, rec_z, rec_x, true))) return rc;
+        if ((rc = build_point_list_tb2(p, p->rec_own2, nrec, rec_z, rec_x, false))) return rc;
+    }
     p->nsrc = nsrc; p->nrec = nrec;
     return FWI_OK;
 }
@@ -797,7 +959,7 @@ int fwi_fd2d_forward(fwi_fd2d* p, const float* wavelet_dev, int nt, float* trace
     rc = run_cached(p, 0, nt, 0, 0, [&](cudaStream_t st) { return record_forward(p, nt, st); });
     if (rc) return rc;
     if (nt * p->nrec) FWI_CUDA(cudaMemcpyAsync(traces_dev, p->syn, (size_t)nt * p->nrec * sizeof(float), cudaMemcpyDeviceToDevice, p->work));
-    p->fwd_cur = nt & 1;
+    { State fs = advance_state(p, State{0, 1}, 0, nt); p->fwd_c = fs.c; p->fwd_o = fs.o; }
     return leave(p, user);
 }
 
@@ -807,7 +969,7 @@ int fwi_fd2d_wavefield(fwi_fd2d* p, int which, float* out_dev, void* stream) {
     cudaStream_t user = (cudaStream_t)stream;
     int rc = enter(p, user);
     if (rc) return rc;
-    const float* src = (which == 0) ? p->fld[p->fwd_cur] : (which == 1 ? p->fld[p->fwd_cur ^ 1] : p->acc);
+    const float* src = (which == 0) ? p->fld[p->fwd_c] : (which == 1 ? p->fld[p->fwd_o] : p->acc);
     dim3 grid(p->rows(), (p->nx + 127) / 128);
     fd_unpitch_kernel<<<grid, 128, 0, p->work>>>(src, p->rows(), p->nx, p->px, out_dev);
     FWI_CUDA(cudaGetLastError());
@@ -851,7 +1013,7 @@ int fwi_fd2d_gradient(fwi_fd2d* p, const float* wavelet_dev, const float* obs_de
     FWI_CUDA(cudaMemcpyAsync(p->obs, obs_dev, ntr * sizeof(float), cudaMemcpyDeviceToDevice, p->work));
     rc = run_cached(p, 1, nt, seg, nseg, [&](cudaStream_t st) { return record_gradient(p, nt, seg, nseg, st); });
     if (rc) return rc;
-    p->fwd_cur = nt & 1;
+    { State fs = advance_state(p, State{0, 1}, 0, nt); p->fwd_c = fs.c; p->fwd_o = fs.o; }
     dim3 grid(p->rows(), (p->nx + 127) / 128);
     fd_grad_finalize_kernel<<<grid, 128, 0, p->work>>>(p->acc, p->vp, p->rows(), p->nx, p->px, grad_dev);
     FWI_CUDA(cudaGetLastError());
@@ -877,7 +1039,7 @@ int fwi_fd_set_profiles(fwi_fd2d* p, const float* gz_host, const float* gy_host,
     return FWI_OK;
 }
 
-void* fwi_fd_field_ptr(fwi_fd2d* p, int idx) { return (p && idx >= 0 && idx < 4) ? (void*)p->fld[idx] : nullptr; }
+void* fwi_fd_field_ptr(fwi_fd2d* p, int idx) { return (p && idx >= 0 && idx < 8) ? (void*)p->fld[idx] : nullptr; }
 int fwi_fd_pitch(fwi_fd2d* p) { return p ? p->px : 0; }
 
 int fwi_fd_reserve_snapshots(fwi_fd2d* p, int nsteps) {
@@ -893,8 +1055,8 @@ int fwi_fd_reset(fwi_fd2d* p, int pair, void* stream) {
     DeviceGuard g(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t pl = p->plane();
-    FWI_CUDA(cudaMemsetAsync(p->fld[2 * pair], 0, pl * sizeof(float), st));
-    FWI_CUDA(cudaMemsetAsync(p->fld[2 * pair + 1], 0, pl * sizeof(float), st));
+    FWI_CUDA(cudaMemsetAsync(p->fld[4 * pair], 0, pl * sizeof(float), st));
+    FWI_CUDA(cudaMemsetAsync(p->fld[4 * pair + 1], 0, pl * sizeof(float), st));
     if (pair == 1) FWI_CUDA(cudaMemsetAsync(p->acc, 0, pl * sizeof(float), st));
     return FWI_OK;
 }
@@ -908,13 +1070,13 @@ int fwi_fd_step(fwi_fd2d* p, int mode, int cur, const float* inj_vals_dev, float
     FWI_REQUIRE(mode >= 0 && mode <= 2 && (cur == 0 || cur == 1), "fwi_fd_step: bad mode / cur");
     FWI_REQUIRE(mode == 0 || (snap_index >= 0 && (size_t)(snap_index + 1) * p->plane() <= p->snap_steps), "fwi_fd_step: snapshot %lld not reserved", (long long)snap_index);
     DeviceGuard g(p->device);
-    const int base = (mode == STEP_ADJ) ? 2 : 0;
+    const int base = (mode == STEP_ADJ) ? 4 : 0;
     float* snap = (mode == 0) ? nullptr : p->snap + (size_t)snap_index * p->plane();
     int rc = launch_step(p, mode, base + cur, p->fld[base + (cur ^ 1)], mode == STEP_ADJ ? &p->rec : &p->src, inj_vals_dev,
                          (mode != STEP_ADJ && rec_out_dev) ? &p->rec : nullptr, rec_out_dev, snap, (cudaStream_t)stream);
     if (rc) return rc;
     FWI_CUDA(cudaGetLastError());
-    if (mode != STEP_ADJ) p->fwd_cur = cur ^ 1;
+    if (mode != STEP_ADJ) { p->fwd_c = cur ^ 1; p->fwd_o = cur; }
     return FWI_OK;
 }
 

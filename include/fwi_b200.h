@@ -138,6 +138,9 @@ int fwi_fd2d_set_tile(fwi_fd2d* plan, int bz, int nw);
 /* Select the persistent streaming step kernel with nw warps per SM and nc TMA pipeline slots per warp.
  * Clears the geometry. */
 int fwi_fd2d_set_stream(fwi_fd2d* plan, int nw, int nc);
+/* Select the temporally blocked kernel: two leapfrog steps per pass on 120 x cz core tiles (cz in 16, 24, 32, 56);
+ * an odd leftover step runs the one-step tile kernel.  Clears the geometry. */
+int fwi_fd2d_set_tb2(fwi_fd2d* plan, int cz);
 /* Replay the time loops as cached CUDA graphs (default on) or as individual launches (0). */
 int fwi_fd2d_set_graphs(fwi_fd2d* plan, int enable);
 /* Cap (bytes) on the forward-field storage used by fwi_fd2d_gradient; 0 = 85 % of free HBM.  When all nt
@@ -174,7 +177,7 @@ int fwi_fd3d_set_geometry(fwi_fd2d* plan, int nsrc, const int* src_z_host, const
  * Used by the slab-decomposed multi-GPU path (acoustic.SlabPropagator), which exchanges the 4-plane halos of the
  * slab with its neighbours over NCCL/NVLink between steps. */
 int fwi_fd_set_profiles(fwi_fd2d* plan, const float* gz_host, const float* gy_host, const float* gx_host); /* override sponge profiles (nullable each) */
-void* fwi_fd_field_ptr(fwi_fd2d* plan, int idx);   /* wavefield buffer idx: 0/1 forward pair, 2/3 adjoint pair; layout [rows][pitch] */
+void* fwi_fd_field_ptr(fwi_fd2d* plan, int idx);   /* wavefield buffer idx: 0/1 forward pair, 4/5 adjoint pair; layout [rows][pitch] */
 int fwi_fd_pitch(fwi_fd2d* plan);                  /* floats per row (nx rounded up to 32) */
 int fwi_fd_reserve_snapshots(fwi_fd2d* plan, int nsteps);
 int fwi_fd_reset(fwi_fd2d* plan, int pair, void* stream);   /* zero pair 0 (forward) or 1 (adjoint + imaging sum) */

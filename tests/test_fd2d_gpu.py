@@ -59,7 +59,8 @@ def test_forward_traces_and_wavefield(ac, nz, nx, nt, nsrc):
 
 @pytest.mark.parametrize("kind,cfg", [("tile", (32, 4)), ("tile", (32, 8)), ("tile", (16, 4)), ("tile", (64, 8)),
                                       ("tile", (16, 2)), ("tile", (64, 4)), ("stream", (8, 4)), ("stream", (4, 8)),
-                                      ("stream", (6, 5)), ("stream", (8, 3)), ("stream", (12, 3)), ("graphs", False)])
+                                      ("stream", (6, 5)), ("stream", (8, 3)), ("stream", (12, 3)), ("graphs", False),
+                                      ("tb2", 32), ("tb2", 16), ("tb2", 24), ("tb2", 56)])
 def test_kernel_variants_agree(ac, kind, cfg):
     """Every step-kernel variant (one-tile-per-CTA and persistent streaming) gives the oracle's traces and gradient."""
     v, h, dt, src, rec, wav = _case(75, 300, 150, seed=3)

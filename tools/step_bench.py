@@ -19,9 +19,13 @@ def time_forward(nz, nx, nt, **kw):
 
 variants = [("tile", (16, 2)), ("stream", (8, 4)), ("tile", (32, 4)), ("tile", (16, 4))]
 if len(sys.argv) > 1:
-    variants = [tuple([a.split(":")[0], tuple(int(x) for x in a.split(":")[1].split(","))]) for a in sys.argv[1:]]
+    variants = []
+    for a in sys.argv[1:]:
+        k, v = a.split(":")
+        vals = tuple(int(x) for x in v.split(","))
+        variants.append((k, vals[0] if k == "tb2" else vals))
 for kind, cfg in variants:
-  for graphs in (True, False):
+  for graphs in ((True,) if kind == 'tb2' else (True, False)):
     pts, ts = [], []
     print("graphs =", graphs)
     for nz in (125, 500, 1000, 2000, 4000):
