@@ -265,6 +265,21 @@ def run_b200(args):
     for i in range(args.warmup):
         one_step(i, False)
     barrier()
+    # settle: the first second after the 60 GB snapshot buffer is created runs ~20 % slow (first-touch of fresh
+    # HBM pages); keep stepping (untimed) until two consecutive steps agree within 2 %, at most 12 extra steps.
+    prev = None
+    for k in range(12):
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        one_step(k % max(1, args.warmup), False)
+        s1.record()
+        torch.cuda.synchronize(dev)
+        cur_ms = s0.elapsed_time(s1)
+        if prev is not None and abs(cur_ms - prev) <= 0.02 * prev:
+            break
+        prev = cur_ms
+    grad.zero_()
+    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
