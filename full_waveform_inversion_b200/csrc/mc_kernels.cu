@@ -40,6 +40,9 @@ struct FlatConst {   // constants of the flattened (K*Tv) data array; index = no
 };
 
 enum { MODE_SSE = 0, MODE_MOM = 1, MODE_MOM_MAX = 2 };
+#ifndef MC_MIN_BLOCKS
+#define MC_MIN_BLOCKS 3
+#endif
 
 struct EvalParams {
     const float* rows;
@@ -76,7 +79,7 @@ __device__ __forceinline__ void make_coef(float (&coef)[C * NM], const float (&m
 
 // ---------------------------------------------------------------------------------------------
 template <int C, int NM, int S, int MODE>
-__global__ void __launch_bounds__(384) mc_eval_kernel(EvalParams p) {
+__global__ void __launch_bounds__(256, MC_MIN_BLOCKS) mc_eval_kernel(EvalParams p) {
     constexpr int CC = C * NM;
     constexpr int RW = row_width(CC);
     constexpr int RW4 = RW / 4;
@@ -130,28 +133,57 @@ __global__ void __launch_bounds__(384) mc_eval_kernel(EvalParams p) {
             float a0[S], a1[S];
 #pragma unroll
             for (int s = 0; s < S; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
-#pragma unroll 4
-            for (int t = tb; t < te; ++t) {
+            // two time samples per iteration: 2*S independent FMA chains per lane keep the fp32 pipe fed
+            auto finish = [&](const float (&r)[RW], const float (&v)[S]) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    if (MODE == MODE_SSE) {
+                        const float e = r[CC] - v[s];              // raw d - raw synth (FWI:515)
+                        a0[s] = fmaf(e, e, a0[s]);
+                    } else {
+                        a0[s] = fmaf(v[s], v[s], a0[s]);           // sum s'^2
+                        a1[s] = fmaf(r[CC + 1], v[s], a1[s]);      // sum d' s'
+                        if (MODE == MODE_MOM_MAX) { vmax[s] = fmaxf(vmax[s], v[s]); vmin[s] = fminf(vmin[s], v[s]); }
+                    }
+                }
+            };
+            int t = tb;
+#pragma unroll 2
+            for (; t + 1 < te; t += 2) {
+                float r0[RW], r1[RW];
+#pragma unroll
+                for (int q = 0; q < RW4; ++q) {
+                    const float4 u = __ldg(rp + (size_t)t * RW4 + q), w = __ldg(rp + (size_t)(t + 1) * RW4 + q);
+                    r0[4 * q] = u.x; r0[4 * q + 1] = u.y; r0[4 * q + 2] = u.z; r0[4 * q + 3] = u.w;
+                    r1[4 * q] = w.x; r1[4 * q + 1] = w.y; r1[4 * q + 2] = w.z; r1[4 * q + 3] = w.w;
+                }
+                float v0[S], v1[S];
+#pragma unroll
+                for (int s = 0; s < S; ++s) { v0[s] = (MODE == MODE_SSE) ? 0.f : -mu[s]; v1[s] = v0[s]; }
+#pragma unroll
+                for (int c = 0; c < CC; ++c) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) { v0[s] = fmaf(r0[c], coef[s][c], v0[s]); v1[s] = fmaf(r1[c], coef[s][c], v1[s]); }
+                }
+                finish(r0, v0);
+                finish(r1, v1);
+            }
+            for (; t < te; ++t) {
                 float r[RW];
 #pragma unroll
                 for (int q = 0; q < RW4; ++q) {
-                    float4 v = __ldg(rp + (size_t)t * RW4 + q);
-                    r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+                    const float4 u = __ldg(rp + (size_t)t * RW4 + q);
+                    r[4 * q] = u.x; r[4 * q + 1] = u.y; r[4 * q + 2] = u.z; r[4 * q + 3] = u.w;
                 }
+                float v[S];
 #pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    float v = (MODE == MODE_SSE) ? 0.f : -mu[s];
+                for (int s = 0; s < S; ++s) v[s] = (MODE == MODE_SSE) ? 0.f : -mu[s];
 #pragma unroll
-                    for (int c = 0; c < CC; ++c) v = fmaf(r[c], coef[s][c], v);
-                    if (MODE == MODE_SSE) {
-                        float e = r[CC] - v;                 // raw d - raw synth (FWI:515)
-                        a0[s] = fmaf(e, e, a0[s]);
-                    } else {
-                        a0[s] = fmaf(v, v, a0[s]);           // sum s'^2
-                        a1[s] = fmaf(r[CC + 1], v, a1[s]);   // sum d' s'
-                        if (MODE == MODE_MOM_MAX) { vmax[s] = fmaxf(vmax[s], v); vmin[s] = fminf(vmin[s], v); }
-                    }
+                for (int c = 0; c < CC; ++c) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) v[s] = fmaf(r[c], coef[s][c], v[s]);
                 }
+                finish(r, v);
             }
 #pragma unroll
             for (int s = 0; s < S; ++s) { t0[s] += (double)a0[s]; t1[s] += (double)a1[s]; }
@@ -580,7 +612,7 @@ struct fwi_mc_ctx {
     RowSet base, hr, hrflat;
     // scratch
     float* stage_M = nullptr; float* stage_sim = nullptr; float* stage_frac = nullptr; int64_t stage_cap = 0;
-    double* h_pin = nullptr; int64_t h_pin_bytes = 0;
+    double* dstage = nullptr; int64_t dstage_bytes = 0;
     double* red_sum = nullptr; float* red_max = nullptr; long long* red_arg = nullptr;
     int sm_count = 148;
     bool uploaded = false;
@@ -707,7 +739,7 @@ static int launch_eval_m(const EvalParams& p, int mode, int S, int nwarps, cudaS
 static int pick_warps(int K) {
     // warps per CTA so that ceil(K/nw)*nw wastes the least; ties -> more warps
     int best = 4; double best_w = 1e9;
-    for (int nw = 4; nw <= 12; ++nw) {
+    for (int nw = 4; nw <= 8; ++nw) {
         const double waste = (double)(((K + nw - 1) / nw) * nw) / K;
         if (waste <= best_w + 1e-12) { best_w = waste; best = nw; }
     }
@@ -755,7 +787,7 @@ int fwi_mc_destroy(fwi_mc_ctx* c) {
     if (c->stage_M) cudaFree(c->stage_M);
     if (c->stage_sim) cudaFree(c->stage_sim);
     if (c->stage_frac) cudaFree(c->stage_frac);
-    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->dstage) cudaFree(c->dstage);
     cudaFree(c->red_sum); cudaFree(c->red_max); cudaFree(c->red_arg);
     delete c;
     return FWI_OK;
@@ -969,8 +1001,13 @@ int fwi_mc_eval_host(fwi_mc_ctx* c, const double* M_host, int64_t N, int n_comp,
         c->stage_cap = N;
     }
     const int64_t need = (int64_t)N * (n_comp + 3) * sizeof(double);
-    double* dbuf = nullptr;
-    FWI_CUDA(cudaMalloc(&dbuf, (size_t)need));
+    if (c->dstage_bytes < need) {
+        if (c->dstage) cudaFree(c->dstage);
+        c->dstage = nullptr; c->dstage_bytes = 0;
+        FWI_CUDA(cudaMalloc(&c->dstage, (size_t)need));
+        c->dstage_bytes = need;
+    }
+    double* dbuf = c->dstage;
     int rc = FWI_OK;
     do {
         if (cudaMemcpy(dbuf, M_host, (size_t)N * n_comp * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { rc = FWI_ECUDA; break; }
@@ -987,7 +1024,6 @@ int fwi_mc_eval_host(fwi_mc_ctx* c, const double* M_host, int64_t N, int n_comp,
         mc_unstage_kernel<<<(unsigned)ceil_div(N, 256), 256>>>(c->stage_sim, N, dbuf);
         if (cudaMemcpy(sim_host, dbuf, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = FWI_ECUDA; break; }
     } while (0);
-    cudaFree(dbuf);
     if (rc == FWI_ECUDA) set_error("fwi_mc_eval_host: CUDA copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     return rc;
 }
