@@ -590,6 +590,37 @@ __global__ void mc_normalise_kernel(const float* __restrict__ L, int64_t N, doub
     if (i < N) out[i] = (float)((double)L[i] * scale);
 }
 
+
+// --------------------------------------------------------------------------------------------- input preparation (f2)
+// Green's-function conditioning of load_input_data / get_overall_real_and_green_func_data (FWI:92-111, FWI:178-196):
+// integer time shift (np.roll along t) with the wrapped head zeroed, optional per-trace phase-window cut, unit
+// scaling.  float64 in, float64 out, the two scale factors applied one after the other exactly like the
+// reference's `*(10**3)` then `*(10**7)`, so the result is bit-identical to NumPy's.
+__global__ void mc_prepare_kernel(const double* __restrict__ raw, int K, int C, int T, int NM, const int* __restrict__ shift,
+                                  int zero_head, const int* __restrict__ cut_start, int Tout, double scale1, double scale2,
+                                  double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)K * C * Tout * NM;
+    if (i >= total) return;
+    const int med = (int)(i % NM);
+    const int64_t j = i / NM;
+    const int t_out = (int)(j % Tout);
+    const int c = (int)((j / Tout) % C);
+    const int k = (int)(j / ((int64_t)Tout * C));
+    const int t = t_out + (cut_start ? cut_start[k] : 0);          // index in the shifted, uncut trace (FWI:108-109)
+    double v = 0.0;
+    if (t >= 0 && t < T) {
+        const int sh = shift ? shift[k] : 0;
+        int src = (t - sh) % T;                                     // np.roll(x, sh)[t] = x[(t - sh) mod T]   (FWI:97)
+        if (src < 0) src += T;
+        v = raw[(((int64_t)k * C + c) * T + src) * NM + med];
+        if (shift && zero_head && t < sh) v = 0.0;                  // FWI:98-99
+    }
+    if (scale1 != 1.0) v *= scale1;
+    if (scale2 != 1.0) v *= scale2;
+    out[i] = v;
+}
+
 }  // namespace fwi
 
 // =============================================================================================== host side
@@ -1026,6 +1057,19 @@ int fwi_mc_eval_host(fwi_mc_ctx* c, const double* M_host, int64_t N, int n_comp,
     } while (0);
     if (rc == FWI_ECUDA) set_error("fwi_mc_eval_host: CUDA copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     return rc;
+}
+
+
+int fwi_mc_prepare(const double* raw_dev, int K, int C, int T, int n_media, const int* shift_dev, int zero_head,
+                   const int* cut_start_dev, int cut_len, double scale1, double scale2, double* out_dev, void* stream) {
+    FWI_REQUIRE(raw_dev && out_dev && K >= 1 && C >= 1 && T >= 1 && (n_media == 1 || n_media == 2), "fwi_mc_prepare: bad arguments");
+    FWI_REQUIRE(cut_start_dev == nullptr || cut_len >= 1, "fwi_mc_prepare: cut_len must be >= 1 when cut_start is given");
+    const int Tout = cut_start_dev ? cut_len : T;
+    const int64_t total = (int64_t)K * C * Tout * n_media;
+    mc_prepare_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(raw_dev, K, C, T, n_media, shift_dev, zero_head,
+                                                                                      cut_start_dev, Tout, scale1, scale2, out_dev);
+    FWI_CUDA(cudaGetLastError());
+    return FWI_OK;
 }
 
 }  // extern "C"

@@ -121,6 +121,15 @@ int fwi_mc_reduce(const float* L_dev, int64_t N, double* sum_host, int64_t* argm
 int fwi_mc_eval_host(fwi_mc_ctx* ctx, const double* M_host, int64_t N, int n_comp, const double* media_frac_host,
                      int nfrac, int metric, int flags, double* similarity_host);
 
+/* Input preparation: the Green's-function conditioning of load_input_data /
+ * get_overall_real_and_green_func_data (FWI:92-111, FWI:178-196) as one device op.  raw_dev: float64 (K,C,T) or
+ * (K,C,T,2); shift_dev: K integer sample shifts (np.roll, FWI:97) or NULL; zero_head: zero the wrapped head
+ * (FWI:98-99); cut_start_dev: K window starts or NULL, cut_len the common window length (FWI:104-111);
+ * scale1, scale2: unit factors applied in this order (FWI:178/192 then FWI:196).  out_dev: float64
+ * (K,C,Tout[,2]), Tout = cut_len or T.  Bit-identical to the NumPy operations it replaces. */
+int fwi_mc_prepare(const double* raw_dev, int K, int C, int T, int n_media, const int* shift_dev, int zero_head,
+                   const int* cut_start_dev, int cut_len, double scale1, double scale2, double* out_dev, void* stream);
+
 /* ===================================================================== Track B (2-D acoustic)
  * No reference counterpart exists: the specification these entry points implement is
  * frozen in oracle/fd_oracle.py (sections B1-B4 of its header), which is what each comment cites. */

@@ -41,6 +41,7 @@ WANTED = {
     "generate_random_DC_crack_coupled_tensor", "generate_random_single_force_crack_uncoupled_tensor",
     "variance_reduction", "cross_corr_comparison", "cross_corr_comparison_shift_allowed",
     "pearson_correlation_comparison", "gaussian_comparison", "compare_synth_to_real_waveforms",
+    "load_input_data", "load_input_data_multiple_media", "get_overall_real_and_green_func_data",
 }
 GENERATOR = {
     "full_mt": "generate_random_MT",
@@ -95,13 +96,17 @@ def load_reference_namespace(replay):
         if not name.startswith("__"):
             setattr(np_proxy, name, getattr(np, name))
     np_proxy.random = replay
-    ns = {"np": np_proxy, "signal": signal, "eigh": eigh, "random": replay, "math": math}
+    ns = {"np": np_proxy, "signal": signal, "eigh": eigh, "random": replay, "math": math, "sys": sys}
     for a, b in zip(starts[:-1], starts[1:]):
         name = lines[a][4:].split("(")[0].strip()
         if name not in WANTED:
             continue
-        body = "\n".join(lines[a:b])
-        # stop at the "# ---- End of defining" banner if it trails the last def
+        body_lines = lines[a:b]
+        if name == "load_input_data_multiple_media":
+            # the one Python-2 statement on this path is a print inside an error branch (FWI:124); blank it at load
+            # time so the function body compiles - the arithmetic is untouched
+            body_lines = [(ln[: len(ln) - len(ln.lstrip())] + "pass") if ln.lstrip().startswith("print ") else ln for ln in body_lines]
+        body = "\n".join(body_lines)
         exec(compile(body, "%s:%d" % (REF, a + 1), "exec"), ns)
     missing = WANTED - set(ns)
     if missing:
@@ -209,6 +214,40 @@ def main():
     out.update(med_d=d2, med_G=G2, med_M=M2, med_f1=f1, med_f3=f3,
                med_phase_index=np.array([orc.PHASE_ORDER.index(x) for x in labels]),
                med_sim_single=sim_single, med_sim_phase=sim_phase)
+
+    # ---- input preparation (FWI:75-197): files on disk -> conditioned arrays, via the reference's own loaders ----
+    import tempfile
+    rng = np.random.default_rng(77)
+    K, T = 5, 48
+    with tempfile.TemporaryDirectory() as tmp:
+        real = rng.standard_normal((K, T))
+        mt1, mt2 = rng.standard_normal((K, T, 6)), rng.standard_normal((K, T, 6))      # files hold (T, C) (FWI:90 transposes)
+        sf1, sf2 = rng.standard_normal((K, T, 3)), rng.standard_normal((K, T, 3))
+        names = {"real": [], "mt": [], "sf": [], "mt2": [], "sf2": []}
+        for k in range(K):
+            for key, arr in (("real", real), ("mt", mt1), ("sf", sf1), ("mt2", mt2), ("sf2", sf2)):
+                fn = "%s_%d.txt" % (key, k)
+                np.savetxt(os.path.join(tmp, fn), arr[k], fmt="%.17e")
+                names[key].append(fn)
+        sh_mt, sh_sf = [3, 0, 5, 2, 7], [2, 1, 4, 2, 6]
+        cuts = [4, 0, 9, 3, 6]
+        cases = {
+            "prep_a": dict(itype="full_mt", kw=dict(manual_indices_time_shift_MT=sh_mt)),
+            "prep_b": dict(itype="single_force_crack_no_coupling", kw=dict(manual_indices_time_shift_MT=sh_mt, manual_indices_time_shift_SF=sh_sf,
+                                                                           cut_phase_start_vals=cuts, cut_phase_length=30)),
+            "prep_c": dict(itype="single_force", kw=dict(manual_indices_time_shift_SF=sh_sf, set_pre_time_shift_values_to_zero_switch=False)),
+            "prep_d": dict(itype="DC", kw=dict(manual_indices_time_shift_MT=sh_mt, cut_phase_start_vals=cuts, cut_phase_length=25,
+                                               invert_for_ratio_of_multiple_media_greens_func_switch=True, green_func_fnames_split_index=K)),
+            "prep_e": dict(itype="DC_single_force_no_coupling", kw=dict()),
+        }
+        for key, c in cases.items():
+            multi = c["kw"].get("invert_for_ratio_of_multiple_media_greens_func_switch", False)
+            mtn = names["mt"] + (names["mt2"] if multi else [])
+            sfn = names["sf"] + (names["sf2"] if multi else [])
+            r, g = ref["get_overall_real_and_green_func_data"](tmp, names["real"], mtn, sfn, c["itype"], **c["kw"])
+            out[key + "_real"], out[key + "_G"] = r, g
+        out.update(prep_file_real=real, prep_file_mt=mt1, prep_file_sf=sf1, prep_file_mt2=mt2, prep_file_sf2=sf2,
+                   prep_sh_mt=np.array(sh_mt), prep_sh_sf=np.array(sh_sf), prep_cuts=np.array(cuts))
 
     dst = os.path.join(os.path.dirname(HERE), "tests", "golden", "track_a_reference.npz")
     np.savez_compressed(dst, **out)

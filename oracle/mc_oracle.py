@@ -373,3 +373,25 @@ def synthetic_inputs(K=21, C=9, T=512, seed=0, noise=0.3, n_media=1):
     G1 = G if n_media == 1 else G.mean(-1)
     d = np.einsum("kct,c->kt", G1, m_true) + noise * rng.standard_normal((K, T))
     return d, G, m_true
+
+
+# --------------------------------------------------------------------------- input preparation (f2)
+def prepare_green_functions(raw, shifts=(), cut_starts=(), cut_length=0, zero_head=True, scale1=1.0, scale2=1.0):
+    """Roll each trace's Green's functions along t by an integer shift and zero the wrapped head (FWI:94-101),
+    optionally cut a window per trace (FWI:104-111), apply the unit factors in order (FWI:178/192, FWI:196).
+    raw (K,C,T) or (K,C,T,2)."""
+    raw = np.asarray(raw, float)
+    G = raw.copy()
+    if len(shifts) > 0:
+        G = np.zeros_like(raw)
+        for i, sh in enumerate(shifts):
+            G[i] = np.roll(raw[i], sh, axis=1)
+            if zero_head:
+                G[i, :, 0:sh] = 0.0
+    if len(cut_starts) > 0:
+        G = np.stack([G[i, :, int(s): int(s) + int(cut_length)] for i, s in enumerate(cut_starts)])
+    if scale1 != 1.0:
+        G = G * scale1
+    if scale2 != 1.0:
+        G = G * scale2
+    return G
