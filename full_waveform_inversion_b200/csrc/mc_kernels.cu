@@ -621,6 +621,87 @@ __global__ void mc_prepare_kernel(const double* __restrict__ raw, int K, int C, 
     out[i] = v;
 }
 
+
+// --------------------------------------------------------------------------------------------- posterior reductions (f4)
+// The consumer's per-sample Python loops (plot_full_waveform_inversion.py, cited PLOT:<line>) as histogram kernels.
+// float64 throughout so that bin assignment matches NumPy's; block-private shared histograms, one flush per block.
+__device__ __forceinline__ int nearest_label(double v, double first, double step, int n) {
+    // index of the label closest to v in arange(first, ..., step) (find_nearest, PLOT:84-86; ties -> lower index)
+    if (!(v == v)) return 0;                                   // NaN: argmin of all-NaN is 0
+    double q = (v - first) / step;
+    int i = (int)floor(q + 0.5);
+    if (q + 0.5 == (double)i && i > 0) {                        // exact tie: argmin keeps the first (lower) label
+        const double dl = fabs(first + (i - 1) * step - v), dh = fabs(first + i * step - v);
+        if (dl <= dh) i -= 1;
+    }
+    return min(max(i, 0), n - 1);
+}
+
+// mode 0: theta-phi 5-degree histogram of force vectors weighted by MTp (PLOT:522-555, single_force branch)
+// mode 1: percentage histograms of the amp-frac row, f and 1-f, 101 one-percent bins (PLOT:943-960)
+// mode 2: lune delta-gamma counts of 6-vectors from the eigenvalues of the 3x3 tensor (PLOT:1011-1059)
+__global__ void mc_hist_kernel(int mode, const float* __restrict__ MTs, int64_t ldn, const float* __restrict__ MTp,
+                               const long long* __restrict__ idx, int64_t n, int row0, double* __restrict__ hist, int nbins) {
+    extern __shared__ double sh[];
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    const double PI = 3.14159265358979323846;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = idx ? idx[t] : t;
+        if (mode == 0) {
+            // x, y, z in NED from the (E, N, D)-ordered force: x = F[1], y = F[0], z = -F[2]  (PLOT:528-530)
+            const double x = MTs[(int64_t)(row0 + 1) * ldn + j], y = MTs[(int64_t)row0 * ldn + j], z = -(double)MTs[(int64_t)(row0 + 2) * ldn + j];
+            const double r = sqrt(x * x + y * y + z * z);
+            const double theta = acos(z / r);                                   // PLOT:478
+            double phi;
+            if (y == 0.0) phi = (x >= 0.0) ? 0.0 : PI;                          // PLOT:480-484
+            else {
+                const double a = acos(x / (r * sin(theta)));
+                phi = (y > 0.0) ? a : 2.0 * PI - a;                             // PLOT:485-488
+            }
+            const int it = nearest_label(theta, PI / 360.0, 5.0 * PI / 180.0, 36);     // PLOT:524
+            const int ip = nearest_label(phi, PI / 720.0, 5.0 * PI / 180.0, 72);       // PLOT:525
+            atomicAdd(&sh[it * 72 + ip], (double)MTp[j]);
+        } else if (mode == 1) {
+            const double p = MTp[j];
+            if (p != 0.0) {                                                     // PLOT:951
+                const double f = MTs[(int64_t)row0 * ldn + j];
+                atomicAdd(&sh[nearest_label(f * 100.0, 0.0, 1.0, 101)], p);                // PLOT:957-958
+                atomicAdd(&sh[101 + nearest_label((1.0 - f) * 100.0, 0.0, 1.0, 101)], p);  // PLOT:960-961
+            }
+        } else {
+            double m[6];
+            for (int c = 0; c < 6; ++c) m[c] = MTs[(int64_t)(row0 + c) * ldn + j];
+            const double s2 = 0.70710678118654752440;
+            const double a11 = m[0], a22 = m[1], a33 = m[2], a12 = m[3] * s2, a13 = m[4] * s2, a23 = m[5] * s2;   // PLOT:93-97
+            // eigenvalues of a symmetric 3x3 (trigonometric form), l1 >= l2 >= l3
+            const double q = (a11 + a22 + a33) / 3.0;
+            const double p1 = a12 * a12 + a13 * a13 + a23 * a23;
+            const double p2 = (a11 - q) * (a11 - q) + (a22 - q) * (a22 - q) + (a33 - q) * (a33 - q) + 2.0 * p1;
+            double l1, l2, l3;
+            if (p2 <= 0.0) { l1 = l2 = l3 = q; }
+            else {
+                const double pp = sqrt(p2 / 6.0);
+                const double b11 = (a11 - q) / pp, b22 = (a22 - q) / pp, b33 = (a33 - q) / pp, b12 = a12 / pp, b13 = a13 / pp, b23 = a23 / pp;
+                double rr = 0.5 * (b11 * (b22 * b33 - b23 * b23) - b12 * (b12 * b33 - b23 * b13) + b13 * (b12 * b23 - b22 * b13));
+                rr = fmin(1.0, fmax(-1.0, rr));
+                const double ph = acos(rr) / 3.0;
+                l1 = q + 2.0 * pp * cos(ph);
+                l3 = q + 2.0 * pp * cos(ph + 2.0 * PI / 3.0);
+                l2 = 3.0 * q - l1 - l3;
+            }
+            const double gamma = atan((-l1 + 2.0 * l2 - l3) / (sqrt(3.0) * (l1 - l3)));                       // PLOT:1026
+            const double beta = acos((l1 + l2 + l3) / (sqrt(3.0) * sqrt(l1 * l1 + l2 * l2 + l3 * l3)));        // PLOT:1027
+            const double delta = PI / 2.0 - beta;                                                              // PLOT:1028
+            const double bs = PI / 120.0;
+            const int id = nearest_label(delta, -PI / 2.0, bs, 122), ig = nearest_label(gamma, -PI / 6.0, bs, 41);   // PLOT:1041-1042, 1056-1057
+            atomicAdd(&sh[id * 41 + ig], 1.0);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x) if (sh[i] != 0.0) atomicAdd(&hist[i], sh[i]);
+}
+
 }  // namespace fwi
 
 // =============================================================================================== host side
@@ -1068,6 +1149,21 @@ int fwi_mc_prepare(const double* raw_dev, int K, int C, int T, int n_media, cons
     const int64_t total = (int64_t)K * C * Tout * n_media;
     mc_prepare_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(raw_dev, K, C, T, n_media, shift_dev, zero_head,
                                                                                       cut_start_dev, Tout, scale1, scale2, out_dev);
+    FWI_CUDA(cudaGetLastError());
+    return FWI_OK;
+}
+
+
+int fwi_mc_posterior_hist(int mode, const float* MTs_dev, int64_t ldn, const float* MTp_dev, const int64_t* idx_dev, int64_t n,
+                          int row0, double* hist_dev, void* stream) {
+    FWI_REQUIRE(mode >= 0 && mode <= 2 && MTs_dev && hist_dev && n >= 0 && ldn >= 1 && row0 >= 0, "fwi_mc_posterior_hist: bad arguments");
+    FWI_REQUIRE(mode == 2 || MTp_dev, "fwi_mc_posterior_hist: MTp_dev is required for modes 0 and 1");
+    const int nbins = (mode == 0) ? 36 * 72 : (mode == 1 ? 202 : 122 * 41);   // np.arange(-pi/2, pi/2 + bs, bs) has 122 labels
+    cudaStream_t st = (cudaStream_t)stream;
+    FWI_CUDA(cudaMemsetAsync(hist_dev, 0, nbins * sizeof(double), st));
+    if (n == 0) return FWI_OK;
+    const int blocks = (int)std::min<int64_t>(296, ceil_div(n, 256));
+    mc_hist_kernel<<<blocks, 256, nbins * sizeof(double), st>>>(mode, MTs_dev, ldn, MTp_dev, (const long long*)idx_dev, n, row0, hist_dev, nbins);
     FWI_CUDA(cudaGetLastError());
     return FWI_OK;
 }

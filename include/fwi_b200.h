@@ -130,6 +130,16 @@ int fwi_mc_eval_host(fwi_mc_ctx* ctx, const double* M_host, int64_t N, int n_com
 int fwi_mc_prepare(const double* raw_dev, int K, int C, int T, int n_media, const int* shift_dev, int zero_head,
                    const int* cut_start_dev, int cut_len, double scale1, double scale2, double* out_dev, void* stream);
 
+/* Posterior reductions: the per-sample Python loops of plot_full_waveform_inversion.py (PLOT)
+ * as float64 histogram kernels over the device-resident MTs (rows, ldn) / MTp.  idx_dev: NULL (all n samples) or
+ * n int64 sample indices (e.g. the top fraction by MTp, PLOT:517-520, PLOT:1003-1007).
+ *   mode 0: theta-phi 5-degree bins of the force vector in rows row0..row0+2, weighted by MTp -> hist[36*72] (PLOT:522-555)
+ *   mode 1: 1 % bins of the amp-frac row (row0) f and 1-f weighted by MTp, zero-probability samples skipped
+ *           -> hist[2*101] (PLOT:943-961; the reference then doubles the edge bins, PLOT:963-966 - left to the caller)
+ *   mode 2: lune delta-gamma bins (pi/120) of the 6-vector in rows row0..row0+5, counts -> hist[122*41] (PLOT:1011-1059) */
+int fwi_mc_posterior_hist(int mode, const float* MTs_dev, int64_t ldn, const float* MTp_dev, const int64_t* idx_dev, int64_t n,
+                          int row0, double* hist_dev, void* stream);
+
 /* ===================================================================== Track B (2-D acoustic)
  * No reference counterpart exists: the specification these entry points implement is
  * frozen in oracle/fd_oracle.py (sections B1-B4 of its header), which is what each comment cites. */

@@ -249,6 +249,47 @@ def main():
         out.update(prep_file_real=real, prep_file_mt=mt1, prep_file_sf=sf1, prep_file_mt2=mt2, prep_file_sf2=sf2,
                    prep_sh_mt=np.array(sh_mt), prep_sh_sf=np.array(sh_sf), prep_cuts=np.array(cuts))
 
+    # ---- posterior reductions (plot_full_waveform_inversion.py): the reference's own helper functions, driven by
+    # the binning loops of PLOT:517-555, PLOT:943-966 and PLOT:1041-1059 (those loops sit inside plotting
+    # functions that cannot run here, so they are restated around the live helpers) -------------------------------
+    plot_lines = open("/root/reference/plot_full_waveform_inversion.py").read().split("\n")
+    pst = [i for i, ln in enumerate(plot_lines) if ln.startswith("def ")] + [len(plot_lines)]
+    pns = {"np": np, "eigh": eigh, "math": math}
+    for a, b in zip(pst[:-1], pst[1:]):
+        nm = plot_lines[a][4:].split("(")[0].strip()
+        if nm in ("find_nearest", "get_full_MT_array", "convert_cart_coords_to_spherical_coords", "find_delta_gamm_values_from_sixMT"):
+            exec(compile("\n".join(plot_lines[a:b]), "PLOT:%d" % (a + 1), "exec"), pns)
+    rng = np.random.default_rng(31)
+    n = 4000
+    F = rng.standard_normal((3, n)); F /= np.linalg.norm(F, axis=0)
+    F[:, 0] = [0.0, 1.0, 0.0]; F[:, 1] = [0.0, -1.0, 0.0]; F[:, 2] = [1.0, 0.0, 0.0]          # y == 0 branches (PLOT:480-484)
+    MTp = rng.random(n); MTp[5:60] = 0.0; MTp /= MTp.sum()
+    top = MTp.argsort()[-int(0.1 * n):][::-1]                                                   # PLOT:517-518
+    tp = np.zeros((36, 72))
+    tl = np.arange(0. + (np.pi / 180.) / 2., np.pi, 5 * np.pi / 180.)                         # PLOT:524
+    pl = np.arange(0. + (np.pi / 360.) / 2., 2. * np.pi, 5 * 2. * np.pi / 360.)               # PLOT:525
+    for i in top:
+        r_, th, ph = pns["convert_cart_coords_to_spherical_coords"](F[1, i], F[0, i], -1 * F[2, i])   # PLOT:528-530, 549
+        tp[pns["find_nearest"](tl, th)[1], pns["find_nearest"](pl, ph)[1]] += MTp[i]                   # PLOT:550-553
+    frac = rng.random(n); frac[:4] = [0.0, 1.0, 0.005, 0.995]
+    bins = np.arange(0., 101., 1.)
+    hd, hs = np.zeros(101), np.zeros(101)
+    for i in range(n):
+        if not MTp[i] == 0:                                                                    # PLOT:951
+            hd[pns["find_nearest"](bins, frac[i] * 100.)[1]] += MTp[i]                         # PLOT:957-958
+            hs[pns["find_nearest"](bins, (1. - frac[i]) * 100.)[1]] += MTp[i]                  # PLOT:960-961
+    M6 = rng.standard_normal((6, n)); M6 /= np.linalg.norm(M6, axis=0)
+    bs = np.pi / 120.
+    dl = np.arange(-np.pi / 2, np.pi / 2 + bs, bs); gl = np.arange(-np.pi / 6, np.pi / 6 + bs, bs)   # PLOT:1041-1042
+    lune = np.zeros((len(dl), len(gl)))
+    dg = np.zeros((n, 2))
+    for a in range(n):
+        d_, g_ = pns["find_delta_gamm_values_from_sixMT"](M6[:, a])                            # PLOT:1053
+        dg[a] = d_, g_
+        lune[(np.abs(dl - d_)).argmin(), (np.abs(gl - g_)).argmin()] += 1.                     # PLOT:1056-1058
+    out.update(post_F=F, post_MTp=MTp, post_top=top, post_theta_phi=tp, post_frac=frac, post_hist_dc=hd, post_hist_sf=hs,
+               post_M6=M6, post_lune=lune, post_delta_gamma=dg)
+
     dst = os.path.join(os.path.dirname(HERE), "tests", "golden", "track_a_reference.npz")
     np.savez_compressed(dst, **out)
     print("wrote", dst, "%.1f KB" % (os.path.getsize(dst) / 1024.0))
