@@ -246,7 +246,7 @@ class SlabPropagator:
 
     HALO = 4
 
-    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=None):
+    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=None, use_graphs=True):
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("SlabPropagator needs an initialised torch.distributed process group")
@@ -269,8 +269,15 @@ class SlabPropagator:
         self.prop.set_profiles(gz=gz)
         self.fields = [self.prop.field_view(i) for i in range(8)]
         self.nsrc = self.nrec = 0
+        self.use_graphs = use_graphs
+        self._graphs = {}
 
     def close(self):
+        # captured graphs hold NCCL work: drop them (and drain the device) BEFORE the process group goes away,
+        # otherwise communicator teardown can hang
+        torch.cuda.synchronize()
+        self._graphs = {}
+        torch.cuda.synchronize()
         self.prop.close()
 
     @property
@@ -296,6 +303,7 @@ class SlabPropagator:
         self.rec_ids, r_loc = mine(rec)
         self.nsrc_global, self.nrec_global = len(src), len(rec)
         self.prop.set_geometry(s_loc, r_loc)
+        self._graphs = {}                               # captured loops hold the old list sizes
 
     def _exchange(self, idx):
         """Refresh the ghost planes of wavefield buffer idx from the neighbours' boundary planes."""
@@ -317,7 +325,7 @@ class SlabPropagator:
         return w[:, torch.as_tensor(self.src_ids, device=w.device)].contiguous() if len(self.src_ids) else \
             torch.zeros((w.shape[0], 1), dtype=torch.float32, device=w.device)
 
-    def _run(self, nt, mode, pair, inj, out, snap_offset=0, reverse=False):
+    def _loop(self, nt, mode, pair, inj, out, snap_offset, reverse):
         self.prop.reset(pair)
         cur = 0
         for k in range(nt):
@@ -327,6 +335,35 @@ class SlabPropagator:
                            snap_index=n + snap_offset if mode else -1)
             cur ^= 1
             self._exchange(4 * pair + cur)
+
+    def _run(self, nt, mode, pair, inj, out, snap_offset=0, reverse=False):
+        """nt steps + halo exchanges.  The whole loop (step kernels and NCCL send/recv) is captured once per
+        (nt, mode) into a CUDA graph over persistent staging buffers and replayed, which removes the ~0.4 ms of
+        host + NCCL launch latency per step; falls back to eager stepping if capture is not possible."""
+        if not self.use_graphs:
+            return self._loop(nt, mode, pair, inj, out, snap_offset, reverse)
+        key = (nt, mode, pair, inj.shape[1], -1 if out is None else out.shape[1], snap_offset, reverse)
+        ent = self._graphs.get(key)
+        if ent is None:
+            try:
+                inj_s = torch.empty_like(inj)
+                out_s = None if out is None else torch.empty_like(out)
+                self._exchange(4 * pair)                       # NCCL communicators / P2P channels must exist before capture
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._loop(nt, mode, pair, inj_s, out_s, snap_offset, reverse)
+                ent = (g, inj_s, out_s)
+                self._graphs[key] = ent
+            except Exception:
+                self.use_graphs = False
+                torch.cuda.synchronize()
+                return self._loop(nt, mode, pair, inj, out, snap_offset, reverse)
+        g, inj_s, out_s = ent
+        inj_s.copy_(inj)
+        g.replay()
+        if out is not None:
+            out.copy_(out_s)
 
     def _gather_traces(self, local, nt):
         full = torch.zeros((nt, self.nrec_global), dtype=torch.float32, device=local.device)
