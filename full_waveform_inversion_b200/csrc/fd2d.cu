@@ -266,7 +266,7 @@ struct fwi_fd2d {
     float h = 0, dt = 0, alpha = 0;
     int tiles_y = 1, zchunk = 0, nzch = 1;                      // 3-D tiling: 128 x 16 columns, z chunks
     float* gy = nullptr;
-    CUtensorMap tm3[8];
+    CUtensorMap tm3[8], tm3_old[8], tm3_m;
     int bz = 32, nw = 4;              // tiled variant: tile rows / warps per CTA (tunable)
     int tiles_x = 0, tiles_z = 0;
     int variant = 0;                  // 0 = one-tile-per-CTA kernel (default), 1 = persistent streaming kernel
@@ -347,6 +347,11 @@ static int make_tmaps3(fwi_fd2d* p) {
         const uint32_t box[3] = {(uint32_t)k3SX, (uint32_t)k3SY, 1u};
         int rc = encode_tiled_f32(&p->tm3[i], p->fld[i], 3, dims, strides, box);
         if (rc) return rc;
+        const uint64_t dims_p[3] = {(uint64_t)p->px, (uint64_t)p->ny, (uint64_t)p->nz};
+        const uint32_t box_o[3] = {(uint32_t)k3BX, (uint32_t)k3BY, 1u};
+        rc = encode_tiled_f32(&p->tm3_old[i], p->fld[i], 3, dims_p, strides, box_o);
+        if (rc) return rc;
+        if (i == 0 && (rc = encode_tiled_f32(&p->tm3_m, p->m, 3, dims_p, strides, box_o))) return rc;
     }
     return FWI_OK;
 }
@@ -511,10 +516,12 @@ static int launch_step3(fwi_fd2d* p, int mode, int cur, float* oldnew, const Poi
     a.rec = (rec && rec->n) ? rec->dev() : PointListDev{nullptr, nullptr, nullptr};
     a.rec_out = rec_out;
     const dim3 grid(p->tiles_x, p->tiles_y, p->nzch), block((k3CW + 1) * 32);
-    const size_t smem = (size_t)k3NP * k3PlaneFloats * sizeof(float);
-    if (mode == STEP_FWD) fd3d_step_kernel<STEP_FWD><<<grid, block, smem, st>>>(p->tm3[cur], a);
-    else if (mode == STEP_FWD_SAVE) fd3d_step_kernel<STEP_FWD_SAVE><<<grid, block, smem, st>>>(p->tm3[cur], a);
-    else fd3d_step_kernel<STEP_ADJ><<<grid, block, smem, st>>>(p->tm3[cur], a);
+    const size_t smem = ((size_t)k3NP * k3PlaneFloats + (size_t)k3NO * 2 * k3OmFloats) * sizeof(float);
+    int oi = -1;
+    for (int i = 0; i < 8; ++i) if (p->fld[i] == oldnew) oi = i;
+    if (mode == STEP_FWD) fd3d_step_kernel<STEP_FWD><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
+    else if (mode == STEP_FWD_SAVE) fd3d_step_kernel<STEP_FWD_SAVE><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
+    else fd3d_step_kernel<STEP_ADJ><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
     return FWI_OK;
 }
 
@@ -837,7 +844,7 @@ static int create_plan(int device, int nz, int ny, int nx, float h, float dt, in
     if (rc) return rc;
     if ((rc = stream_attrs<8, 4>()) || (rc = stream_attrs<4, 8>()) || (rc = stream_attrs<6, 5>()) || (rc = stream_attrs<8, 3>()) || (rc = stream_attrs<12, 3>())) return rc;
     if ((rc = tb2_attrs<32, 8>()) || (rc = tb2_attrs<24, 8>()) || (rc = tb2_attrs<16, 8>()) || (rc = tb2_attrs<56, 8>())) return rc;
-    const int smem3 = k3NP * k3PlaneFloats * (int)sizeof(float);
+    const int smem3 = (k3NP * k3PlaneFloats + k3NO * 2 * k3OmFloats) * (int)sizeof(float);
     FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));

@@ -7,7 +7,8 @@
 //   * 8 consumer warps own two y rows each, a lane owns a float4 of x.  The nine z-neighbours of every output live
 //     in a register window that rotates as the march advances (one LDS.128 per new plane); the x and y neighbours
 //     come from the centre plane, which is still in the ring four planes behind the newest one;
-//   * u_{n-1} and m are read once per point from global, u_{n+1} overwrites u_{n-1} in place; snapshot write /
+//   * u_{n-1} and m ride a second, 4-deep TMA plane ring (128 x 16 x 1 boxes, issued three planes before use: plain
+//     per-warp global loads of these rows cost 40 % of the step); u_{n+1} overwrites u_{n-1} in place; snapshot write /
 //     snapshot read + imaging are fused exactly as in 2-D; the CTA applies its own source / receiver points at the end.
 // Algorithmic traffic: 16 B per point update (+ halo re-reads that hit L2).
 #pragma once
@@ -18,6 +19,8 @@ namespace fwi {
 constexpr int k3BX = 128, k3BY = 16, k3NP = 8, k3CW = 8;            // tile, ring depth, consumer warps
 constexpr int k3SX = k3BX + 2 * kHalo, k3SY = k3BY + 2 * kHalo;     // 136 x 24
 constexpr int k3PlaneFloats = k3SX * k3SY;                          // 3264 floats = 13056 B (102 * 128)
+constexpr int k3NO = 4, k3OmLead = 5;                               // u_{n-1}/m plane ring depth; issued 3 planes before use
+constexpr int k3OmFloats = k3BX * k3BY;                             // 2048 floats = 8 KB per array per plane
 
 struct Step3DArgs {
     float* oldnew;
@@ -35,9 +38,12 @@ struct Step3DArgs {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __grid_constant__ CUtensorMap tm_cur, Step3DArgs a) {
-    extern __shared__ __align__(128) float ring[];                   // [NP][SY][SX]
-    __shared__ __align__(8) uint64_t full_bar[k3NP], empty_bar[k3NP];
+__global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __grid_constant__ CUtensorMap tm_cur,
+                                                                       const __grid_constant__ CUtensorMap tm_old,
+                                                                       const __grid_constant__ CUtensorMap tm_m, Step3DArgs a) {
+    extern __shared__ __align__(128) float ring[];                   // [NP][SY][SX] u_n planes, then [NO][2][BY][BX] u_{n-1} / m planes
+    float* om_ring = ring + (size_t)k3NP * k3PlaneFloats;
+    __shared__ __align__(8) uint64_t full_bar[k3NP], empty_bar[k3NP], om_full[k3NO], om_empty[k3NO];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x0 = blockIdx.x * k3BX, y0 = blockIdx.y * k3BY;
@@ -48,6 +54,8 @@ __global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __g
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < k3NP; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], k3CW); }
+#pragma unroll
+        for (int i = 0; i < k3NO; ++i) { mbar_init(&om_full[i], 1); mbar_init(&om_empty[i], k3CW); }
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -56,11 +64,23 @@ __global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __g
     if (warp == k3CW) {
         // ---------------- producer warp: one lane feeds the plane ring
         if (lane == 0) {
-            for (int p = 0; p < nplanes; ++p) {
-                const int slot = p % k3NP;
-                if (p >= k3NP) mbar_wait(&empty_bar[slot], ((p / k3NP) - 1) & 1);
-                mbar_expect_tx(&full_bar[slot], k3PlaneFloats * (uint32_t)sizeof(float));
-                tma_load_3d(ring + (size_t)slot * k3PlaneFloats, &tm_cur, x0 - kHalo, y0 - kHalo, zc0 - kHalo + p, &full_bar[slot]);
+            // tick t: u_n plane t, then the u_{n-1} / m planes of output row t - k3OmLead (3 planes before they are used)
+            for (int t = 0; t < nplanes + k3OmLead; ++t) {
+                if (t < nplanes) {
+                    const int slot = t % k3NP;
+                    if (t >= k3NP) mbar_wait(&empty_bar[slot], ((t / k3NP) - 1) & 1);
+                    mbar_expect_tx(&full_bar[slot], k3PlaneFloats * (uint32_t)sizeof(float));
+                    tma_load_3d(ring + (size_t)slot * k3PlaneFloats, &tm_cur, x0 - kHalo, y0 - kHalo, zc0 - kHalo + t, &full_bar[slot]);
+                }
+                const int j = t - k3OmLead;
+                if (j >= 0 && j < nout) {
+                    const int slot = j % k3NO;
+                    if (j >= k3NO) mbar_wait(&om_empty[slot], ((j / k3NO) - 1) & 1);
+                    float* dst = om_ring + (size_t)slot * 2 * k3OmFloats;
+                    mbar_expect_tx(&om_full[slot], 2 * k3OmFloats * (uint32_t)sizeof(float));
+                    tma_load_3d(dst, &tm_old, x0, y0, zc0 + j, &om_full[slot]);
+                    tma_load_3d(dst + k3OmFloats, &tm_m, x0, y0, zc0 + j, &om_full[slot]);
+                }
             }
         }
     } else {
@@ -101,13 +121,17 @@ __global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __g
                 ok[r] = col_ok && y < a.ny;
                 off[r] = ((size_t)z * a.ny + y) * a.px + x;
                 if (ok[r]) {
-                    o4[r] = ld4(a.oldnew + off[r]);
-                    m4[r] = ld4(a.m + off[r]);
                     if (MODE == STEP_ADJ) { s4[r] = ld4_stream(a.snap + off[r]); c4[r] = ld4(a.acc + off[r]); }
                 }
             }
             const float gzv = __ldg(a.gz + z);
             mbar_wait(&full_bar[ptop % k3NP], (ptop / k3NP) & 1);
+            mbar_wait(&om_full[iz % k3NO], (iz / k3NO) & 1);
+            {
+                const float* om = om_ring + (size_t)(iz % k3NO) * 2 * k3OmFloats + (yl * k3BX) + 4 * lane;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) { o4[r] = ld4(om + r * k3BX); m4[r] = ld4(om + k3OmFloats + r * k3BX); }
+            }
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
 #pragma unroll
@@ -153,7 +177,10 @@ __global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __g
             }
             // the centre plane is dead now (later outputs see it only through the register windows)
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[pmid % k3NP])) : "memory");
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[pmid % k3NP])) : "memory");
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&om_empty[iz % k3NO])) : "memory");
+            }
         }
     }
 

@@ -3,7 +3,10 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from full_waveform_inversion_b200 import acoustic as ac
-for n, nt in ((128, 200), (256, 100), (384, 60), (512, 40)):
+sizes = ((128, 200), (256, 100), (384, 60), (512, 40))
+if len(sys.argv) > 1:
+    sizes = tuple((int(a), 30) for a in sys.argv[1:])
+for n, nt in sizes:
     prop = ac.Propagator((n, n, n), 10.0, 5e-4, nabs=20)
     prop.set_model(torch.full((n, n, n), 2500.0, device="cuda"))
     prop.set_geometry([(n // 2, n // 2, n // 2)], [(4, n // 2, x) for x in range(0, n, 4)])
