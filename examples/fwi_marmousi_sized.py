@@ -26,7 +26,7 @@ def models(nz, nx):
     for cz, cx, a in ((0.35, 0.3, 500.0), (0.55, 0.62, -400.0), (0.75, 0.45, 600.0)):
         v += a * np.exp(-(((z - cz) / 0.05) ** 2 + ((x - cx) / 0.08) ** 2))
     true = v.astype(np.float32)
-    k = 41
+    k = 121
     pad = np.pad(true, k // 2, mode="edge")
     cs = pad.cumsum(0).cumsum(1)
     cs = np.pad(cs, ((1, 0), (1, 0)))
@@ -69,7 +69,7 @@ def main():
             print("iter %2d  misfit %.6e  model rel. error %.4f  (%.1f s)" % (it, J, err, time.perf_counter() - t0), flush=True)
 
     v, hist = ac.fwi(v0, h, dt, shots, wav, [o if o is not None else torch.zeros(1) for o in observed], a.iters,
-                     1400.0, 5000.0, step_frac=0.01, nabs=40, callback=report)
+                     1400.0, 5000.0, step_frac=0.005, max_backtrack=6, nabs=40, callback=report)
     if rank == 0:
         print("misfit %.4e -> %.4e over %d iterations, %.1f s total" % (hist[0], hist[-1], a.iters, time.perf_counter() - t0))
     if world > 1:
