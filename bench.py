@@ -196,6 +196,19 @@ def track_a_numbers(device):
         torch.cuda.synchronize(device)
         dt = e0.elapsed_time(e1) / reps * 1e-3
         out["N=%d" % N] = {"samples_per_s": N / dt, "ms": dt * 1e3, "fp32_tflops_direct": N * flops / dt / 1e12}
+    # Gram-matrix mode: a different algorithm (2 K C^2 fp64 flop per sample, un-normalised metrics only) - own line
+    N = 4_000_000
+    prob.sample_eval_dev(6, 1, 0, N, amp, 0, 8, reduce=False)
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for r in range(5):
+        prob.sample_eval_dev(6, 1 + r, 0, N, amp, 0, 8, reduce=False)
+    e1.record()
+    torch.cuda.synchronize(device)
+    dt = e0.elapsed_time(e1) / 5 * 1e-3
+    out["gram_mode_N=%d" % N] = {"samples_per_s": N / dt, "ms": dt * 1e3, "fp64_gflops_gram": N * 2 * K * (C * (C + 1) // 2 + C) / dt / 1e9,
+                                 "note": "different algorithm (quadratic forms, no traces); not comparable to the direct flop count"}
     # host-buffer e2e of config 5: 10k caller-supplied source vectors, float64 in / float64 out
     Ms = np.random.default_rng(0).standard_normal((10_000, C)) * amp
     prob.similarity(Ms, "VR", False, False)

@@ -300,6 +300,76 @@ __global__ void __launch_bounds__(256, MC_MIN_BLOCKS) mc_eval_kernel(EvalParams 
     }
 }
 
+// --------------------------------------------------------------------------------------------- Gram-matrix mode
+// For the un-normalised metrics the misfit of a sample is a quadratic form in M (SURVEY 7 "algebraic shortcut"):
+//   sum_t s^2 = M^T A_k M,  sum_t d s = b_k^T M,  mean_t s = gbar_k^T M     with A_k = G_k G_k^T (C x C) per trace,
+// so a sample costs O(K C^2) instead of O(K C T) flops.  It is a DIFFERENT ALGORITHM from the reference's
+// (no synthetic trace is ever formed, so per-trace max-abs normalisation is impossible) and is reported as its
+// own mode.  float64 throughout: the forms cancel (SSE = dd - 2 b.M + M.A.M), and 2 K C^2 ~ 3.4 kflop per sample is
+// cheap even on the fp64 pipe.  Per trace: [A raw (C(C+1)/2), b raw (C), A centred, b centred, gbar (C)] doubles.
+template <int C>
+__global__ void __launch_bounds__(128) mc_gram_kernel(const double* __restrict__ gram, EvalParams p) {
+    constexpr int NS = C * (C + 1) / 2;
+    constexpr int PT = 2 * NS + 3 * C;
+    extern __shared__ double sg[];
+    for (int i = threadIdx.x; i < p.K * PT; i += blockDim.x) sg[i] = gram[i];
+    __syncthreads();
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= p.N) return;
+    double m[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) m[c] = (double)__ldg(p.M + (int64_t)c * p.ldm + n);
+    const bool simul = p.flags & FWI_FLAG_SIMULTANEOUS;
+    const bool pcc_like = !(p.metric == FWI_METRIC_VR || p.metric == FWI_METRIC_GAU);
+    const double Tn = (double)p.Tv;
+    double acc = 0.0, tot_sse = 0.0, tot_dd = 0.0, A1 = 0.0, A2 = 0.0, A3 = 0.0;
+    for (int k = 0; k < p.K; ++k) {
+        const double* g = sg + (size_t)k * PT + (pcc_like ? NS + C : 0);
+        double quad = 0.0, lin = 0.0;
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            double row = 0.5 * g[e++] * m[i];                    // diagonal once, off-diagonals twice
+#pragma unroll
+            for (int j = i + 1; j < C; ++j) row = fma(g[e++], m[j], row);
+            quad = fma(2.0 * m[i], row, quad);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) lin = fma(g[NS + c], m[c], lin);
+        const TraceConst tc = p.tc[k];
+        if (!pcc_like) {
+            const double sse = fmax(0.0, tc.sumd2 - 2.0 * lin + quad);
+            tot_sse += sse;
+            tot_dd += tc.sumd2;
+            if (p.metric == FWI_METRIC_VR) acc += fmax(0.0, 1.0 - sse / tc.sumd2);
+            else acc += exp(-sse / (2.0 * tc.sigma * tc.sigma));
+        } else {
+            double mu = 0.0;
+            const double* gb = sg + (size_t)k * PT + 2 * NS + 2 * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) mu = fma(gb[c], m[c], mu);
+            const double pcc = lin / sqrt(quad * tc.ssd);
+            acc += (pcc < 0.0) ? 0.0 : pcc;
+            A1 += Tn * mu;
+            A2 += quad + Tn * mu * mu;
+            A3 += lin + Tn * tc.mean_d * mu;
+        }
+    }
+    double result;
+    if (!pcc_like) {
+        if (simul) result = (p.metric == FWI_METRIC_VR) ? fmax(0.0, 1.0 - tot_sse / tot_dd) : exp(-tot_sse / (2.0 * p.fc.sigma[0] * p.fc.sigma[0]));
+        else { result = acc / p.K; if (p.metric == FWI_METRIC_GAU && (p.flags & FWI_FLAG_STRICT_REF)) result = 0.0; }
+    } else if (!simul) {
+        result = acc / p.K;
+    } else {
+        const double nn = p.fc.n, D1 = p.fc.D1[0], D2 = p.fc.D2[0];
+        const double pcc = (A3 - A1 * D1 / nn) / sqrt((A2 - A1 * A1 / nn) * (D2 - D1 * D1 / nn));
+        result = (pcc < 0.0) ? 0.0 : pcc;
+    }
+    p.sim[n] = (float)result;
+    if (p.like) p.like[n] = (float)exp(-(1.0 - result) * 0.5);
+}
+
 // --------------------------------------------------------------------------------------------- forward traces
 template <int C, int NM>
 __global__ void mc_forward_kernel(const float* __restrict__ rows, const int* __restrict__ phase,
@@ -714,6 +784,7 @@ struct RowSet {
     FlatConst fc{};
     int Tv = 0;
     bool built = false;
+    double* gram = nullptr;     // per-trace Gram blocks for the Gram mode (built with the row set, n_media == 1 only)
 };
 
 struct fwi_mc_ctx {
@@ -734,6 +805,7 @@ static void free_rowset(RowSet& r) {
     if (r.rows) cudaFree(r.rows);
     if (r.gbar) cudaFree(r.gbar);
     if (r.tc) cudaFree(r.tc);
+    if (r.gram) cudaFree(r.gram);
     r = RowSet{};
 }
 
@@ -797,6 +869,42 @@ static int build_rowset(fwi_mc_ctx* c, RowSet& rs, int variant) {
             rows[((size_t)k * Tv + tv) * RW + CC + 1] = (float)(dv[(size_t)k * Tv + tv] - q.mean_d);
         }
     }
+    // Gram blocks (float64, from the float64 Green's functions of this variant): A raw, b raw, A centred, b centred, gbar
+    std::vector<double> gram;
+    if (NM == 1) {
+        const int NS = C * (C + 1) / 2, PT = 2 * NS + 3 * C;
+        gram.assign((size_t)K * PT, 0.0);
+        std::vector<double> gv((size_t)C * Tv);
+        for (int k = 0; k < K; ++k) {
+            for (int comp = 0; comp < C; ++comp) {
+                auto gval = [&](int kk, int t) { return G_at(c, kk, comp, t, 0); };
+                for (int tv = 0; tv < Tv; ++tv) gv[(size_t)comp * Tv + tv] = interp(gval, k, tv);
+            }
+            double* g = gram.data() + (size_t)k * PT;
+            std::vector<double> gb(C, 0.0);
+            for (int comp = 0; comp < C; ++comp) { double s_ = 0.0; for (int tv = 0; tv < Tv; ++tv) s_ += gv[(size_t)comp * Tv + tv]; gb[comp] = s_ / Tv; }
+            int e = 0;
+            for (int i = 0; i < C; ++i)
+                for (int j = i; j < C; ++j) {
+                    double raw = 0.0, cen = 0.0;
+                    for (int tv = 0; tv < Tv; ++tv) {
+                        const double a_ = gv[(size_t)i * Tv + tv], b_ = gv[(size_t)j * Tv + tv];
+                        raw += a_ * b_;
+                        cen += (a_ - gb[i]) * (b_ - gb[j]);
+                    }
+                    g[e] = raw; g[NS + C + e] = cen; ++e;
+                }
+            for (int comp = 0; comp < C; ++comp) {
+                double raw = 0.0, cen = 0.0;
+                for (int tv = 0; tv < Tv; ++tv) {
+                    const double dd_ = dv[(size_t)k * Tv + tv], gg_ = gv[(size_t)comp * Tv + tv];
+                    raw += dd_ * gg_;
+                    cen += (dd_ - tc[k].mean_d) * (gg_ - gb[comp]);
+                }
+                g[NS + comp] = raw; g[2 * NS + C + comp] = cen; g[2 * NS + 2 * C + comp] = gb[comp];
+            }
+        }
+    }
     // flattened constants (raw and normalised)
     FlatConst fc{};
     fc.n = (double)K * Tv;
@@ -820,6 +928,10 @@ static int build_rowset(fwi_mc_ctx* c, RowSet& rs, int variant) {
     FWI_CUDA(cudaMemcpy(rs.rows, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice));
     FWI_CUDA(cudaMemcpy(rs.gbar, gbar.data(), gbar.size() * sizeof(float), cudaMemcpyHostToDevice));
     FWI_CUDA(cudaMemcpy(rs.tc, tc.data(), tc.size() * sizeof(TraceConst), cudaMemcpyHostToDevice));
+    if (!gram.empty()) {
+        FWI_CUDA(cudaMalloc(&rs.gram, gram.size() * sizeof(double)));
+        FWI_CUDA(cudaMemcpy(rs.gram, gram.data(), gram.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     rs.fc = fc; rs.Tv = Tv; rs.built = true;
     return FWI_OK;
 }
@@ -995,6 +1107,21 @@ int fwi_mc_eval(fwi_mc_ctx* c, const float* M, int64_t ldm, const float* frac, i
     p.phase = c->phase_dev; p.M = M; p.ldm = ldm; p.frac = frac; p.nfrac = nfrac; p.N = N; p.K = c->K; p.Tv = rs->Tv;
     p.metric = metric; p.flags = flags; p.boundary_fix = boundary_fix; p.sim = sim; p.like = like;
 
+    if (flags & FWI_FLAG_GRAM) {
+        FWI_REQUIRE(!norm, "fwi_mc_eval: the Gram mode cannot normalise traces (it never forms them); drop FWI_FLAG_GRAM or FWI_FLAG_NORMALISED");
+        FWI_REQUIRE(c->NM == 1 && rs->gram, "fwi_mc_eval: the Gram mode supports single-medium Green's functions only");
+        const int NS = c->C * (c->C + 1) / 2, PT = 2 * NS + 3 * c->C;
+        const size_t smem = (size_t)c->K * PT * sizeof(double);
+        FWI_REQUIRE(smem <= 200 * 1024, "fwi_mc_eval: K=%d traces exceed the shared-memory Gram buffer", c->K);
+        cudaStream_t gst = (cudaStream_t)stream;
+        const unsigned blocks = (unsigned)ceil_div(N, 128);
+#define GRAM(CV) do { if (smem > 48 * 1024) FWI_CUDA(cudaFuncSetAttribute(mc_gram_kernel<CV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                      mc_gram_kernel<CV><<<blocks, 128, smem, gst>>>(rs->gram, p); } while (0)
+        if (c->C == 3) GRAM(3); else if (c->C == 6) GRAM(6); else GRAM(9);
+#undef GRAM
+        FWI_CUDA(cudaGetLastError());
+        return FWI_OK;
+    }
     // samples per lane: 4 when there is enough work to fill the machine twice over, else fewer
     int S = 4;
     const int64_t full = (int64_t)c->sm_count * 2 * 128;

@@ -30,7 +30,7 @@ INVERSION_TYPES = ("full_mt", "DC", "single_force", "DC_single_force_couple", "D
 METRICS = ("VR", "CC", "PCC", "CC-shift", "gau")                                  # FWI:56
 _COMBINED = INVERSION_TYPES[3:]                                                   # FWI:797
 _PHASES = ("P", "S", "surface")                                                   # FWI:719-721
-FLAG_NORMALISED, FLAG_SIMULTANEOUS, FLAG_STRICT_REF = 1, 2, 4
+FLAG_NORMALISED, FLAG_SIMULTANEOUS, FLAG_STRICT_REF, FLAG_GRAM = 1, 2, 4, 8
 
 
 def _metric_id(comparison_metric):
@@ -47,8 +47,9 @@ def _type_id(inversion_type):
         raise ValueError("inversion_type must be one of %s, got %r" % (INVERSION_TYPES, inversion_type))
 
 
-def _flags(norm, simul, strict=False):
-    return (FLAG_NORMALISED if norm else 0) | (FLAG_SIMULTANEOUS if simul else 0) | (FLAG_STRICT_REF if strict else 0)
+def _flags(norm, simul, strict=False, gram=False):
+    return (FLAG_NORMALISED if norm else 0) | (FLAG_SIMULTANEOUS if simul else 0) | (FLAG_STRICT_REF if strict else 0) | \
+        (FLAG_GRAM if gram else 0)
 
 
 class SourceInversion:
@@ -130,7 +131,7 @@ class SourceInversion:
 
     # ---- host-array conveniences ----------------------------------------------------------------
     def similarity(self, M, comparison_metric, perform_normallised_waveform_inversion=True,
-                   compare_all_waveforms_simultaneously=True, media_frac=None, strict_reference=False):
+                   compare_all_waveforms_simultaneously=True, media_frac=None, strict_reference=False, gram=False):
         """Similarity of each source vector in M ((C,), (C,1) or (N,C)) -> float64 (N,).  Host in, host out
         through ``fwi_mc_eval_host`` (copies inside the call)."""
         M = np.asarray(M, dtype=np.float64)
@@ -147,7 +148,7 @@ class SourceInversion:
                                          None if fr is None else fr.ctypes.data_as(c_void_p), nf,
                                          _metric_id(comparison_metric),
                                          _flags(perform_normallised_waveform_inversion,
-                                                compare_all_waveforms_simultaneously, strict_reference),
+                                                compare_all_waveforms_simultaneously, strict_reference, gram),
                                          out.ctypes.data_as(c_void_p)))
         return out
 
@@ -241,7 +242,7 @@ def perform_monte_carlo_sampled_waveform_inversion(real_data_array, green_func_a
                                                    return_absolute_similarity_values_switch=False,
                                                    invert_for_ratio_of_multiple_media_greens_func_switch=False,
                                                    green_func_phase_labels=[], num_phase_types_for_media_ratios=0,
-                                                   seed=0, strict_reference=False, return_device_tensors=False):
+                                                   seed=0, strict_reference=False, return_device_tensors=False, use_gram=False):
     """Monte-Carlo sampling of the source -> (MTs, MTp, MTp_absolute)        (FWI:786-870)
 
     Row order of MTs as in the reference: C source rows, amp-frac row for combined types
@@ -251,7 +252,7 @@ def perform_monte_carlo_sampled_waveform_inversion(real_data_array, green_func_a
     """
     type_id = _type_id(inversion_type)
     metric = _metric_id(comparison_metric)
-    flags = _flags(perform_normallised_waveform_inversion, compare_all_waveforms_simultaneously, strict_reference)
+    flags = _flags(perform_normallised_waveform_inversion, compare_all_waveforms_simultaneously, strict_reference, use_gram)
     G = np.asarray(green_func_array, dtype=np.float64)
     media = bool(invert_for_ratio_of_multiple_media_greens_func_switch)
     if media and G.ndim != 4:

@@ -50,7 +50,9 @@ enum { FWI_METRIC_VR = 0, FWI_METRIC_CC = 1, FWI_METRIC_PCC = 2, FWI_METRIC_CC_S
 enum {
     FWI_FLAG_NORMALISED   = 1,  /* perform_normallised_waveform_inversion (FWI:53)      */
     FWI_FLAG_SIMULTANEOUS = 2,  /* compare_all_waveforms_simultaneously  (FWI:54)       */
-    FWI_FLAG_STRICT_REF   = 4   /* reproduce quirk q1: per-trace 'gau' returns 0 (FWI:659-661, 678-682) */
+    FWI_FLAG_STRICT_REF   = 4,  /* reproduce quirk q1: per-trace 'gau' returns 0 (FWI:659-661, 678-682) */
+    FWI_FLAG_GRAM         = 8   /* Gram-matrix mode (a different algorithm): un-normalised metrics only,
+                                   O(K C^2) per sample in float64, no synthetic traces formed; one medium only */
 };
 /* inversion_type (FWI:52), in the order of the reference's dispatch FWI:734-751 */
 enum {

@@ -203,3 +203,24 @@ def test_large_batch_size_independent_properties(fw):
     best = prob.similarity(lsq, "VR", False, True)[0]
     assert best >= vr.max()
     prob.close()
+
+
+@pytest.mark.parametrize("metric,simul", [("VR", False), ("VR", True), ("PCC", False), ("PCC", True), ("CC", True),
+                                          ("gau", False), ("gau", True), ("CC-shift", False), ("CC-shift", True)])
+@pytest.mark.parametrize("K,C,T", [(21, 9, 128), (5, 6, 90), (3, 3, 64)])
+def test_gram_mode_matches_oracle(fw, metric, simul, K, C, T):
+    """The Gram-matrix mode (a different algorithm: quadratic forms in float64, no traces formed) gives the same
+    un-normalised similarities as the reference's direct evaluation."""
+    d, G, m_true = orc.synthetic_inputs(K=K, C=C, T=T, seed=3 * K + T)
+    rng = np.random.default_rng(8)
+    Ms = rng.standard_normal((257, C))
+    Ms[:40] = m_true + 0.03 * rng.standard_normal((40, C))
+    prob = fw.SourceInversion(d, G)
+    got = prob.similarity(Ms, metric, False, simul, gram=True)
+    want = orc.similarity_batch(d, G, Ms, metric, False, simul)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
+    direct = prob.similarity(Ms, metric, False, simul)
+    np.testing.assert_allclose(got, direct, rtol=0, atol=2e-6)
+    with pytest.raises(ValueError):
+        prob.similarity(Ms, metric, True, simul, gram=True)           # normalisation needs the traces
+    prob.close()
