@@ -383,7 +383,8 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(obs_host.numel() * 4 + wav_host.numel() * 4), "d2h_bytes_per_step": 8,
                     "misfit_last_step": J_last},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": 12.2e6 if (nz, nx) == (1000, 3000) else None, "peak_source": peak_src,
+                         "traffic_note": "dram read+write per adjoint launch from ncu --set full --cache-control none (profiles/r1_fd2d_step_ncu_full_warm.txt): the snapshot stream; the 3 x 12 MB wavefields are served by L2",
                          "kernel": ("fd2d_stream_kernel" if stream else "fd2d_step_kernel") + " (forward-save and adjoint-image variants, averaged)",
                          "algorithmic_bytes_per_launch": 16 * nz * nx,
                          "avg_launch_us": avg_launch_s * 1e6,
