@@ -22,7 +22,7 @@
 
 namespace fwi {
 
-enum { STEP_FWD = 0, STEP_FWD_SAVE = 1, STEP_ADJ = 2 };
+enum { STEP_FWD = 0, STEP_FWD_SAVE = 1, STEP_ADJ = 2, STEP_ADJ2 = 3 };   // ADJ2: image this step AND the previous one (deferred)
 }  // namespace fwi
 #include "fd2d_stream.cuh"
 #include "fd3d.cuh"
@@ -35,6 +35,7 @@ struct Step2DArgs {
     const float* gx;
     const float* gz;
     float* snap;          // w_n: written (FWD_SAVE) or read (ADJ)
+    const float* snap_prev; // ADJ2: snapshot paired with the field of the previous adjoint step (= u_n of this launch)
     float* acc;           // imaging accumulator (ADJ)
     int nx, nz, px;
     PointListDev inj;     // sources (forward) / receivers (adjoint)
@@ -109,9 +110,16 @@ __global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constan
                 }
                 st4(a.oldnew + off, make_float4(nv[0], nv[1], nv[2], nv[3]));
                 if (MODE == STEP_FWD_SAVE) st4_stream(a.snap + off, make_float4(wv[0], wv[1], wv[2], wv[3]));
-                if (MODE == STEP_ADJ) {
+                if (MODE == STEP_ADJ || MODE == STEP_ADJ2) {
                     const float4 s4 = ld4_stream(a.snap + off);
                     float4 c4 = ld4(a.acc + off);
+                    if (MODE == STEP_ADJ2) {
+                        // deferred imaging of the previous adjoint step: its field is this launch's u_n (centre value C);
+                        // same fma order as two consecutive ADJ launches, so the accumulator is bit-identical
+                        const float4 sp = ld4_stream(a.snap_prev + off);
+                        c4.x = fmaf(C.x, sp.x, c4.x); c4.y = fmaf(C.y, sp.y, c4.y);
+                        c4.z = fmaf(C.z, sp.z, c4.z); c4.w = fmaf(C.w, sp.w, c4.w);
+                    }
                     c4.x = fmaf(nv[0], s4.x, c4.x); c4.y = fmaf(nv[1], s4.y, c4.y);
                     c4.z = fmaf(nv[2], s4.z, c4.z); c4.w = fmaf(nv[3], s4.w, c4.w);
                     st4(a.acc + off, c4);
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constan
             const float gm = a.gx[xx] * a.gz[z] * a.m[off];
             atomicAdd(a.oldnew + off, gm * val);                       // u_{n+1} += g m f
             if (MODE == STEP_FWD_SAVE) atomicAdd(a.snap + off, val);   // w_n includes f_n
-            if (MODE == STEP_ADJ) atomicAdd(a.acc + off, gm * val * a.snap[off]);
+            if (MODE == STEP_ADJ || MODE == STEP_ADJ2) atomicAdd(a.acc + off, gm * val * a.snap[off]);
         }
         if (r1 > r0) {
             __syncthreads();
@@ -296,6 +304,7 @@ struct fwi_fd2d {
     int fwd_c = 0, fwd_o = 1;         // fld[] indices of u_n and u_{n-1} after the last forward
     bool model_set = false;
     bool use_graphs = true;
+    bool defer_imaging = true;        // tile variant: image two adjoint steps per accumulator update
     int64_t launches = 0;
     cudaStream_t work = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -421,7 +430,10 @@ static int build_point_list(fwi_fd2d* p, PointList& pl, int n, const int* iz, co
     FWI_CUDA(cudaMemcpyAsync(pl.d_tile_ptr, tile_ptr.data(), (nbins + 1) * sizeof(int), cudaMemcpyHostToDevice, p->work));
     FWI_CUDA(cudaMemcpyAsync(pl.d_off, off.data(), std::max(n, 1) * sizeof(int), cudaMemcpyHostToDevice, p->work));
     FWI_CUDA(cudaMemcpyAsync(pl.d_id, id.data(), std::max(n, 1) * sizeof(int), cudaMemcpyHostToDevice, p->work));
-    FWI_CUDA(cudaStreamSynchronize(p->work));       // the host vectors go out of scope
+    // Pageable sources of <= 64 KB are staged by the driver before cudaMemcpyAsync returns, so the host vectors may go
+    // out of scope without waiting for the previous shot's graph (the CPU can then enqueue the next shot while the GPU
+    // still runs this one); larger lists must wait.
+    if ((size_t)std::max(nbins + 1, n) * sizeof(int) > 48 * 1024) FWI_CUDA(cudaStreamSynchronize(p->work));
     pl.n = n;
     return FWI_OK;
 }
@@ -456,16 +468,16 @@ static int build_point_list_tb2(fwi_fd2d* p, PointList& pl, int n, const int* iz
     FWI_CUDA(cudaMemcpyAsync(pl.d_tile_ptr, tile_ptr.data(), (nbins + 1) * sizeof(int), cudaMemcpyHostToDevice, p->work));
     FWI_CUDA(cudaMemcpyAsync(pl.d_off, off.data(), tot * sizeof(int), cudaMemcpyHostToDevice, p->work));
     FWI_CUDA(cudaMemcpyAsync(pl.d_id, id.data(), tot * sizeof(int), cudaMemcpyHostToDevice, p->work));
-    FWI_CUDA(cudaStreamSynchronize(p->work));
+    if ((size_t)std::max(nbins + 1, tot) * sizeof(int) > 48 * 1024) FWI_CUDA(cudaStreamSynchronize(p->work));
     pl.n = tile_ptr[nbins];
     return FWI_OK;
 }
 
 template <int BZ, int NW>
 static int launch_step_cfg(fwi_fd2d* p, int mode, int cur, float* oldnew, const PointList* inj, const float* inj_vals,
-                           const PointList* rec, float* rec_out, float* snap, cudaStream_t st) {
+                           const PointList* rec, float* rec_out, float* snap, cudaStream_t st, const float* snap_prev = nullptr) {
     Step2DArgs a{};
-    a.oldnew = oldnew; a.m = p->m; a.gx = p->gx; a.gz = p->gz; a.snap = snap; a.acc = p->acc;
+    a.oldnew = oldnew; a.m = p->m; a.gx = p->gx; a.gz = p->gz; a.snap = snap; a.acc = p->acc; a.snap_prev = snap_prev;
     a.nx = p->nx; a.nz = p->nz; a.px = p->px;
     a.inj = (inj && inj->n) ? inj->dev() : PointListDev{nullptr, nullptr, nullptr};
     a.inj_vals = inj_vals;
@@ -475,6 +487,7 @@ static int launch_step_cfg(fwi_fd2d* p, int mode, int cur, float* oldnew, const 
     const size_t smem = (size_t)(kBX + 2 * kHalo) * (BZ + 2 * kHalo) * sizeof(float);
     if (mode == STEP_FWD) fd2d_step_kernel<BZ, NW, STEP_FWD><<<grid, block, smem, st>>>(p->tmap[cur], a);
     else if (mode == STEP_FWD_SAVE) fd2d_step_kernel<BZ, NW, STEP_FWD_SAVE><<<grid, block, smem, st>>>(p->tmap[cur], a);
+    else if (mode == STEP_ADJ2) fd2d_step_kernel<BZ, NW, STEP_ADJ2><<<grid, block, smem, st>>>(p->tmap[cur], a);
     else fd2d_step_kernel<BZ, NW, STEP_ADJ><<<grid, block, smem, st>>>(p->tmap[cur], a);
     return FWI_OK;
 }
@@ -526,7 +539,7 @@ static int launch_step3(fwi_fd2d* p, int mode, int cur, float* oldnew, const Poi
 }
 
 static int launch_step(fwi_fd2d* p, int mode, int cur, float* oldnew, const PointList* inj, const float* inj_vals,
-                       const PointList* rec, float* rec_out, float* snap, cudaStream_t st) {
+                       const PointList* rec, float* rec_out, float* snap, cudaStream_t st, const float* snap_prev = nullptr) {
     p->launches++;
     if (p->ny > 1) return launch_step3(p, mode, cur, oldnew, inj, inj_vals, rec, rec_out, snap, st);
     if (p->variant == 1) {
@@ -540,7 +553,7 @@ static int launch_step(fwi_fd2d* p, int mode, int cur, float* oldnew, const Poin
         set_error("fd2d: unsupported streaming configuration nw=%d nc=%d", p->snw, p->snc);
         return FWI_EINVAL;
     }
-#define CFG(BZV, NWV) if (p->bz == BZV && p->nw == NWV) return launch_step_cfg<BZV, NWV>(p, mode, cur, oldnew, inj, inj_vals, rec, rec_out, snap, st)
+#define CFG(BZV, NWV) if (p->bz == BZV && p->nw == NWV) return launch_step_cfg<BZV, NWV>(p, mode, cur, oldnew, inj, inj_vals, rec, rec_out, snap, st, snap_prev)
     CFG(16, 2); CFG(32, 4); CFG(32, 8); CFG(16, 4); CFG(64, 8); CFG(64, 4);
 #undef CFG
     set_error("fd2d: unsupported tile configuration bz=%d nw=%d", p->bz, p->nw);
@@ -654,6 +667,19 @@ static int run_adjoint(fwi_fd2d* p, const float* resid, int n0, int n1, size_t s
                                 nullptr, nullptr, nullptr, p->snap + (size_t)(n - snap_base) * pl, p->snap + (size_t)(n - 1 - snap_base) * pl, st);
             if (rc) return rc;
             s = State{jc, jd};
+        }
+    }
+    if (p->variant == 0 && p->ny == 1 && p->defer_imaging) {
+        // deferred imaging: the first step of a pair only propagates (17 B/pt of traffic instead of 29), the second one
+        // images both fields, touching the accumulator once per two steps
+        for (; n - 1 >= n0; n -= 2) {
+            int rc = launch_step(p, STEP_FWD, s.c, p->fld[s.o], &p->rec, resid + (size_t)n * p->nrec, nullptr, nullptr, nullptr, st);
+            if (rc) return rc;
+            s = State{s.o, s.c};
+            rc = launch_step(p, STEP_ADJ2, s.c, p->fld[s.o], &p->rec, resid + (size_t)(n - 1) * p->nrec, nullptr, nullptr,
+                             p->snap + (size_t)(n - 1 - snap_base) * pl, st, p->snap + (size_t)(n - snap_base) * pl);
+            if (rc) return rc;
+            s = State{s.o, s.c};
         }
     }
     for (; n >= n0; --n) {

