@@ -520,9 +520,9 @@ static int launch_stream_cfg(fwi_fd2d* p, int mode, int cur, int oldidx, const P
 }
 
 static int launch_step3(fwi_fd2d* p, int mode, int cur, float* oldnew, const PointList* inj, const float* inj_vals,
-                        const PointList* rec, float* rec_out, float* snap, cudaStream_t st) {
+                        const PointList* rec, float* rec_out, float* snap, cudaStream_t st, const float* snap_prev) {
     Step3DArgs a{};
-    a.oldnew = oldnew; a.m = p->m; a.gx = p->gx; a.gy = p->gy; a.gz = p->gz; a.snap = snap; a.acc = p->acc;
+    a.oldnew = oldnew; a.m = p->m; a.gx = p->gx; a.gy = p->gy; a.gz = p->gz; a.snap = snap; a.acc = p->acc; a.snap_prev = snap_prev;
     a.nx = p->nx; a.ny = p->ny; a.nz = p->nz; a.px = p->px; a.zchunk = p->zchunk;
     a.inj = (inj && inj->n) ? inj->dev() : PointListDev{nullptr, nullptr, nullptr};
     a.inj_vals = inj_vals;
@@ -534,6 +534,7 @@ static int launch_step3(fwi_fd2d* p, int mode, int cur, float* oldnew, const Poi
     for (int i = 0; i < 8; ++i) if (p->fld[i] == oldnew) oi = i;
     if (mode == STEP_FWD) fd3d_step_kernel<STEP_FWD><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
     else if (mode == STEP_FWD_SAVE) fd3d_step_kernel<STEP_FWD_SAVE><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
+    else if (mode == STEP_ADJ2) fd3d_step_kernel<STEP_ADJ2><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
     else fd3d_step_kernel<STEP_ADJ><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
     return FWI_OK;
 }
@@ -541,7 +542,7 @@ static int launch_step3(fwi_fd2d* p, int mode, int cur, float* oldnew, const Poi
 static int launch_step(fwi_fd2d* p, int mode, int cur, float* oldnew, const PointList* inj, const float* inj_vals,
                        const PointList* rec, float* rec_out, float* snap, cudaStream_t st, const float* snap_prev = nullptr) {
     p->launches++;
-    if (p->ny > 1) return launch_step3(p, mode, cur, oldnew, inj, inj_vals, rec, rec_out, snap, st);
+    if (p->ny > 1) return launch_step3(p, mode, cur, oldnew, inj, inj_vals, rec, rec_out, snap, st, snap_prev);
     if (p->variant == 1) {
         int oldidx = -1;
         for (int i = 0; i < 8; ++i) if (p->fld[i] == oldnew) oldidx = i;
@@ -669,7 +670,7 @@ static int run_adjoint(fwi_fd2d* p, const float* resid, int n0, int n1, size_t s
             s = State{jc, jd};
         }
     }
-    if (p->variant == 0 && p->ny == 1 && p->defer_imaging) {
+    if ((p->ny > 1 || p->variant == 0) && p->defer_imaging) {
         // deferred imaging: the first step of a pair only propagates (17 B/pt of traffic instead of 29), the second one
         // images both fields, touching the accumulator once per two steps
         for (; n - 1 >= n0; n -= 2) {
@@ -874,6 +875,7 @@ static int create_plan(int device, int nz, int ny, int nx, float h, float dt, in
     FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_ADJ2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     *out = p;
     return FWI_OK;
 }

@@ -29,6 +29,7 @@ struct Step3DArgs {
     const float* gy;
     const float* gz;
     float* snap;
+    const float* snap_prev;   // ADJ2: snapshot paired with the previous adjoint step's field (= u_n of this launch)
     float* acc;
     int nx, ny, nz, px, zchunk;
     PointListDev inj;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __g
             const int z = zc0 + iz;
             const int ptop = iz + 2 * kHalo, pmid = iz + kHalo;
             // global operands first: their latency overlaps the barrier wait and the shared-memory reads
-            float4 o4[2], m4[2], s4[2], c4[2];
+            float4 o4[2], m4[2], s4[2], c4[2], sp4[2];
             size_t off[2];
             bool ok[2];
 #pragma unroll
@@ -121,7 +122,8 @@ __global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __g
                 ok[r] = col_ok && y < a.ny;
                 off[r] = ((size_t)z * a.ny + y) * a.px + x;
                 if (ok[r]) {
-                    if (MODE == STEP_ADJ) { s4[r] = ld4_stream(a.snap + off[r]); c4[r] = ld4(a.acc + off[r]); }
+                    if (MODE == STEP_ADJ || MODE == STEP_ADJ2) { s4[r] = ld4_stream(a.snap + off[r]); c4[r] = ld4(a.acc + off[r]); }
+                    if (MODE == STEP_ADJ2) sp4[r] = ld4_stream(a.snap_prev + off[r]);
                 }
             }
             const float gzv = __ldg(a.gz + z);
@@ -167,8 +169,12 @@ __global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __g
                 if (ok[r]) {
                     st4(a.oldnew + off[r], make_float4(nv[0], nv[1], nv[2], nv[3]));
                     if (MODE == STEP_FWD_SAVE) st4_stream(a.snap + off[r], make_float4(wv[0], wv[1], wv[2], wv[3]));
-                    if (MODE == STEP_ADJ) {
+                    if (MODE == STEP_ADJ || MODE == STEP_ADJ2) {
                         float4 c = c4[r];
+                        if (MODE == STEP_ADJ2) {      // deferred imaging of the previous adjoint step (its field is this launch's u_n)
+                            c.x = fmaf(C.x, sp4[r].x, c.x); c.y = fmaf(C.y, sp4[r].y, c.y);
+                            c.z = fmaf(C.z, sp4[r].z, c.z); c.w = fmaf(C.w, sp4[r].w, c.w);
+                        }
                         c.x = fmaf(nv[0], s4[r].x, c.x); c.y = fmaf(nv[1], s4[r].y, c.y);
                         c.z = fmaf(nv[2], s4[r].z, c.z); c.w = fmaf(nv[3], s4[r].w, c.w);
                         st4(a.acc + off[r], c);
@@ -198,7 +204,7 @@ __global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __g
             const float gm = a.gx[xx] * a.gy[y] * a.gz[z] * a.m[off];
             atomicAdd(a.oldnew + off, gm * val);
             if (MODE == STEP_FWD_SAVE) atomicAdd(a.snap + off, val);
-            if (MODE == STEP_ADJ) atomicAdd(a.acc + off, gm * val * a.snap[off]);
+            if (MODE == STEP_ADJ || MODE == STEP_ADJ2) atomicAdd(a.acc + off, gm * val * a.snap[off]);
         }
         if (r1 > r0) {
             __syncthreads();

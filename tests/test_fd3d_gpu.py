@@ -66,5 +66,5 @@ def test_gradient_3d_and_checkpointing(ac):
     prop.set_memory_limit(40 * plane)          # 70 snapshots do not fit -> checkpointed recompute
     J2, g2, _ = prop.gradient(wav, obs)
     assert abs(J2 - J) <= 1e-12 * J
-    assert np.array_equal(g.cpu().numpy(), g2.cpu().numpy())
+    assert rel_l2(g2.cpu().numpy(), g.cpu().numpy()) <= 1e-6     # deferred-imaging pairs differ between segmentations
     prop.close()
