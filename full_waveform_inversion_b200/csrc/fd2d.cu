@@ -793,6 +793,9 @@ static int leave(fwi_fd2d* p, cudaStream_t user) {       // ... and the caller's
 
 extern "C" {
 
+static int init_plan(fwi_fd2d* p, int device, int nz, int ny, int nx, float h, float dt, int nabs, float alpha);
+extern "C" int fwi_fd2d_destroy(fwi_fd2d* p);
+
 static int create_plan(int device, int nz, int ny, int nx, float h, float dt, int nabs, float alpha, fwi_fd2d** out) {
     FWI_REQUIRE(out != nullptr, "fwi_fd_create: out is NULL");
     FWI_REQUIRE(nz >= 1 && nx >= 1 && ny >= 1, "fwi_fd_create: grid must be at least 1 x 1 (got %d x %d x %d)", nz, ny, nx);
@@ -804,6 +807,13 @@ static int create_plan(int device, int nz, int ny, int nx, float h, float dt, in
     FWI_REQUIRE(device >= 0 && device < ndev, "fwi_fd2d_create: device %d out of range (%d visible)", device, ndev);
     DeviceGuard g(device);
     auto* p = new fwi_fd2d();
+    const int rc = init_plan(p, device, nz, ny, nx, h, dt, nabs, alpha);
+    if (rc) { fwi_fd2d_destroy(p); return rc; }          // nothing half-built leaks
+    *out = p;
+    return FWI_OK;
+}
+
+static int init_plan(fwi_fd2d* p, int device, int nz, int ny, int nx, float h, float dt, int nabs, float alpha) {
     p->device = device; p->nz = nz; p->ny = ny; p->nx = nx; p->h = h; p->dt = dt; p->nabs = nabs; p->alpha = alpha;
     p->px = (nx + 31) & ~31;
     p->tiles_x = (nx + kBX - 1) / kBX;
@@ -876,7 +886,6 @@ static int create_plan(int device, int nz, int ny, int nx, float h, float dt, in
     FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_ADJ2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-    *out = p;
     return FWI_OK;
 }
 

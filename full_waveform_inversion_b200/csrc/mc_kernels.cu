@@ -796,7 +796,6 @@ struct fwi_mc_ctx {
     // scratch
     float* stage_M = nullptr; float* stage_sim = nullptr; float* stage_frac = nullptr; int64_t stage_cap = 0;
     double* dstage = nullptr; int64_t dstage_bytes = 0;
-    double* red_sum = nullptr; float* red_max = nullptr; long long* red_arg = nullptr;
     int sm_count = 148;
     bool uploaded = false;
 };
@@ -996,9 +995,6 @@ int fwi_mc_create(int device, int K, int C, int T, int n_media, fwi_mc_ctx** out
     auto* c = new fwi_mc_ctx();
     c->device = device; c->K = K; c->C = C; c->T = T; c->NM = n_media; c->CC = C * n_media; c->RW = row_width(c->CC);
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-    FWI_CUDA(cudaMalloc(&c->red_sum, 1024 * sizeof(double)));
-    FWI_CUDA(cudaMalloc(&c->red_max, 1024 * sizeof(float)));
-    FWI_CUDA(cudaMalloc(&c->red_arg, 1024 * sizeof(long long)));
     *out = c;
     return FWI_OK;
 }
@@ -1012,7 +1008,6 @@ int fwi_mc_destroy(fwi_mc_ctx* c) {
     if (c->stage_sim) cudaFree(c->stage_sim);
     if (c->stage_frac) cudaFree(c->stage_frac);
     if (c->dstage) cudaFree(c->dstage);
-    cudaFree(c->red_sum); cudaFree(c->red_max); cudaFree(c->red_arg);
     delete c;
     return FWI_OK;
 }
