@@ -1050,6 +1050,7 @@ static int check_media(const fwi_mc_ctx* c, const float* frac, int nfrac, const 
 int fwi_mc_forward(fwi_mc_ctx* c, const float* M, int64_t ldm, int n_comp, const float* frac, int nfrac,
                    int64_t N, float* traces, void* stream) {
     FWI_REQUIRE(c && c->uploaded, "fwi_mc_forward: context has no data (call fwi_mc_upload)");
+    if (N == 0) return FWI_OK;                       // empty batch: nothing to do (pointers may be NULL)
     FWI_REQUIRE(M && traces && N >= 0 && ldm >= N, "fwi_mc_forward: bad M / traces / N / ldm");
     FWI_REQUIRE(n_comp >= 0 && n_comp <= c->C, "fwi_mc_forward: n_comp=%d exceeds C=%d", n_comp, c->C);
     int rc = check_media(c, frac, nfrac, "fwi_mc_forward");
@@ -1070,6 +1071,7 @@ int fwi_mc_forward(fwi_mc_ctx* c, const float* M, int64_t ldm, int n_comp, const
 int fwi_mc_eval(fwi_mc_ctx* c, const float* M, int64_t ldm, const float* frac, int nfrac, int64_t N, int metric,
                 int flags, float* sim, float* like, void* stream) {
     FWI_REQUIRE(c && c->uploaded, "fwi_mc_eval: context has no data (call fwi_mc_upload)");
+    if (N == 0) return FWI_OK;                       // empty batch: nothing to do (pointers may be NULL)
     FWI_REQUIRE(M && sim && N >= 0 && ldm >= N, "fwi_mc_eval: bad M / similarity / N / ldm");
     FWI_REQUIRE(metric >= 0 && metric <= 4, "fwi_mc_eval: unknown metric %d", metric);
     int rc = check_media(c, frac, nfrac, "fwi_mc_eval");
