@@ -225,8 +225,12 @@ int encode_tiled_f32(CUtensorMap* out, void* base, int rank, const uint64_t* dim
     cuuint64_t d[5]; cuuint64_t s[5]; cuuint32_t b[5]; cuuint32_t es[5];
     for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
     for (int i = 0; i < rank - 1; ++i) s[i] = strides_bytes[i];
+    static int promo = -1;
+    if (promo < 0) { const char* e = getenv("FWI_TMA_L2PROMO"); promo = e ? atoi(e) : 2; }      // 0 none, 1 64B, 2 128B, 3 256B
+    const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
+                                      (promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return FWI_ECUDA; }
     return FWI_OK;
 }
@@ -345,11 +349,22 @@ static int make_stream_partition(fwi_fd2d* p) {
 static int make_tmaps3(fwi_fd2d* p) {
     p->tiles_x = (p->nx + k3BX - 1) / k3BX;
     p->tiles_y = (p->ny + k3BY - 1) / k3BY;
-    const int target = 6 * p->sm_count;                         // ~3 waves of 2 resident CTAs per SM
-    int nzch = (target + p->tiles_x * p->tiles_y - 1) / (p->tiles_x * p->tiles_y);
-    nzch = std::max(1, std::min(nzch, std::max(1, p->nz / 16)));
-    p->zchunk = (p->nz + nzch - 1) / nzch;
-    p->nzch = (p->nz + p->zchunk - 1) / p->zchunk;
+    // z chunks: one CTA per SM is resident (170 KB of plane rings), every chunk re-reads 8 halo planes; pick the chunk
+    // count that minimises  waves x (planes per chunk + 8)
+    {
+        const int txy = p->tiles_x * p->tiles_y;
+        int best = 1;
+        double best_cost = 1e300;
+        for (int nzch = 1; nzch <= std::max(1, p->nz / 8); ++nzch) {
+            const int zc = (p->nz + nzch - 1) / nzch;
+            const int real = (p->nz + zc - 1) / zc;
+            const double waves = std::ceil((double)txy * real / p->sm_count);
+            const double cost = waves * (zc + 2 * kHalo);
+            if (cost < best_cost - 1e-9) { best_cost = cost; best = nzch; }
+        }
+        p->zchunk = (p->nz + best - 1) / best;
+        p->nzch = (p->nz + p->zchunk - 1) / p->zchunk;
+    }
     for (int i = 0; i < 8; ++i) {
         const uint64_t dims[3] = {(uint64_t)p->nx, (uint64_t)p->ny, (uint64_t)p->nz};
         const uint64_t strides[2] = {(uint64_t)p->px * sizeof(float), (uint64_t)p->px * p->ny * sizeof(float)};

@@ -16,7 +16,11 @@
 
 namespace fwi {
 
-constexpr int k3BX = 128, k3BY = 16, k3NP = 8, k3CW = 8;            // tile, ring depth, consumer warps
+#ifndef FD3_RPW
+#define FD3_RPW 2
+#endif
+constexpr int k3BX = 128, k3BY = 16, k3NP = 8;                       // tile, ring depth
+constexpr int k3RPW = FD3_RPW, k3CW = k3BY / k3RPW;                  // y rows per consumer warp, consumer warps
 constexpr int k3SX = k3BX + 2 * kHalo, k3SY = k3BY + 2 * kHalo;     // 136 x 24
 constexpr int k3PlaneFloats = k3SX * k3SY;                          // 3264 floats = 13056 B (102 * 128)
 constexpr int k3NO = 4, k3OmLead = 5;                               // u_{n-1}/m plane ring depth; issued 3 planes before use
@@ -87,23 +91,23 @@ __global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __g
     } else {
         // ---------------- consumer warps
         const int x = x0 + 4 * lane;
-        const int yl = 2 * warp;                       // first of this warp's two rows inside the tile
+        const int yl = k3RPW * warp;                   // first of this warp's rows inside the tile
         const bool col_ok = x < a.px;
         float4 gx4 = make_float4(1.f, 1.f, 1.f, 1.f);
         if (col_ok) gx4 = ld4(a.gx + x);
-        float gyv[2];
+        float gyv[k3RPW];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) gyv[r] = (y0 + yl + r < a.ny) ? __ldg(a.gy + y0 + yl + r) : 1.f;
+        for (int r = 0; r < k3RPW; ++r) gyv[r] = (y0 + yl + r < a.ny) ? __ldg(a.gy + y0 + yl + r) : 1.f;
 
-        float4 win[2][9];
+        float4 win[k3RPW][9];
         auto own = [&](int p, int r) {                 // this lane's element of row r in ring plane p
             return ld4(ring + (size_t)(p % k3NP) * k3PlaneFloats + (yl + r + kHalo) * k3SX + kHalo + 4 * lane);
         };
         // prime with planes 0..7 (z = zc0-4 .. zc0+3); planes 0..3 are never centre planes -> release them
         for (int p = 0; p < 2 * kHalo; ++p) {
             mbar_wait(&full_bar[p % k3NP], (p / k3NP) & 1);
-            win[0][p + 1] = own(p, 0);
-            win[1][p + 1] = own(p, 1);
+#pragma unroll
+            for (int r = 0; r < k3RPW; ++r) win[r][p + 1] = own(p, r);
             if (p < kHalo) {
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[p % k3NP])) : "memory");
@@ -113,11 +117,11 @@ __global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __g
             const int z = zc0 + iz;
             const int ptop = iz + 2 * kHalo, pmid = iz + kHalo;
             // global operands first: their latency overlaps the barrier wait and the shared-memory reads
-            float4 o4[2], m4[2], s4[2], c4[2], sp4[2];
-            size_t off[2];
-            bool ok[2];
+            float4 o4[k3RPW], m4[k3RPW], s4[k3RPW], c4[k3RPW], sp4[k3RPW];
+            size_t off[k3RPW];
+            bool ok[k3RPW];
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
+            for (int r = 0; r < k3RPW; ++r) {
                 const int y = y0 + yl + r;
                 ok[r] = col_ok && y < a.ny;
                 off[r] = ((size_t)z * a.ny + y) * a.px + x;
@@ -132,20 +136,20 @@ __global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __g
             {
                 const float* om = om_ring + (size_t)(iz % k3NO) * 2 * k3OmFloats + (yl * k3BX) + 4 * lane;
 #pragma unroll
-                for (int r = 0; r < 2; ++r) { o4[r] = ld4(om + r * k3BX); m4[r] = ld4(om + k3OmFloats + r * k3BX); }
+                for (int r = 0; r < k3RPW; ++r) { o4[r] = ld4(om + r * k3BX); m4[r] = ld4(om + k3OmFloats + r * k3BX); }
             }
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
+            for (int r = 0; r < k3RPW; ++r) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) win[r][k] = win[r][k + 1];
                 win[r][8] = own(ptop, r);
             }
             const float* mid = ring + (size_t)(pmid % k3NP) * k3PlaneFloats;
-            float4 yc[10];                               // rows yl-4 .. yl+5 of the centre plane, this lane's float4
+            float4 yc[8 + k3RPW];                        // rows yl-4 .. yl+3+RPW of the centre plane, this lane's float4
 #pragma unroll
-            for (int k = 0; k < 10; ++k) yc[k] = ld4(mid + (yl + k) * k3SX + kHalo + 4 * lane);
+            for (int k = 0; k < 8 + k3RPW; ++k) yc[k] = ld4(mid + (yl + k) * k3SX + kHalo + 4 * lane);
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
+            for (int r = 0; r < k3RPW; ++r) {
                 const float* row = mid + (yl + r + kHalo) * k3SX + 4 * lane;
                 const float4 L = ld4(row), R = ld4(row + 8);
                 const float4 C = yc[r + 4];
