@@ -570,7 +570,7 @@ static int launch_step(fwi_fd2d* p, int mode, int cur, float* oldnew, const Poin
         return FWI_EINVAL;
     }
 #define CFG(BZV, NWV) if (p->bz == BZV && p->nw == NWV) return launch_step_cfg<BZV, NWV>(p, mode, cur, oldnew, inj, inj_vals, rec, rec_out, snap, st, snap_prev)
-    CFG(16, 2); CFG(32, 4); CFG(32, 8); CFG(16, 4); CFG(64, 8); CFG(64, 4);
+    CFG(16, 2); CFG(32, 4); CFG(32, 8); CFG(16, 4); CFG(64, 8); CFG(64, 4); CFG(24, 4); CFG(24, 2); CFG(24, 3); CFG(40, 4); CFG(48, 4);
 #undef CFG
     set_error("fd2d: unsupported tile configuration bz=%d nw=%d", p->bz, p->nw);
     return FWI_EINVAL;
@@ -950,7 +950,8 @@ int fwi_fd2d_set_stream(fwi_fd2d* p, int nw, int nc) {
 
 int fwi_fd2d_set_tile(fwi_fd2d* p, int bz, int nw) {
     FWI_REQUIRE(p, "fwi_fd2d_set_tile: NULL plan");
-    const bool ok = (bz == 32 && (nw == 4 || nw == 8)) || (bz == 16 && (nw == 4 || nw == 2)) || (bz == 64 && (nw == 8 || nw == 4));
+    const bool ok = (bz == 32 && (nw == 4 || nw == 8)) || (bz == 16 && (nw == 4 || nw == 2)) || (bz == 64 && (nw == 8 || nw == 4)) ||
+                    (bz == 24 && (nw == 4 || nw == 2 || nw == 3)) || (bz == 40 && nw == 4) || (bz == 48 && nw == 4);
     FWI_REQUIRE(ok, "fwi_fd2d_set_tile: unsupported (bz=%d, nw=%d)", bz, nw);
     FWI_REQUIRE(p->ny == 1, "fwi_fd2d_set_tile: 2-D plans only");
     DeviceGuard g(p->device);
