@@ -46,6 +46,9 @@ _lib.register({
     "fwi_fd_reset": (c_int, [c_void_p, c_int, c_void_p]),
     "fwi_fd_step": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "fwi_fd_finalize_gradient": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "fwi_fd_slab_info": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "fwi_fd_slab_connect": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "fwi_fd_slab_error": (c_int, [c_void_p, POINTER(c_int)]),
     "fwi_fd_misfit": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_double), c_void_p]),
     "fwi_fd_model_update": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_void_p]),
     "fwi_fd_absmax": (c_int, [c_void_p, c_int64, POINTER(c_float), c_void_p]),
@@ -238,15 +241,17 @@ def sponge_profile(n, nabs, alpha):
 class SlabPropagator:
     """Large grids split into z slabs over the ranks of the default process group (BASELINE config 4).
 
-    Every rank owns a contiguous range of z planes plus a 4-plane ghost zone towards each neighbour and runs the
-    ordinary step kernel on its local grid; after every step the freshly computed boundary planes are exchanged
-    with the neighbours (NCCL send/recv on the compute stream - NVLink peer traffic, stream ordered, no host
-    barrier).  Values in the ghost planes are overwritten by the neighbour's, so the owned planes are bit-identical
-    to a single-GPU run.  The time loop is driven from Python, one `fwi_fd_step` per step."""
+    Every rank owns a contiguous range of z planes plus a 4-plane ghost zone towards each neighbour.
+    3-D (default, `p2p`): compute and halo exchange are ONE kernel - the neighbours' wavefield arenas are mapped with
+    CUDA IPC, the step kernel computes the owned planes, stores its 4 boundary planes straight into the neighbours'
+    ghost planes over NVLink and publishes a step id (system-scope release) that the neighbours' next launch
+    acquires; no collective call per step.  Fallback / 2-D (`p2p=False`): the ordinary step kernel runs on the local
+    grid and the boundary planes are exchanged with NCCL send/recv, the whole loop captured as a CUDA graph.
+    Either way the owned planes are bit-identical to a single-GPU run.  One `fwi_fd_step` per step."""
 
     HALO = 4
 
-    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=None, use_graphs=True):
+    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=None, use_graphs=True, p2p=None):
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("SlabPropagator needs an initialised torch.distributed process group")
@@ -271,6 +276,58 @@ class SlabPropagator:
         self.nsrc = self.nrec = 0
         self.use_graphs = use_graphs
         self._graphs = {}
+        # 3-D slabs default to the fused mode (boundary planes pushed over NVLink peer memory by the step kernel
+        # itself); p2p=False forces the NCCL send/recv exchange, which is also the fallback if IPC mapping fails.
+        self.p2p = (p2p is None or bool(p2p)) and len(self.shape) == 3 and self.world > 1
+        if self.p2p:
+            ok = torch.ones(1, device=self.prop.torch_device)
+            try:
+                self._connect_peers()
+            except Exception:
+                if p2p:
+                    raise
+                ok.zero_()
+            self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                raise RuntimeError("peer-memory slab mode could not be set up on every rank; pass p2p=False to use NCCL")
+
+    def _connect_peers(self):
+        """Fused mode: map the neighbours' wavefield arenas (CUDA IPC over NVLink) so that the step kernel itself stores
+        its boundary planes into their ghost planes; no collective call per step."""
+        lib = self.prop._lib
+        handle = (ctypes.c_ubyte * 64)()
+        offs = (ctypes.c_uint64 * 9)()
+        check(lib.fwi_fd_slab_info(self.prop._h, ctypes.cast(handle, c_void_p), ctypes.cast(offs, c_void_p)))
+        mine = (bytes(handle), list(offs), self.local_shape[0])
+        infos = [None] * self.world
+        self.dist.all_gather_object(infos, mine)
+
+        def pack(info):
+            if info is None:
+                return None, None
+            hb = (ctypes.c_ubyte * 64).from_buffer_copy(info[0])
+            ob = (ctypes.c_uint64 * 9)(*info[1])
+            return hb, ob
+        up = infos[self.rank - 1] if self.up else None
+        dn = infos[self.rank + 1] if self.down else None
+        uh, uo = pack(up)
+        dh, do = pack(dn)
+        self._peer_keepalive = (uh, uo, dh, do)
+        up_ghost_z = (up[2] - self.HALO) if up else 0
+        check(lib.fwi_fd_slab_connect(self.prop._h, self.up, self.up + self.n_own,
+                                      None if uh is None else ctypes.cast(uh, c_void_p), None if uo is None else ctypes.cast(uo, c_void_p),
+                                      up_ghost_z,
+                                      None if dh is None else ctypes.cast(dh, c_void_p), None if do is None else ctypes.cast(do, c_void_p)))
+        self.use_graphs = False          # step ids are kernel arguments: the loop is issued eagerly (no NCCL in it anyway)
+        self.dist.barrier()
+
+    def check_peers(self):
+        """Raise if a launch timed out waiting for a neighbour (fused mode)."""
+        if self.p2p:
+            e = c_int(0)
+            check(self.prop._lib.fwi_fd_slab_error(self.prop._h, ctypes.byref(e)))
+            if e.value:
+                raise RuntimeError("slab halo exchange: a step kernel timed out waiting for its neighbour")
 
     def close(self):
         # captured graphs hold NCCL work: drop them (and drain the device) BEFORE the process group goes away,
@@ -307,6 +364,8 @@ class SlabPropagator:
 
     def _exchange(self, idx):
         """Refresh the ghost planes of wavefield buffer idx from the neighbours' boundary planes."""
+        if self.p2p:
+            return                        # the step kernel already pushed them over NVLink
         f, H, ops = self.fields[idx], self.HALO, []
         n = f.shape[0]
         P2P = self.dist.P2POp
@@ -326,7 +385,16 @@ class SlabPropagator:
             torch.zeros((w.shape[0], 1), dtype=torch.float32, device=w.device)
 
     def _loop(self, nt, mode, pair, inj, out, snap_offset, reverse):
-        self.prop.reset(pair)
+        if self.p2p:
+            # neighbours write into this GPU's ghost planes: nobody may still be pushing the previous loop's data when
+            # the fields are zeroed, and nobody may push new data before they are
+            torch.cuda.synchronize()
+            self.dist.barrier()
+            self.prop.reset(pair)
+            torch.cuda.synchronize()
+            self.dist.barrier()
+        else:
+            self.prop.reset(pair)
         cur = 0
         for k in range(nt):
             n = nt - 1 - k if reverse else k

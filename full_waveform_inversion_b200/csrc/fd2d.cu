@@ -279,6 +279,15 @@ struct fwi_fd2d {
     int tiles_y = 1, zchunk = 0, nzch = 1;                      // 3-D tiling: 128 x 16 columns, z chunks
     float* gy = nullptr;
     CUtensorMap tm3[8], tm3_old[8], tm3_m;
+    // slab decomposition over peer memory (3-D only)
+    int z_own0 = 0, z_own1 = 0;                 // owned planes of the local grid; 0,0 = whole grid
+    void* peer_arena[2] = {nullptr, nullptr};   // IPC-opened arenas of the upper / lower neighbour
+    size_t peer_fld_off[2][8] = {};             // byte offsets of the neighbours' wavefield buffers in their arenas
+    size_t peer_flags_off[2] = {0, 0};
+    int peer_up_z = 0;
+    int* sync_area = nullptr;                   // [0..1] flags_local, [2] done counter, [3] error flag (inside the arena)
+    int step_base = 0;                          // monotonically increasing step ids across runs
+    int slab_wait = 0, slab_signal = 0;         // ids of the launch being issued
     int bz = 32, nw = 4;              // tiled variant: tile rows / warps per CTA (tunable)
     int tiles_x = 0, tiles_z = 0;
     int variant = 0;                  // 0 = one-tile-per-CTA kernel (default), 1 = persistent streaming kernel
@@ -355,15 +364,16 @@ static int make_tmaps3(fwi_fd2d* p) {
         const int txy = p->tiles_x * p->tiles_y;
         int best = 1;
         double best_cost = 1e300;
-        for (int nzch = 1; nzch <= std::max(1, p->nz / 8); ++nzch) {
-            const int zc = (p->nz + nzch - 1) / nzch;
-            const int real = (p->nz + zc - 1) / zc;
+        const int nzo = (p->z_own1 > 0 ? p->z_own1 : p->nz) - p->z_own0;
+        for (int nzch = 1; nzch <= std::max(1, nzo / 8); ++nzch) {
+            const int zc = (nzo + nzch - 1) / nzch;
+            const int real = (nzo + zc - 1) / zc;
             const double waves = std::ceil((double)txy * real / p->sm_count);
             const double cost = waves * (zc + 2 * kHalo);
             if (cost < best_cost - 1e-9) { best_cost = cost; best = nzch; }
         }
-        p->zchunk = (p->nz + best - 1) / best;
-        p->nzch = (p->nz + p->zchunk - 1) / p->zchunk;
+        p->zchunk = (nzo + best - 1) / best;
+        p->nzch = (nzo + p->zchunk - 1) / p->zchunk;
     }
     for (int i = 0; i < 8; ++i) {
         const uint64_t dims[3] = {(uint64_t)p->nx, (uint64_t)p->ny, (uint64_t)p->nz};
@@ -410,7 +420,7 @@ static int make_tmaps(fwi_fd2d* p) {
 
 // bin that owns grid point (z, x): the CTA tile (tiled variant) or the warp whose row-unit range holds it
 static int owner_bin(const fwi_fd2d* p, int z, int y, int x) {
-    if (p->ny > 1) return ((z / p->zchunk) * p->tiles_y + y / k3BY) * p->tiles_x + x / k3BX;
+    if (p->ny > 1) return ((std::max(0, z - p->z_own0) / p->zchunk) * p->tiles_y + y / k3BY) * p->tiles_x + x / k3BX;
     if (p->variant != 1) return (z / p->bz) * p->tiles_x + x / kBX;
     const int u = (x / 128) * p->nz + z;
     return (int)(std::upper_bound(p->h_u0.begin(), p->h_u0.end(), u) - p->h_u0.begin()) - 1;
@@ -543,6 +553,18 @@ static int launch_step3(fwi_fd2d* p, int mode, int cur, float* oldnew, const Poi
     a.inj_vals = inj_vals;
     a.rec = (rec && rec->n) ? rec->dev() : PointListDev{nullptr, nullptr, nullptr};
     a.rec_out = rec_out;
+    a.z_own0 = p->z_own0; a.z_own1 = p->z_own1 > 0 ? p->z_own1 : p->nz;
+    {
+        int oi_ = -1;
+        for (int i = 0; i < 8; ++i) if (p->fld[i] == oldnew) oi_ = i;
+        a.peer_up = p->peer_arena[0] ? (float*)((char*)p->peer_arena[0] + p->peer_fld_off[0][oi_]) : nullptr;
+        a.peer_dn = p->peer_arena[1] ? (float*)((char*)p->peer_arena[1] + p->peer_fld_off[1][oi_]) : nullptr;
+        a.peer_up_z = p->peer_up_z;
+        a.flags_local = p->sync_area; a.done_counter = (unsigned int*)(p->sync_area + 2); a.error_flag = p->sync_area + 3;
+        a.flag_peer_up = p->peer_arena[0] ? (int*)((char*)p->peer_arena[0] + p->peer_flags_off[0]) + 1 : nullptr;   // I am its lower neighbour
+        a.flag_peer_dn = p->peer_arena[1] ? (int*)((char*)p->peer_arena[1] + p->peer_flags_off[1]) + 0 : nullptr;   // I am its upper neighbour
+        a.wait_id = p->slab_wait; a.signal_id = p->slab_signal;
+    }
     const dim3 grid(p->tiles_x, p->tiles_y, p->nzch), block((k3CW + 1) * 32);
     const size_t smem = ((size_t)k3NP * k3PlaneFloats + (size_t)k3NO * 2 * k3OmFloats) * sizeof(float);
     int oi = -1;
@@ -841,8 +863,9 @@ static int init_plan(fwi_fd2d* p, int device, int nz, int ny, int nx, float h, f
     // access-policy window can keep it resident while the snapshots stream past:
     //   [m, acc, fld0, fld1, fld4, fld5 | fld2, fld3, fld6, fld7, vp]
     const size_t plb = (pl * sizeof(float) + 255) & ~(size_t)255;
-    FWI_CUDA(cudaMalloc(&p->arena, 11 * plb));
-    FWI_CUDA(cudaMemset(p->arena, 0, 11 * plb));
+    FWI_CUDA(cudaMalloc(&p->arena, 11 * plb + 256));
+    FWI_CUDA(cudaMemset(p->arena, 0, 11 * plb + 256));
+    p->sync_area = (int*)((char*)p->arena + 11 * plb);
     {
         char* a = (char*)p->arena;
         const int order[8] = {0, 1, 4, 5, 2, 3, 6, 7};
@@ -927,6 +950,7 @@ int fwi_fd2d_destroy(fwi_fd2d* p) {
     if (p->wav) cudaFree(p->wav);
     p->src.release(); p->rec.release();
     p->src_ext2.release(); p->src_own2.release(); p->rec_ext2.release(); p->rec_own2.release();
+    for (int s = 0; s < 2; ++s) if (p->peer_arena[s]) cudaIpcCloseMemHandle(p->peer_arena[s]);
     if (p->d_u0) cudaFree(p->d_u0);
     if (p->ev_in) cudaEventDestroy(p->ev_in);
     if (p->ev_out) cudaEventDestroy(p->ev_out);
@@ -1156,6 +1180,10 @@ int fwi_fd_reset(fwi_fd2d* p, int pair, void* stream) {
 // rec_out_dev: this step's trace row (modes 0/1, nullable).
 int fwi_fd_step(fwi_fd2d* p, int mode, int cur, const float* inj_vals_dev, float* rec_out_dev, int64_t snap_index, void* stream) {
     FWI_REQUIRE(p && p->model_set, "fwi_fd_step: set the model first");
+    if (p->peer_arena[0] || p->peer_arena[1]) {      // peer-memory slab mode: step ids order the launches across GPUs
+        p->slab_wait = p->step_base;
+        p->slab_signal = ++p->step_base;
+    }
     FWI_REQUIRE(mode >= 0 && mode <= 2 && (cur == 0 || cur == 1), "fwi_fd_step: bad mode / cur");
     FWI_REQUIRE(mode == 0 || (snap_index >= 0 && (size_t)(snap_index + 1) * p->plane() <= p->snap_steps), "fwi_fd_step: snapshot %lld not reserved", (long long)snap_index);
     DeviceGuard g(p->device);
@@ -1166,6 +1194,51 @@ int fwi_fd_step(fwi_fd2d* p, int mode, int cur, const float* inj_vals_dev, float
     if (rc) return rc;
     FWI_CUDA(cudaGetLastError());
     if (mode != STEP_ADJ) { p->fwd_c = cur ^ 1; p->fwd_o = cur; }
+    return FWI_OK;
+}
+
+// ---- slab decomposition over NVLink peer memory (3-D): the step kernel itself stores its boundary planes into the
+// neighbours' ghost planes and publishes a step id; the next launch of the neighbour waits for it. -------------------
+int fwi_fd_slab_info(fwi_fd2d* p, void* ipc_handle_out /*64 bytes*/, uint64_t* offsets_out /*9: 8 wavefield buffers + sync area*/) {
+    FWI_REQUIRE(p && ipc_handle_out && offsets_out, "fwi_fd_slab_info: bad arguments");
+    DeviceGuard g(p->device);
+    cudaIpcMemHandle_t h;
+    FWI_CUDA(cudaIpcGetMemHandle(&h, p->arena));
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    for (int i = 0; i < 8; ++i) offsets_out[i] = (uint64_t)((char*)p->fld[i] - (char*)p->arena);
+    offsets_out[8] = (uint64_t)((char*)p->sync_area - (char*)p->arena);
+    return FWI_OK;
+}
+
+// own planes [z_own0, z_own1) of the local grid; neighbour handles (null = no neighbour on that side); up_ghost_z = first
+// ghost plane index, in the upper neighbour's local grid, that receives this rank's first four owned planes.
+int fwi_fd_slab_connect(fwi_fd2d* p, int z_own0, int z_own1, const void* up_handle, const uint64_t* up_offsets, int up_ghost_z,
+                        const void* dn_handle, const uint64_t* dn_offsets) {
+    FWI_REQUIRE(p && p->ny > 1, "fwi_fd_slab_connect: needs a 3-D plan");
+    FWI_REQUIRE(z_own0 >= 0 && z_own1 <= p->nz && z_own1 - z_own0 >= 2 * kHalo, "fwi_fd_slab_connect: owned range [%d, %d) invalid for nz=%d", z_own0, z_own1, p->nz);
+    DeviceGuard g(p->device);
+    FWI_CUDA(cudaStreamSynchronize(p->work));
+    drop_graphs(p);
+    const void* hs[2] = {up_handle, dn_handle};
+    const uint64_t* offs[2] = {up_offsets, dn_offsets};
+    for (int s = 0; s < 2; ++s) {
+        if (!hs[s]) continue;
+        FWI_REQUIRE(offs[s], "fwi_fd_slab_connect: offsets missing");
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs[s], sizeof(h));
+        FWI_CUDA(cudaIpcOpenMemHandle(&p->peer_arena[s], h, cudaIpcMemLazyEnablePeerAccess));
+        for (int i = 0; i < 8; ++i) p->peer_fld_off[s][i] = (size_t)offs[s][i];
+        p->peer_flags_off[s] = (size_t)offs[s][8];
+    }
+    p->z_own0 = z_own0; p->z_own1 = z_own1; p->peer_up_z = up_ghost_z;
+    p->src.release(); p->rec.release(); p->nsrc = p->nrec = 0;         // z chunking (and so the point binning) changes
+    return make_tmaps(p);
+}
+
+int fwi_fd_slab_error(fwi_fd2d* p, int* error_out) {
+    FWI_REQUIRE(p && error_out, "fwi_fd_slab_error: bad arguments");
+    DeviceGuard g(p->device);
+    FWI_CUDA(cudaMemcpy(error_out, p->sync_area + 3, sizeof(int), cudaMemcpyDeviceToHost));
     return FWI_OK;
 }
 

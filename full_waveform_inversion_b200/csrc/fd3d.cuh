@@ -40,7 +40,27 @@ struct Step3DArgs {
     const float* inj_vals;
     PointListDev rec;
     float* rec_out;
+    // ---- slab decomposition over NVLink peer memory (all null / zero for a single-GPU plan) -----------------------
+    int z_own0, z_own1;        // owned plane range of the local grid (ghost planes lie outside and are never computed)
+    float* peer_up;            // the upper / lower neighbour's copy of `oldnew` (peer-mapped), or null
+    float* peer_dn;
+    int peer_up_z;             // first ghost plane (in the upper neighbour's local grid) that receives my first 4 owned planes
+    int* flags_local;          // [0] written by the upper neighbour, [1] by the lower one: "my step k is complete"
+    int* flag_peer_up;         // where I announce completion to the upper / lower neighbour (their flags_local slots)
+    int* flag_peer_dn;
+    int wait_id, signal_id;    // this launch needs neighbours' flags >= wait_id and publishes signal_id
+    unsigned int* done_counter;
+    int* error_flag;
 };
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 template <int MODE>
 __global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __grid_constant__ CUtensorMap tm_cur,
@@ -52,11 +72,25 @@ __global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __g
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x0 = blockIdx.x * k3BX, y0 = blockIdx.y * k3BY;
-    const int zc0 = blockIdx.z * a.zchunk, zc1 = min(a.nz, zc0 + a.zchunk);
+    const int zc0 = a.z_own0 + blockIdx.z * a.zchunk, zc1 = min(a.z_own1, zc0 + a.zchunk);
     const int nout = zc1 - zc0;                   // output planes of this CTA
     const int nplanes = nout + 2 * kHalo;         // planes zc0-4 .. zc1+3
 
     if (threadIdx.x == 0) {
+        // slab mode: the ghost planes of u_n are written by the neighbours' previous launch straight into this GPU's
+        // memory; wait until both have announced it (bounded spin: a dead neighbour raises error_flag instead of hanging)
+        // Only the first / last z chunk reads (and later pushes to) the upper / lower ghost planes, so only those CTAs wait.
+        if (a.wait_id > 0) {
+            for (int side = 0; side < 2; ++side) {
+                if ((side == 0 && !a.peer_up) || (side == 1 && !a.peer_dn)) continue;
+                if ((side == 0 && blockIdx.z != 0) || (side == 1 && blockIdx.z != gridDim.z - 1)) continue;
+                const long long t0 = clock64();
+                while (ld_acquire_sys(a.flags_local + side) < a.wait_id) {
+                    if (clock64() - t0 > 6000000000LL) { atomicExch(a.error_flag, 1); break; }      // ~3 s
+                    __nanosleep(200);
+                }
+            }
+        }
 #pragma unroll
         for (int i = 0; i < k3NP; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], k3CW); }
 #pragma unroll
@@ -213,6 +247,40 @@ __global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __g
         if (r1 > r0) {
             __syncthreads();
             for (int e = r0 + threadIdx.x; e < r1; e += blockDim.x) a.rec_out[a.rec.id[e]] = __ldcg(a.oldnew + a.rec.off[e]);
+        }
+    }
+
+    // ---- slab mode: push this CTA's share of the 4 boundary planes into the neighbours' ghost planes over NVLink
+    //      (plain stores to peer-mapped pointers), then the last CTA of the grid publishes the step id -------------
+    if (a.peer_up || a.peer_dn) {
+        __syncthreads();                                   // dense stores and fix-ups of this CTA are done
+        bool pushed = false;
+        for (int side = 0; side < 2; ++side) {
+            float* peer = side == 0 ? a.peer_up : a.peer_dn;
+            if (!peer) continue;
+            const int zb0 = side == 0 ? a.z_own0 : a.z_own1 - kHalo;            // my 4 boundary planes
+            const int zdst0 = side == 0 ? a.peer_up_z : 0;                      // where they land in the neighbour's grid
+            for (int z = max(zb0, zc0); z < min(zb0 + kHalo, zc1); ++z) {
+                pushed = true;
+                for (int i = threadIdx.x; i < k3BY * (k3BX / 4); i += blockDim.x) {
+                    const int yy = y0 + i / (k3BX / 4), xx = x0 + 4 * (i % (k3BX / 4));
+                    if (yy < a.ny && xx < a.px) {
+                        const float4 v = __ldcg(reinterpret_cast<const float4*>(a.oldnew + ((size_t)z * a.ny + yy) * a.px + xx));
+                        *reinterpret_cast<float4*>(peer + ((size_t)(zdst0 + z - zb0) * a.ny + yy) * a.px + xx) = v;
+                    }
+                }
+            }
+        }
+        if (pushed) __threadfence_system();                // block-uniform: make the peer stores visible before counting in
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+            if (atomicAdd(a.done_counter, 1u) == total - 1) {
+                *a.done_counter = 0;
+                __threadfence_system();
+                if (a.flag_peer_up) st_release_sys(a.flag_peer_up, a.signal_id);
+                if (a.flag_peer_dn) st_release_sys(a.flag_peer_dn, a.signal_id);
+            }
         }
     }
 }

@@ -208,6 +208,16 @@ int fwi_fd_reset(fwi_fd2d* plan, int pair, void* stream);   /* zero pair 0 (forw
 int fwi_fd_step(fwi_fd2d* plan, int mode, int cur, const float* inj_vals_dev, float* rec_out_dev, int64_t snap_index,
                 void* stream);
 int fwi_fd_finalize_gradient(fwi_fd2d* plan, float* grad_dev, void* stream);   /* grad += (2/v) I */
+/* Slab decomposition over NVLink peer memory (3-D plans, one process per GPU): every rank exports its arena
+ * (fwi_fd_slab_info: a cudaIpcMemHandle_t plus the byte offsets of the 8 wavefield buffers and of the sync area),
+ * the host layer swaps them between neighbours (torch.distributed), and fwi_fd_slab_connect maps the neighbours'
+ * memory.  From then on fwi_fd_step computes only the owned planes [z_own0, z_own1), stores its 4 boundary planes
+ * straight into the neighbours' ghost planes from inside the step kernel and publishes a step id that the
+ * neighbours' next launch waits for - compute and halo exchange are one kernel, no collective call per step. */
+int fwi_fd_slab_info(fwi_fd2d* plan, void* ipc_handle_out, uint64_t* offsets_out);
+int fwi_fd_slab_connect(fwi_fd2d* plan, int z_own0, int z_own1, const void* up_handle, const uint64_t* up_offsets, int up_ghost_z,
+                        const void* dn_handle, const uint64_t* dn_offsets);
+int fwi_fd_slab_error(fwi_fd2d* plan, int* error_out);       /* 1 if a launch timed out waiting for a neighbour */
 
 /* residual = syn - obs, J = 1/2 sum residual^2 (fd_oracle.misfit). Synchronises. */
 int fwi_fd_misfit(const float* syn_dev, const float* obs_dev, int64_t n, float* resid_dev, double* misfit_host,

@@ -12,6 +12,7 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 nt = int(sys.argv[2]) if len(sys.argv) > 2 else 120
+p2p = None if len(sys.argv) <= 3 else (sys.argv[3] == "p2p")
 shape = (n, n - 8, n + 32)
 v = (fo.layered_model(shape, 1700.0, 3000.0, 4) + 40.0 * np.random.default_rng(0).standard_normal(shape)).astype(np.float32)
 h = 10.0; dt = fo.stable_dt(float(v.max()), h, 3)
@@ -20,7 +21,7 @@ src = [(6, shape[1] // 2, shape[2] // 3), (n - 9, shape[1] // 3, shape[2] // 2)]
 rec = [(z, y, x) for z in (5, n // 2, n - 7) for y in range(3, shape[1] - 3, 9) for x in range(3, shape[2] - 3, 11)]
 vt = torch.from_numpy(v).cuda()
 
-slab = ac.SlabPropagator(shape, h, dt, nabs=10)
+slab = ac.SlabPropagator(shape, h, dt, nabs=10, p2p=p2p)
 slab.set_model(vt * 1.03)
 slab.set_geometry(src, rec)
 obs = slab.forward(wav)
@@ -29,6 +30,7 @@ J, g_own, tr = slab.gradient(wav, obs)           # first call captures the loops
 torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
 J, g_own, tr = slab.gradient(wav, obs)
 torch.cuda.synchronize(); t_slab = time.perf_counter() - t0
+slab.check_peers()
 
 single = ac.Propagator(shape, h, dt, nabs=10)
 single.set_model(vt * 1.03); single.set_geometry(src, rec)
@@ -41,8 +43,8 @@ g_ref = g1[slab.z0: slab.z0 + slab.n_own]
 e_g = float((g_own - g_ref).norm() / g1.norm())
 ok = torch.tensor([1.0 if (e_obs < 1e-6 and e_tr < 1e-6 and e_g < 1e-6 and abs(J - J1) < 1e-6 * J1) else 0.0], device="cuda")
 dist.all_reduce(ok)
-print("rank %d/%d graphs=%s slab z0=%d n_own=%d: obs diff %.2e traces diff %.2e grad diff %.2e J %.6e vs %.6e  (slab gradient %.2f s, %d steps)"
-      % (rank, world, slab.use_graphs, slab.z0, slab.n_own, e_obs, e_tr, e_g, J, J1, t_slab, 2 * nt), flush=True)
+print("rank %d/%d p2p=%s graphs=%s slab z0=%d n_own=%d: obs diff %.2e traces diff %.2e grad diff %.2e J %.6e vs %.6e  (slab gradient %.4f s, %d steps)"
+      % (rank, world, slab.p2p, slab.use_graphs, slab.z0, slab.n_own, e_obs, e_tr, e_g, J, J1, t_slab, 2 * nt), flush=True)
 dist.barrier()
 if rank == 0:
     print("SLAB_CHECK_OK" if ok.item() == world else "SLAB_CHECK_FAILED", flush=True)
