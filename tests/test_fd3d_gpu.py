@@ -68,3 +68,66 @@ def test_gradient_3d_and_checkpointing(ac):
     assert abs(J2 - J) <= 1e-12 * J
     assert rel_l2(g2.cpu().numpy(), g.cpu().numpy()) <= 1e-6     # deferred-imaging pairs differ between segmentations
     prop.close()
+
+
+def test_slab_owned_range_logic_on_one_gpu(ac):
+    """The slab decomposition's per-rank logic, emulated on ONE GPU: two plans own the upper / lower half of the grid
+    (4 ghost planes each), compute only their owned planes (`fwi_fd_slab_connect` without peers) and the ghost planes
+    are refreshed by device copies standing in for the NVLink push.  Owned planes must equal a single-grid run
+    bit for bit.  (The peer-memory push itself needs two GPUs: tools/slab_check.py.)"""
+    import ctypes
+    import torch
+    from full_waveform_inversion_b200 import _lib
+    shape, nt = (48, 20, 140), 50
+    v, h, dt, src, rec, wav = _case(shape, nt, seed=11)
+    src = [(6, 10, 40), (40, 8, 100)]
+    rec = [(5, y, x) for y in (3, 9, 15) for x in range(4, 136, 12)] + [(44, 10, 70)]
+    wav = wav[:, :2]
+    full = ac.Propagator(shape, h, dt, nabs=6)
+    full.set_model(v)
+    full.set_geometry(src, rec)
+    want = full.forward(wav).cpu().numpy()
+    want_field = full.wavefield(0).cpu().numpy()
+    full.close()
+
+    H, half = 4, shape[0] // 2
+    lib = _lib.load()
+    gz = ac.sponge_profile(shape[0], 6, 0.3)
+    plans, metas = [], []
+    for r in range(2):
+        z0, up, down = r * half, (H if r else 0), (0 if r else H)
+        lo, hi = z0 - up, z0 + half + down
+        p = ac.Propagator((hi - lo,) + shape[1:], h, dt, nabs=6, graphs=False)
+        p.set_profiles(gz=gz[lo:hi])
+        _lib.check(lib.fwi_fd_slab_connect(p._h, up, up + half, None, None, 0, None, None))
+        p.set_model(v[lo:hi])
+        s_loc = [(z - lo, y, x) for z, y, x in src if z0 <= z < z0 + half]
+        r_ids = [i for i, (z, y, x) in enumerate(rec) if z0 <= z < z0 + half]
+        r_loc = [(rec[i][0] - lo, rec[i][1], rec[i][2]) for i in r_ids]
+        s_ids = [i for i, (z, y, x) in enumerate(src) if z0 <= z < z0 + half]
+        p.set_geometry(s_loc if s_loc else np.zeros((0, 3), int), r_loc)
+        plans.append(p)
+        metas.append((lo, up, s_ids, r_ids))
+    got = np.zeros_like(want)
+    fields = [[p.field_view(i) for i in range(2)] for p in plans]
+    wav_d = [torch.tensor(np.ascontiguousarray(wav[:, m[2]]) if m[2] else np.zeros((nt, 1)), dtype=torch.float32, device="cuda") for m in metas]
+    out_d = [torch.zeros((nt, max(1, len(m[3]))), dtype=torch.float32, device="cuda") for m in metas]
+    for p in plans:
+        p.reset(0)
+    cur = 0
+    for n in range(nt):
+        for r, p in enumerate(plans):
+            p.step(0, cur, wav_d[r].data_ptr() + n * wav_d[r].shape[1] * 4, out_d[r].data_ptr() + n * out_d[r].shape[1] * 4)
+        cur ^= 1
+        a, b = fields[0][cur], fields[1][cur]              # upper slab: [own 24 | ghost 4]; lower slab: [ghost 4 | own 24]
+        a[half:half + H].copy_(b[H:2 * H])                 # lower slab's first owned planes -> upper slab's bottom ghost
+        b[0:H].copy_(a[half - H:half])                     # upper slab's last owned planes -> lower slab's top ghost
+    for r, m in enumerate(metas):
+        got[:, m[3]] = out_d[r][:, : len(m[3])].cpu().numpy()
+    assert np.array_equal(got, want)
+    px = fields[0][cur].shape[-1]
+    upper = fields[0][cur][:half, :, : shape[2]].cpu().numpy()
+    lower = fields[1][cur][H:, :, : shape[2]].cpu().numpy()
+    assert np.array_equal(np.concatenate([upper, lower]), want_field)
+    for p in plans:
+        p.close()
