@@ -457,9 +457,16 @@ class SlabPropagator:
         local = torch.zeros((nt, max(1, len(self.rec_ids))), dtype=torch.float32, device=dev)[:, : len(self.rec_ids)].contiguous()
         self._run(nt, 1, 0, w, local)
         obs = _dev_f32(observed, dev)
-        res = (local - obs[:, torch.as_tensor(self.rec_ids, device=dev)]).contiguous() if len(self.rec_ids) else \
-            torch.zeros((nt, 1), dtype=torch.float32, device=dev)
-        J = 0.5 * (res.double() ** 2).sum()
+        if len(self.rec_ids):
+            mine = obs[:, torch.as_tensor(self.rec_ids, device=dev)].contiguous()       # gather = data movement only
+            res = torch.empty_like(local)
+            Jl = c_double(0.0)
+            with torch.cuda.device(dev):
+                check(self.prop._lib.fwi_fd_misfit(ptr(local), ptr(mine), local.numel(), ptr(res), ctypes.byref(Jl), current_stream()))
+            J = torch.tensor([Jl.value], dtype=torch.float64, device=dev)
+        else:
+            res = torch.zeros((nt, 1), dtype=torch.float32, device=dev)
+            J = torch.zeros(1, dtype=torch.float64, device=dev)
         self.dist.all_reduce(J)
         self._run(nt, 2, 1, res, None, reverse=True)
         grad = torch.zeros(self.local_shape, dtype=torch.float32, device=dev)

@@ -772,6 +772,76 @@ __global__ void mc_hist_kernel(int mode, const float* __restrict__ MTs, int64_t 
     for (int i = threadIdx.x; i < nbins; i += blockDim.x) if (sh[i] != 0.0) atomicAdd(&hist[i], sh[i]);
 }
 
+
+// --------------------------------------------------------------------------------------------- least squares (a15)
+// perform_inversion (FWI:242-250): min || A m - d ||, A = stacked (K*T) x C Green's functions.  Normal equations in
+// float64: one pass accumulates A^T A (upper triangle) and A^T d, a single thread then solves the C x C system by
+// Cholesky.  C <= 9 and the Green's functions are far from rank deficient, so this agrees with LAPACK's gelsd to
+// ~1e-12; a non-positive pivot (rank-deficient input) is reported instead of returning garbage.
+template <int C>
+__global__ void mc_normal_eq_kernel(const double* __restrict__ G, const double* __restrict__ d, int K, int T, double* __restrict__ acc) {
+    constexpr int NS = C * (C + 1) / 2;
+    double a[NS + C];
+#pragma unroll
+    for (int i = 0; i < NS + C; ++i) a[i] = 0.0;
+    const int64_t rows = (int64_t)K * T;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(r / T), t = (int)(r % T);
+        double g[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) g[c] = G[((int64_t)k * C + c) * T + t];
+        const double dv = d[r];
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < C; ++i)
+#pragma unroll
+            for (int j = i; j < C; ++j) a[e++] += g[i] * g[j];
+#pragma unroll
+        for (int c = 0; c < C; ++c) a[NS + c] += g[c] * dv;
+    }
+#pragma unroll
+    for (int i = 0; i < NS + C; ++i) {
+        double v = a[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(acc + i, v);
+    }
+}
+
+template <int C>
+__global__ void mc_cholesky_kernel(const double* __restrict__ acc, double* __restrict__ m_out, int* __restrict__ status) {
+    constexpr int NS = C * (C + 1) / 2;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double A[C][C], b[C];
+    int e = 0;
+    for (int i = 0; i < C; ++i)
+        for (int j = i; j < C; ++j) { A[i][j] = acc[e]; A[j][i] = acc[e]; ++e; }
+    for (int c = 0; c < C; ++c) b[c] = acc[NS + c];
+    *status = 0;
+    for (int j = 0; j < C; ++j) {                       // A = L L^T, L stored in the lower triangle
+        double s = A[j][j];
+        for (int k = 0; k < j; ++k) s -= A[j][k] * A[j][k];
+        if (!(s > 0.0)) { *status = 1; return; }
+        const double l = sqrt(s);
+        A[j][j] = l;
+        for (int i = j + 1; i < C; ++i) {
+            double t = A[i][j];
+            for (int k = 0; k < j; ++k) t -= A[i][k] * A[j][k];
+            A[i][j] = t / l;
+        }
+    }
+    for (int i = 0; i < C; ++i) {                       // L y = b
+        double t = b[i];
+        for (int k = 0; k < i; ++k) t -= A[i][k] * b[k];
+        b[i] = t / A[i][i];
+    }
+    for (int i = C - 1; i >= 0; --i) {                  // L^T m = y
+        double t = b[i];
+        for (int k = i + 1; k < C; ++k) t -= A[k][i] * b[k];
+        b[i] = t / A[i][i];
+    }
+    for (int c = 0; c < C; ++c) m_out[c] = b[c];
+}
+
 }  // namespace fwi
 
 // =============================================================================================== host side
@@ -1290,6 +1360,39 @@ int fwi_mc_posterior_hist(int mode, const float* MTs_dev, int64_t ldn, const flo
     mc_hist_kernel<<<blocks, 256, nbins * sizeof(double), st>>>(mode, MTs_dev, ldn, MTp_dev, (const long long*)idx_dev, n, row0, hist_dev, nbins);
     FWI_CUDA(cudaGetLastError());
     return FWI_OK;
+}
+
+
+int fwi_mc_lstsq(int device, const double* G_host, const double* d_host, int K, int C, int T, double* M_host) {
+    FWI_REQUIRE(G_host && d_host && M_host && K >= 1 && T >= 1, "fwi_mc_lstsq: bad arguments");
+    FWI_REQUIRE(C == 3 || C == 6 || C == 9, "fwi_mc_lstsq: C must be 3, 6 or 9 (got %d)", C);
+    int ndev = 0;
+    FWI_CUDA(cudaGetDeviceCount(&ndev));
+    FWI_REQUIRE(device >= 0 && device < ndev, "fwi_mc_lstsq: device %d out of range (%d visible)", device, ndev);
+    DeviceGuard g(device);
+    const size_t nG = (size_t)K * C * T, nd = (size_t)K * T;
+    const int NS = C * (C + 1) / 2;
+    double* buf = nullptr;
+    FWI_CUDA(cudaMalloc(&buf, (nG + nd + NS + C + C + 1) * sizeof(double)));
+    double *dG = buf, *dd = buf + nG, *acc = dd + nd, *dm = acc + NS + C;
+    int* st = (int*)(dm + C);
+    int rc = FWI_OK;
+    do {
+        if (cudaMemcpy(dG, G_host, nG * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(dd, d_host, nd * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemset(acc, 0, (NS + C) * sizeof(double)) != cudaSuccess) { rc = FWI_ECUDA; break; }
+        const unsigned blocks = (unsigned)std::min<int64_t>(296, ceil_div((int64_t)nd, 128));
+        if (C == 3) { mc_normal_eq_kernel<3><<<blocks, 128>>>(dG, dd, K, T, acc); mc_cholesky_kernel<3><<<1, 32>>>(acc, dm, st); }
+        else if (C == 6) { mc_normal_eq_kernel<6><<<blocks, 128>>>(dG, dd, K, T, acc); mc_cholesky_kernel<6><<<1, 32>>>(acc, dm, st); }
+        else { mc_normal_eq_kernel<9><<<blocks, 128>>>(dG, dd, K, T, acc); mc_cholesky_kernel<9><<<1, 32>>>(acc, dm, st); }
+        int hst = 0;
+        if (cudaMemcpy(M_host, dm, C * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(&hst, st, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = FWI_ECUDA; break; }
+        if (hst) { set_error("fwi_mc_lstsq: the Green's functions are rank deficient (non-positive Cholesky pivot)"); rc = FWI_EINVAL; }
+    } while (0);
+    if (rc == FWI_ECUDA) set_error("fwi_mc_lstsq: CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(buf);
+    return rc;
 }
 
 }  // extern "C"

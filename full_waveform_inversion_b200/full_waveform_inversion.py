@@ -216,12 +216,17 @@ def get_unnormallised_prob_for_specific_soln(real_data_array, green_func_array, 
 def perform_inversion(real_data_array, green_func_array):
     """Stacked least squares for the amplitude scale -> (C,1)                 (FWI:242-250)
 
-    Runs once per inversion on a (K*T) x C system; stays on the host."""
-    d = np.asarray(real_data_array, dtype=np.float64)
-    G = np.asarray(green_func_array, dtype=np.float64)
-    A = G.transpose(0, 2, 1).reshape(-1, G.shape[1])
-    m, *_ = np.linalg.lstsq(A, d.reshape(-1, 1), rcond=None)
-    return m
+    Float64 normal equations + Cholesky on the device (`fwi_mc_lstsq`); agrees with the reference's
+    `np.linalg.lstsq` to ~1e-12 for the well-conditioned C <= 9 systems of this problem."""
+    lib = _lib.require_gpu()
+    d = np.ascontiguousarray(real_data_array, dtype=np.float64)
+    G = np.ascontiguousarray(green_func_array, dtype=np.float64)
+    if G.ndim != 3 or d.shape != (G.shape[0], G.shape[2]):
+        raise ValueError("real_data_array must be (K,T) and green_func_array (K,C,T)")
+    M = np.empty(G.shape[1], dtype=np.float64)
+    check(lib.fwi_mc_lstsq(torch.cuda.current_device(), G.ctypes.data_as(c_void_p), d.ctypes.data_as(c_void_p),
+                           G.shape[0], G.shape[1], G.shape[2], M.ctypes.data_as(c_void_p)))
+    return M.reshape(-1, 1)
 
 
 def _shard(num_samples, parts):
@@ -325,15 +330,13 @@ def perform_monte_carlo_sampled_waveform_inversion(real_data_array, green_func_a
 def _one_sample(type_id, seed):
     lib = _lib.require_gpu()
     rows = lib.fwi_mc_type_rows(type_id)
-    nd = lib.fwi_mc_type_draws(type_id)
-    g = torch.Generator(device="cpu")
+    g = torch.Generator(device="cuda")
     g.manual_seed(int(seed))
     pat = ("nnnnnn", "nnn", "nnn", "nnnr", "nnnnnnr", "urrrnnn", "nnnurrnnnr")[type_id]
-    draws = torch.empty((nd, 1), dtype=torch.float32)
-    for j, ch in enumerate(pat):
-        draws[j, 0] = torch.randn(1, generator=g).item() if ch == "n" else \
-            (torch.rand(1, generator=g).item() * 2 - 1 if ch == "u" else torch.rand(1, generator=g).item())
-    return transform_draws(INVERSION_TYPES[type_id], draws.numpy().T)[0], rows
+    nrm = torch.randn(len(pat), generator=g, device="cuda")
+    uni = torch.rand(len(pat), generator=g, device="cuda")
+    draws = torch.stack([nrm[j] if ch == "n" else (uni[j] * 2 - 1 if ch == "u" else uni[j]) for j, ch in enumerate(pat)])
+    return transform_draws(INVERSION_TYPES[type_id], draws.cpu().numpy()[None, :])[0], rows
 
 
 def transform_draws(inversion_type, draws, amplitude=1.0):
@@ -354,40 +357,44 @@ def transform_draws(inversion_type, draws, amplitude=1.0):
 _draw_counter = [0]
 
 
-def _gen(type_id):
-    _draw_counter[0] += 1
-    v, rows = _one_sample(type_id, 0x5EED0000 + _draw_counter[0])
+def _gen(type_id, seed=None):
+    """One sample; `seed=None` (the reference's signature) advances a process-wide counter, an explicit seed is
+    reproducible."""
+    if seed is None:
+        _draw_counter[0] += 1
+        seed = 0x5EED0000 + _draw_counter[0]
+    v, rows = _one_sample(type_id, seed)
     nc = _lib.load().fwi_mc_type_components(type_id)
     tensor = v[:nc].reshape(nc, 1)
     return (tensor, float(v[nc])) if rows > nc else tensor
 
 
-def generate_random_MT():                                   # FWI:282-293
-    return _gen(0)
+def generate_random_MT(seed=None):                                   # FWI:282-293
+    return _gen(0, seed)
 
 
-def generate_random_DC_MT():                                # FWI:295-317
-    return _gen(1)
+def generate_random_DC_MT(seed=None):                                # FWI:295-317
+    return _gen(1, seed)
 
 
-def generate_random_single_force_vector():                  # FWI:320-331
-    return _gen(2)
+def generate_random_single_force_vector(seed=None):                  # FWI:320-331
+    return _gen(2, seed)
 
 
-def generate_random_DC_single_force_coupled_tensor():       # FWI:333-367
-    return _gen(3)
+def generate_random_DC_single_force_coupled_tensor(seed=None):       # FWI:333-367
+    return _gen(3, seed)
 
 
-def generate_random_DC_single_force_uncoupled_tensor():     # FWI:369-382
-    return _gen(4)
+def generate_random_DC_single_force_uncoupled_tensor(seed=None):     # FWI:369-382
+    return _gen(4, seed)
 
 
-def generate_random_DC_crack_coupled_tensor():              # FWI:384-446
-    return _gen(5)
+def generate_random_DC_crack_coupled_tensor(seed=None):              # FWI:384-446
+    return _gen(5, seed)
 
 
-def generate_random_single_force_crack_uncoupled_tensor():  # FWI:448-510
-    return _gen(6)
+def generate_random_single_force_crack_uncoupled_tensor(seed=None):  # FWI:448-510
+    return _gen(6, seed)
 
 
 def get_synth_forward_model_most_likely_result(MTs, MTp, green_func_array, inversion_type,

@@ -224,3 +224,36 @@ def test_gram_mode_matches_oracle(fw, metric, simul, K, C, T):
     with pytest.raises(ValueError):
         prob.similarity(Ms, metric, True, simul, gram=True)           # normalisation needs the traces
     prob.close()
+
+
+@pytest.mark.parametrize("K,C,T", [(1, 6, 64), (5, 6, 203), (3, 3, 1001), (4, 9, 150)])
+def test_device_least_squares_vs_lapack(fw, K, C, T):
+    """perform_inversion (FWI:242-250) on the device: float64 normal equations vs the oracle's lstsq."""
+    rng = np.random.default_rng(K * 100 + C)
+    G = rng.standard_normal((K, C, T)) * 1e7
+    m = rng.standard_normal(C)
+    d = np.einsum("kct,c->kt", G, m) + 1e-3 * rng.standard_normal((K, T)) * 1e7
+    got = fw.perform_inversion(d, G)
+    want = orc.perform_inversion(d, G)
+    assert got.shape == (C, 1)
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12)
+
+
+def test_device_least_squares_rank_deficient(fw):
+    G = np.ones((2, 6, 50))
+    d = np.ones((2, 50))
+    with pytest.raises(Exception, match="rank deficient"):
+        fw.perform_inversion(d, G)
+    with pytest.raises(ValueError):
+        fw.perform_inversion(np.ones((2, 49)), G)
+
+
+def test_single_sample_generators(fw):
+    """generate_random_* (FWI:252-341): shapes, unit norm and determinism of the one-sample entry points."""
+    for name, rows in (("generate_random_MT", 6), ("generate_random_DC_MT", 6), ("generate_random_single_force_vector", 3)):
+        a = getattr(fw, name)(seed=5)
+        b = getattr(fw, name)(seed=5)
+        c = getattr(fw, name)(seed=6)
+        assert a.shape == (rows, 1)
+        assert abs(np.linalg.norm(a) - 1.0) < 1e-5
+        assert np.array_equal(a, b) and not np.array_equal(a, c)
