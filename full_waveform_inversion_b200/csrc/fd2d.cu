@@ -314,6 +314,7 @@ struct fwi_fd2d {
     PointList src_ext2, src_own2, rec_ext2, rec_own2;   // variant 2: binned by the 120 x cz core tiles (+-4 for *_ext2)
     int nsrc = 0, nrec = 0;
     size_t mem_limit = 0;             // 0 = automatic (fraction of free memory)
+    int split_nt = -1, split_seg = 0, split_nseg = 0; size_t split_limit = 0;   // cached storage decision of the last gradient
     int fwd_c = 0, fwd_o = 1;         // fld[] indices of u_n and u_{n-1} after the last forward
     bool model_set = false;
     bool use_graphs = true;
@@ -565,7 +566,7 @@ static int launch_step3(fwi_fd2d* p, int mode, int cur, float* oldnew, const Poi
         a.flag_peer_dn = p->peer_arena[1] ? (int*)((char*)p->peer_arena[1] + p->peer_flags_off[1]) + 0 : nullptr;   // I am its upper neighbour
         a.wait_id = p->slab_wait; a.signal_id = p->slab_signal;
     }
-    const dim3 grid(p->tiles_x, p->tiles_y, p->nzch), block((k3CW + 1) * 32);
+    const dim3 grid(p->tiles_x, p->tiles_y, p->nzch), block((k3CW + k3Prod) * 32);
     const size_t smem = ((size_t)k3NP * k3PlaneFloats + (size_t)k3NO * 2 * k3OmFloats) * sizeof(float);
     int oi = -1;
     for (int i = 0; i < 8; ++i) if (p->fld[i] == oldnew) oi = i;
@@ -1098,19 +1099,25 @@ int fwi_fd2d_gradient(fwi_fd2d* p, const float* wavelet_dev, const float* obs_de
     cudaStream_t user = (cudaStream_t)stream;
     const size_t pl = p->plane();
     // ---- choose between holding every w_n in HBM and two-level checkpointing --------------------------
-    size_t budget = p->mem_limit;
-    if (!budget) {
-        size_t fr = 0, tot = 0;
-        FWI_CUDA(cudaMemGetInfo(&fr, &tot));
-        budget = (size_t)((fr + (p->snap_steps + p->ckpt_slots) * sizeof(float)) * 0.85);   // both capacities are in floats
-    }
-    const size_t max_planes = budget / (pl * sizeof(float));
+    // The decision is cached per (nt, limit): cudaMemGetInfo takes a driver-wide lock and was measured stalling the
+    // host for 5 - 90 ms every few calls, which showed up as sporadic slow shots.
     int seg = nt, nseg = 1;
-    if ((size_t)nt > max_planes) {
-        // segment length S with S + 2*ceil(nt/S) planes minimal-ish: start from sqrt(2 nt)
-        seg = std::max(1, (int)std::ceil(std::sqrt(2.0 * nt)));
-        nseg = (nt + seg - 1) / seg;
-        FWI_REQUIRE((size_t)seg + 2 * (size_t)nseg <= max_planes, "fwi_fd2d_gradient: %zu bytes are not enough even with checkpointing (need %zu planes of %zu bytes)", budget, (size_t)seg + 2 * (size_t)nseg, pl * sizeof(float));
+    if (p->split_nt == nt && p->split_limit == p->mem_limit) {
+        seg = p->split_seg; nseg = p->split_nseg;
+    } else {
+        size_t budget = p->mem_limit;
+        if (!budget) {
+            size_t fr = 0, tot = 0;
+            FWI_CUDA(cudaMemGetInfo(&fr, &tot));
+            budget = (size_t)((fr + (p->snap_steps + p->ckpt_slots) * sizeof(float)) * 0.85);   // both capacities are in floats
+        }
+        const size_t max_planes = budget / (pl * sizeof(float));
+        if ((size_t)nt > max_planes) {
+            // segment length S with S + 2*ceil(nt/S) planes minimal-ish: start from sqrt(2 nt)
+            seg = std::max(1, (int)std::ceil(std::sqrt(2.0 * nt)));
+            nseg = (nt + seg - 1) / seg;
+            FWI_REQUIRE((size_t)seg + 2 * (size_t)nseg <= max_planes, "fwi_fd2d_gradient: %zu bytes are not enough even with checkpointing (need %zu planes of %zu bytes)", budget, (size_t)seg + 2 * (size_t)nseg, pl * sizeof(float));
+        }
     }
     int rc;
     if ((rc = ensure_floats(p, &p->snap, &p->snap_steps, (size_t)seg * pl))) return rc;     // snap_steps counts floats here
@@ -1120,6 +1127,7 @@ int fwi_fd2d_gradient(fwi_fd2d* p, const float* wavelet_dev, const float* obs_de
     if ((rc = ensure_floats(p, &p->syn, &p->syn_cap, ntr))) return rc;
     if ((rc = ensure_floats(p, &p->obs, &p->obs_cap, ntr))) return rc;
     if ((rc = ensure_floats(p, &p->wav, &p->wav_cap, (size_t)nt * p->nsrc))) return rc;
+    p->split_nt = nt; p->split_limit = p->mem_limit; p->split_seg = seg; p->split_nseg = nseg;      // buffers exist now
 
     if ((rc = enter(p, user))) return rc;
     FWI_CUDA(cudaMemcpyAsync(p->wav, wavelet_dev, (size_t)nt * p->nsrc * sizeof(float), cudaMemcpyDeviceToDevice, p->work));

@@ -2,14 +2,17 @@
 //
 // Layout [nz][ny][px] fp32, x contiguous.  A CTA owns a 128 (x) x 16 (y) column of the grid over a chunk of z and
 // marches through it plane by plane:
-//   * a dedicated producer warp keeps a ring of NP = 8 shared-memory planes filled: one 3-D TMA box
-//     (136 x 24 x 1, halo included, out-of-grid zero-filled = Dirichlet) per z plane, full/empty mbarrier pairs;
+//   * two dedicated producer warps (one elected lane each) feed shared memory by TMA with full/empty mbarrier pairs:
+//     the first keeps a ring of NP = 8 u_n planes filled (one 136 x 24 x 1 box per z plane, halo included,
+//     out-of-grid zero-filled = Dirichlet), the second a 4-deep ring of u_{n-1} / m planes (128 x 16 x 1 boxes).
+//     They are separate warps on purpose: a single producer that blocks on one ring's empty barrier also holds back
+//     the other ring's loads, which cost 25 % of the step (290 -> 390 Gpt/s at 512^3);
 //   * 8 consumer warps own two y rows each, a lane owns a float4 of x.  The nine z-neighbours of every output live
 //     in a register window that rotates as the march advances (one LDS.128 per new plane); the x and y neighbours
 //     come from the centre plane, which is still in the ring four planes behind the newest one;
-//   * u_{n-1} and m ride a second, 4-deep TMA plane ring (128 x 16 x 1 boxes, issued three planes before use: plain
-//     per-warp global loads of these rows cost 40 % of the step); u_{n+1} overwrites u_{n-1} in place; snapshot write /
-//     snapshot read + imaging are fused exactly as in 2-D; the CTA applies its own source / receiver points at the end.
+//   * u_{n+1} overwrites u_{n-1} in place (plain per-warp global loads of u_{n-1} / m instead of the second ring cost
+//     40 % of the step); snapshot write / snapshot read + imaging are fused exactly as in 2-D; the CTA applies its own
+//     source / receiver points at the end.
 // Algorithmic traffic: 16 B per point update (+ halo re-reads that hit L2).
 #pragma once
 #include "fd_common.cuh"
@@ -19,11 +22,23 @@ namespace fwi {
 #ifndef FD3_RPW
 #define FD3_RPW 2
 #endif
-constexpr int k3BX = 128, k3BY = 16, k3NP = 8;                       // tile, ring depth
+#ifndef FD3_NP
+#define FD3_NP 8
+#endif
+#ifndef FD3_NO
+#define FD3_NO 4
+#endif
+#ifndef FD3_OMLEAD
+#define FD3_OMLEAD 5
+#endif
+#ifndef FD3_SPLIT
+#define FD3_SPLIT 1
+#endif
+constexpr int k3BX = 128, k3BY = 16, k3NP = FD3_NP;                  // tile, ring depth
 constexpr int k3RPW = FD3_RPW, k3CW = k3BY / k3RPW;                  // y rows per consumer warp, consumer warps
 constexpr int k3SX = k3BX + 2 * kHalo, k3SY = k3BY + 2 * kHalo;     // 136 x 24
 constexpr int k3PlaneFloats = k3SX * k3SY;                          // 3264 floats = 13056 B (102 * 128)
-constexpr int k3NO = 4, k3OmLead = 5;                               // u_{n-1}/m plane ring depth; issued 3 planes before use
+constexpr int k3NO = FD3_NO, k3OmLead = FD3_OMLEAD, k3Prod = 1 + FD3_SPLIT;                               // u_{n-1}/m plane ring depth; issued 3 planes before use
 constexpr int k3OmFloats = k3BX * k3BY;                             // 2048 floats = 8 KB per array per plane
 
 struct Step3DArgs {
@@ -63,7 +78,7 @@ __device__ __forceinline__ void st_release_sys(int* p, int v) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __grid_constant__ CUtensorMap tm_cur,
+__global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(const __grid_constant__ CUtensorMap tm_cur,
                                                                        const __grid_constant__ CUtensorMap tm_old,
                                                                        const __grid_constant__ CUtensorMap tm_m, Step3DArgs a) {
     extern __shared__ __align__(128) float ring[];                   // [NP][SY][SX] u_n planes, then [NO][2][BY][BX] u_{n-1} / m planes
@@ -100,19 +115,20 @@ __global__ void __launch_bounds__((k3CW + 1) * 32, 1) fd3d_step_kernel(const __g
     }
     __syncthreads();
 
-    if (warp == k3CW) {
-        // ---------------- producer warp: one lane feeds the plane ring
+    if (warp >= k3CW) {
+        // ---------------- producer warp(s): one lane feeds the u_n plane ring, one the u_{n-1} / m ring
+        const bool do_u = warp == k3CW, do_om = warp == k3CW + k3Prod - 1;
         if (lane == 0) {
             // tick t: u_n plane t, then the u_{n-1} / m planes of output row t - k3OmLead (3 planes before they are used)
             for (int t = 0; t < nplanes + k3OmLead; ++t) {
-                if (t < nplanes) {
+                if (do_u && t < nplanes) {
                     const int slot = t % k3NP;
                     if (t >= k3NP) mbar_wait(&empty_bar[slot], ((t / k3NP) - 1) & 1);
                     mbar_expect_tx(&full_bar[slot], k3PlaneFloats * (uint32_t)sizeof(float));
                     tma_load_3d(ring + (size_t)slot * k3PlaneFloats, &tm_cur, x0 - kHalo, y0 - kHalo, zc0 - kHalo + t, &full_bar[slot]);
                 }
                 const int j = t - k3OmLead;
-                if (j >= 0 && j < nout) {
+                if (do_om && j >= 0 && j < nout) {
                     const int slot = j % k3NO;
                     if (j >= k3NO) mbar_wait(&om_empty[slot], ((j / k3NO) - 1) & 1);
                     float* dst = om_ring + (size_t)slot * 2 * k3OmFloats;
