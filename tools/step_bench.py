@@ -3,6 +3,9 @@ variants: fits t = a + b * points to separate the fixed per-launch cost from the
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
+from full_waveform_inversion_b200 import _lib
+if os.environ.get("FWI_VARIANT_LIB"):
+    _lib.LIB_PATH = os.environ["FWI_VARIANT_LIB"]          # tuning builds from tools/build_variant.sh
 from full_waveform_inversion_b200 import acoustic as ac
 
 def time_forward(nz, nx, nt, **kw):
