@@ -45,7 +45,12 @@ struct Step2DArgs {
 };
 
 #ifndef FWI_PDL_TRIGGER
-#define FWI_PDL_TRIGGER 2      // 0 implicit at exit, 1 top, 2 after the dense part (measured best), 3 after the TMA wait
+// Where a step lets its successor's CTAs become resident: 0 = implicit, when its own CTAs exit (default), 1 = top,
+// 2 = after the dense part, 3 = after the TMA wait.  Measured on the bench workload (ms per 5000-step gradient):
+// no PDL 85.5, 0: 84.5, 2: 88.6, 1: 101 - an early trigger parks the whole next grid at its dependency wait and releases
+// all CTAs in the same instant, which lines up their load / compute / store phases and costs L2 bandwidth; with the
+// implicit trigger only the launch latency and the prologue overlap and the CTAs stay staggered.
+#define FWI_PDL_TRIGGER 0
 #endif
 template <int BZ, int NW, int MODE>
 __global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constant__ CUtensorMap tm_cur, Step2DArgs a) {
