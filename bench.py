@@ -248,9 +248,11 @@ def track_b_extras(device):
         return float(np.prod(shape)) * nt / (e0.elapsed_time(e1) * 1e-3) / 1e9
 
     out["forward_2d_1000x3000_gpt_s"] = rate((1000, 3000), 2000)
-    out["forward_2d_4000x3000_gpt_s"] = rate((4000, 3000), 600)
-    out["forward_2d_4000x3000_tb2_gpt_s"] = rate((4000, 3000), 600, tb2=32)
+    out["forward_2d_4000x3000_tile_gpt_s"] = rate((4000, 3000), 600, tile=(32, 4))
+    out["forward_2d_4000x3000_gpt_s"] = rate((4000, 3000), 600)          # default for this size: two steps per pass
+    out["forward_2d_500x3000_gpt_s"] = rate((500, 3000), 2000)
     out["forward_3d_384_gpt_s"] = rate((384, 384, 384), 40)
+    out["forward_3d_512_gpt_s"] = rate((512, 512, 512), 30)
     out["note"] = "forward stepping only (fused injection/sampling, no snapshots); 16 B/pt roofline at the measured HBM peak = 404 Gpt/s"
     return out
 

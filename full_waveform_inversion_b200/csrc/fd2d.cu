@@ -961,7 +961,22 @@ static int init_plan(fwi_fd2d* p, int device, int nz, int ny, int nx, float h, f
 }
 
 int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, float alpha, fwi_fd2d** out) {
-    return create_plan(device, nz, 1, nx, h, dt, nabs, alpha, out);
+    int rc = create_plan(device, nz, 1, nx, h, dt, nabs, alpha, out);
+    if (rc) return rc;
+    // Default step kernel by grid size (tools/variant_bench.py, us per forward+adjoint step pair, tile vs two-steps-per-pass):
+    //   250x3000 12.8 vs 7.8 | 500x3000 14.6 vs 11.5 | 1000x3000 18.0 vs 19.6 | 2000x3000 41.9 vs 42.7 | 3000x3000 79.7 vs 60.4
+    // Small grids are launch-bound (half the launches wins), grids whose fields leave the L2 are HBM-bound (12.7 instead
+    // of 17 B per step wins); in between the one-step tile kernel streams from L2 faster than tb2 can compute.
+    // fwi_fd2d_set_tile / set_stream / set_tb2 override this.
+    const char* e = getenv("FWI_FD2D_VARIANT");
+    const bool force_tile = e && !strcmp(e, "tile");
+    const double pts = (double)nz * nx;
+    if (!force_tile && nz >= 32 && nx >= 128) {
+        if (pts <= 2.0e6) rc = fwi_fd2d_set_tb2(*out, 24);
+        else if (pts > 7.5e6) rc = fwi_fd2d_set_tb2(*out, 32);
+        if (rc) { fwi_fd2d_destroy(*out); *out = nullptr; }
+    }
+    return rc;
 }
 
 int fwi_fd3d_create(int device, int nz, int ny, int nx, float h, float dt, int nabs, float alpha, fwi_fd2d** out) {

@@ -37,12 +37,18 @@ def _case(nz, nx, nt, seed=0, nsrc=1, f0=18.0):
     return v.astype(np.float32).astype(np.float64), h, dt, src, rec, wav.astype(np.float32).astype(np.float64)
 
 
+# the default kernel depends on the grid size (two-steps-per-pass for small and for larger-than-L2 grids, the one-step tile
+# kernel in between, which is what the bench workload runs): the parity tests pin both
+KERNELS = [dict(), dict(tile=(32, 4))]
+
+
+@pytest.mark.parametrize("kw", KERNELS)
 @pytest.mark.parametrize("nz,nx,nt,nsrc", [(70, 150, 260, 1), (33, 129, 150, 2), (130, 64, 200, 1), (40, 300, 120, 3)])
-def test_forward_traces_and_wavefield(ac, nz, nx, nt, nsrc):
+def test_forward_traces_and_wavefield(ac, nz, nx, nt, nsrc, kw):
     v, h, dt, src, rec, wav = _case(nz, nx, nt, seed=nz, nsrc=nsrc)
     p = fo.Problem(v, h, dt, src, rec, nabs=12, alpha=0.3)
     want, _, (cur, old) = p.forward(wav, return_state=True)
-    prop = ac.Propagator2D((nz, nx), h, dt, nabs=12, alpha=0.3)
+    prop = ac.Propagator2D((nz, nx), h, dt, nabs=12, alpha=0.3, **kw)
     prop.set_model(v)
     prop.set_geometry(src, rec)
     got = prop.forward(wav).cpu().numpy()
@@ -76,12 +82,13 @@ def test_kernel_variants_agree(ac, kind, cfg):
     prop.close()
 
 
+@pytest.mark.parametrize("kw", KERNELS)
 @pytest.mark.parametrize("nz,nx,nt", [(60, 140, 220), (45, 131, 160)])
-def test_gradient_vs_self_oracle(ac, nz, nx, nt):
+def test_gradient_vs_self_oracle(ac, nz, nx, nt, kw):
     v, h, dt, src, rec, wav = _case(nz, nx, nt, seed=7)
     obs = fo.Problem(v * 1.04, h, dt, src, rec, nabs=10).forward(wav).astype(np.float32).astype(np.float64)
     J_want, g_want, tr_want = fo.Problem(v, h, dt, src, rec, nabs=10).misfit_and_gradient(wav, obs)
-    prop = ac.Propagator2D((nz, nx), h, dt, nabs=10)
+    prop = ac.Propagator2D((nz, nx), h, dt, nabs=10, **kw)
     prop.set_model(v)
     prop.set_geometry(src, rec)
     J, g, tr = prop.gradient(wav, obs, want_traces=True)
@@ -94,12 +101,13 @@ def test_gradient_vs_self_oracle(ac, nz, nx, nt):
     prop.close()
 
 
-def test_checkpointed_gradient_matches_stored(ac):
+@pytest.mark.parametrize("kw", KERNELS)
+def test_checkpointed_gradient_matches_stored(ac, kw):
     """Two-level checkpointing recomputes w_n exactly: same gradient as holding every snapshot in HBM."""
     nz, nx, nt = 50, 160, 210
     v, h, dt, src, rec, wav = _case(nz, nx, nt, seed=9)
     obs = fo.Problem(v * 0.96, h, dt, src, rec, nabs=10).forward(wav)
-    prop = ac.Propagator2D((nz, nx), h, dt, nabs=10)
+    prop = ac.Propagator2D((nz, nx), h, dt, nabs=10, **kw)
     prop.set_model(v)
     prop.set_geometry(src, rec)
     J0, g0, _ = prop.gradient(wav, obs)
@@ -174,6 +182,34 @@ def test_size_independent_properties_at_scale(ac):
     # reciprocity holds for u/m (the injection is scaled by m at the source): both points sit in the same layer
     assert rel_l2(t3[:, 0], t1[:, 0]) <= 1e-4
     prop.close()
+
+
+@pytest.mark.parametrize("shape", [(100, 300), (1000, 3000), (2600, 3000)])
+def test_size_dependent_default_kernel_is_bit_identical_to_the_tile_kernel(ac, shape):
+    """fwi_fd2d_create picks the step kernel by grid size (small / L2-resident / larger than L2); whatever it picks
+    gives the tile kernel's traces and gradient bit for bit."""
+    import torch
+    nz, nx = shape
+    nt = 41
+    v = torch.tensor(fo.layered_model(shape, 1500.0, 4500.0, 5), dtype=torch.float32)
+    h = 10.0
+    dt = fo.stable_dt(4500.0, h, 2)
+    wav = fo.ricker(nt, dt, 40.0).astype(np.float32)
+    src, rec = [(nz // 2, nx // 2)], [(nz // 2 + dz, nx // 2 + dx) for dz in (-3, 0, 6) for dx in range(-40, 41, 8)]
+    out = []
+    for kw in (dict(), dict(tile=(32, 4))):
+        prop = ac.Propagator2D(shape, h, dt, nabs=20, **kw)
+        prop.set_model(v)
+        prop.set_geometry(src, rec)
+        tr = prop.forward(wav)
+        obs = 0.9 * tr
+        J, g, _ = prop.gradient(wav, obs)
+        out.append((tr.cpu().numpy(), J, g.cpu().numpy()))
+        prop.close()
+    assert np.abs(out[0][0]).max() > 0 and np.abs(out[0][2]).max() > 0
+    assert np.array_equal(out[0][0], out[1][0])
+    assert abs(out[0][1] - out[1][1]) <= 1e-12 * abs(out[1][1])
+    assert np.array_equal(out[0][2], out[1][2])
 
 
 def test_argument_errors(ac):
