@@ -336,7 +336,8 @@ struct fwi_fd2d {
     PointList src_ext2, src_own2, rec_ext2, rec_own2;   // variant 2: binned by the 120 x cz core tiles (+-4 for *_ext2)
     int nsrc = 0, nrec = 0;
     size_t mem_limit = 0;             // 0 = automatic (fraction of free memory)
-    bool pdl = true;                  // chain 2-D tile steps with programmatic dependent launch (FWI_PDL=0 turns it off)
+    bool pdl = true;                  // chain 2-D steps with programmatic dependent launch (FWI_PDL=0 turns it off)
+    bool pdl_chain = false;           // false right after a kernel that rewrites what a step reads BEFORE its dependency wait (m)
     int split_nt = -1, split_seg = 0, split_nseg = 0; size_t split_limit = 0;   // cached storage decision of the last gradient
     int fwd_c = 0, fwd_o = 1;         // fld[] indices of u_n and u_{n-1} after the last forward
     bool model_set = false;
@@ -541,7 +542,8 @@ static int launch_step_cfg(fwi_fd2d* p, int mode, int cur, float* oldnew, const 
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = p->pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = (p->pdl && p->pdl_chain) ? 1 : 0;
+    p->pdl_chain = true;
     if (mode == STEP_FWD) FWI_CUDA(cudaLaunchKernelEx(&cfg, fd2d_step_kernel<BZ, NW, STEP_FWD>, p->tmap[cur], a));
     else if (mode == STEP_FWD_SAVE) FWI_CUDA(cudaLaunchKernelEx(&cfg, fd2d_step_kernel<BZ, NW, STEP_FWD_SAVE>, p->tmap[cur], a));
     else if (mode == STEP_ADJ2) FWI_CUDA(cudaLaunchKernelEx(&cfg, fd2d_step_kernel<BZ, NW, STEP_ADJ2>, p->tmap[cur], a));
@@ -672,9 +674,16 @@ static int launch_tb2_cfg(fwi_fd2d* p, int mode, const State& s, int jc, int jd,
     a.rec1 = rec1; a.rec2 = rec2;
     const dim3 grid(p->tiles_x2, p->tiles_z2), block(NW * 32);
     const size_t smem = ((size_t)(CZ + 16) * kT2W0 + 2 * (size_t)(CZ + 8) * kT2W1) * sizeof(float);
-    if (mode == STEP_FWD) fd2d_tb2_kernel<CZ, NW, STEP_FWD><<<grid, block, smem, st>>>(p->tb_cur[s.c], p->tb_old[s.o], p->tb_m, a);
-    else if (mode == STEP_FWD_SAVE) fd2d_tb2_kernel<CZ, NW, STEP_FWD_SAVE><<<grid, block, smem, st>>>(p->tb_cur[s.c], p->tb_old[s.o], p->tb_m, a);
-    else fd2d_tb2_kernel<CZ, NW, STEP_ADJ><<<grid, block, smem, st>>>(p->tb_cur[s.c], p->tb_old[s.o], p->tb_m, a);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = (p->pdl && p->pdl_chain) ? 1 : 0;      // the pass loads m before its dependency wait
+    p->pdl_chain = true;
+    if (mode == STEP_FWD) FWI_CUDA(cudaLaunchKernelEx(&cfg, fd2d_tb2_kernel<CZ, NW, STEP_FWD>, p->tb_cur[s.c], p->tb_old[s.o], p->tb_m, a));
+    else if (mode == STEP_FWD_SAVE) FWI_CUDA(cudaLaunchKernelEx(&cfg, fd2d_tb2_kernel<CZ, NW, STEP_FWD_SAVE>, p->tb_cur[s.c], p->tb_old[s.o], p->tb_m, a));
+    else FWI_CUDA(cudaLaunchKernelEx(&cfg, fd2d_tb2_kernel<CZ, NW, STEP_ADJ>, p->tb_cur[s.c], p->tb_old[s.o], p->tb_m, a));
     return FWI_OK;
 }
 template <int CZ, int NW>
@@ -1070,6 +1079,7 @@ int fwi_fd2d_set_model(fwi_fd2d* p, const float* v_dev, void* stream) {
     fd_model_kernel<<<grid, 128, 0, p->work>>>(v_dev, p->rows(), p->nx, p->px, p->dt / p->h, p->m, p->vp);
     FWI_CUDA(cudaGetLastError());
     p->model_set = true;
+    p->pdl_chain = false;             // the next step must not start reading m while this kernel is still writing it
     return leave(p, user);
 }
 

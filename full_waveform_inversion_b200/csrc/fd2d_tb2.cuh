@@ -56,22 +56,26 @@ __global__ void __launch_bounds__(NW * 32) fd2d_tb2_kernel(const __grid_constant
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x0 = blockIdx.x * kT2CX, z0 = blockIdx.y * CZ;
+    // Prologue that does not depend on the previous pass (programmatic dependent launch, see fd2d_step_kernel): the
+    // barrier, the sponge profile and the TMA load of m, which never changes inside a sweep.
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
         fence_proxy_async();
         mbar_expect_tx(&bar, (Z0 * kT2W0 + 2 * Z1 * kT2W1) * (uint32_t)sizeof(float));
-        tma_load_2d(sCur, &tm_cur, x0 - 8, z0 - 8, &bar);
-        tma_load_2d(sOld, &tm_old, x0 - 4, z0 - 4, &bar);
         tma_load_2d(sM, &tm_m, x0 - 4, z0 - 4, &bar);
     }
-    __syncthreads();
-
     const int x = x0 - 4 + 4 * lane;                         // first column of this lane's float4 (step-1 frame)
     float gxs[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) gxs[q] = __ldg(a.gx + min(max(x + q, 0), a.px - 1));
     const int tid = blockIdx.y * gridDim.x + blockIdx.x;
+    griddep_wait();                                          // the previous pass is complete and visible
+    if (threadIdx.x == 0) {
+        tma_load_2d(sCur, &tm_cur, x0 - 8, z0 - 8, &bar);
+        tma_load_2d(sOld, &tm_old, x0 - 4, z0 - 4, &bar);
+    }
+    __syncthreads();
 
     mbar_wait(&bar, 0);
 

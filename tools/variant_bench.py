@@ -28,7 +28,7 @@ for nz in sizes:
     nt = max(200, min(1000, int(2.4e9 / (nz * 3000 * 4) / 3)))       # keep the snapshots under ~2.4 GB... scaled below
     nt = min(nt, 600)
     row = []
-    for name, kw in (("tile", {}), ("tb2:24", {"tb2": 24}), ("tb2:32", {"tb2": 32})):
+    for name, kw in (("auto", {}), ("tile", {"tile": (32, 4)}), ("tb2:24", {"tb2": 24}), ("tb2:32", {"tb2": 32})):
         f, g = bench(nz, 3000, nt, **kw)
         row.append("%s fwd %6.2f grad %6.2f" % (name, f, g))
     print("%5d x 3000 nt %d | " % (nz, nt) + " | ".join(row), flush=True)
