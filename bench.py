@@ -216,7 +216,37 @@ def track_a_numbers(device):
     for _ in range(5):
         prob.similarity(Ms, "VR", False, False)
     out["cfg5_e2e_likelihood_evals_per_s"] = 5 * 10_000 / (time.perf_counter() - t0)
-    # CPU: vectorised NumPy oracle, 1 core (the "fair CPU" line of BASELINE.md)
+    # roofline of the direct formulation: achieved FP32 rate over the FMA peak measured on this GPU
+    import ctypes
+    from full_waveform_inversion_b200 import _lib
+    peak = ctypes.c_double(0.0)
+    _lib.check(_lib.require_gpu().fwi_diag_fp32_peak(device, ctypes.byref(peak)))
+    ach = out["N=4000000"]["fp32_tflops_direct"]
+    out["roofline"] = {"bound": "fp32 fma", "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value,
+                       "peak_source": "measured: register-only FMA kernel (fwi_diag_fp32_peak)",
+                       "algorithmic_flop_per_sample": flops}
+    # trace-length sweep of config 1 (T in {128, 512, 2048})
+    for T2 in (128, 2048):
+        d2, G2, _ = orc.synthetic_inputs(K=K, C=C, T=T2, seed=0)
+        pr2 = fw.SourceInversion(d2, G2, device=device)
+        N2 = 4_000_000 if T2 == 128 else 1_000_000
+        pr2.sample_eval_dev(6, 1, 0, N2, amp, 0, 0, reduce=False)
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in range(3):
+            pr2.sample_eval_dev(6, 1 + r, 0, N2, amp, 0, 0, reduce=False)
+        e1.record()
+        torch.cuda.synchronize(device)
+        dt = e0.elapsed_time(e1) / 3 * 1e-3
+        out["T=%d_N=%d" % (T2, N2)] = {"samples_per_s": N2 / dt, "fp32_tflops_direct": N2 * (2 * C + 3) * K * T2 / dt / 1e12}
+        pr2.close()
+    # CPU lines (1 core): the reference-style per-sample loop (oracle restatement of FWI:713-774) and the vectorised
+    # NumPy restatement (the "fair CPU" line of BASELINE.md)
+    draws = orc.draw_raw("single_force_crack_no_coupling", np.random.default_rng(1), 200)
+    t0 = time.perf_counter()
+    orc.monte_carlo_from_draws(d, G, "single_force_crack_no_coupling", draws, amp, "VR", False, False)
+    out["cpu_reference_style_loop_samples_per_s_1core"] = 200 / (time.perf_counter() - t0)
     t0 = time.perf_counter()
     orc.similarity_batch_fast_vr(d, G, Ms[:2000])
     out["cpu_numpy_vectorised_samples_per_s_1core"] = 2000 / (time.perf_counter() - t0)

@@ -842,6 +842,27 @@ __global__ void mc_cholesky_kernel(const double* __restrict__ acc, double* __res
     for (int c = 0; c < C; ++c) m_out[c] = b[c];
 }
 
+// --------------------------------------------------------------------------------------------- FP32 peak probe
+// the Monte-Carlo path is bound by FP32 FMA throughput, which MEASURED_PEAKS.json does not hold.  Eight
+// independent FMA chains per thread, no memory traffic; the result is stored so the chains cannot be removed.
+__global__ void __launch_bounds__(256) fp32_fma_probe_kernel(float* out, int iters, float seed) {
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = seed + (float)(threadIdx.x + i);
+    const float b = 1.0000001f, c = 1e-7f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], b, c);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace fwi
 
 // =============================================================================================== host side
@@ -1393,6 +1414,37 @@ int fwi_mc_lstsq(int device, const double* G_host, const double* d_host, int K, 
     if (rc == FWI_ECUDA) set_error("fwi_mc_lstsq: CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
     cudaFree(buf);
     return rc;
+}
+
+int fwi_diag_fp32_peak(int device, double* tflops_out) {
+    FWI_REQUIRE(tflops_out, "fwi_diag_fp32_peak: NULL output");
+    int ndev = 0;
+    FWI_CUDA(cudaGetDeviceCount(&ndev));
+    FWI_REQUIRE(device >= 0 && device < ndev, "fwi_diag_fp32_peak: device %d out of range (%d visible)", device, ndev);
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    FWI_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    float* out = nullptr;
+    FWI_CUDA(cudaMalloc(&out, (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {           // first repetition warms the clocks up
+        cudaEventRecord(e0);
+        fp32_fma_probe_kernel<<<blocks, threads>>>(out, iters, 1.0f + rep);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const cudaError_t err = cudaGetLastError();
+    cudaFree(out);
+    if (err != cudaSuccess) { set_error("fwi_diag_fp32_peak: %s", cudaGetErrorString(err)); return FWI_ECUDA; }
+    *tflops_out = 2.0 * 64.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+    return FWI_OK;
 }
 
 }  // extern "C"

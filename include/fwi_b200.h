@@ -127,6 +127,10 @@ int fwi_mc_eval_host(fwi_mc_ctx* ctx, const double* M_host, int64_t N, int n_com
  * equations + Cholesky on the device.  G_host (K,C,T), d_host (K,T), M_host (C).  Synchronous. */
 int fwi_mc_lstsq(int device, const double* G_host, const double* d_host, int K, int C, int T, double* M_host);
 
+/* Measurement aid (Track A roofline): achieved FP32 FMA throughput of `device` in TFLOP/s from a register-only
+ * FMA kernel (8 independent chains per thread).  Synchronous, ~10 ms. */
+int fwi_diag_fp32_peak(int device, double* tflops_out);
+
 /* Input preparation: the Green's-function conditioning of load_input_data /
  * get_overall_real_and_green_func_data (FWI:92-111, FWI:178-196) as one device op.  raw_dev: float64 (K,C,T) or
  * (K,C,T,2); shift_dev: K integer sample shifts (np.roll, FWI:97) or NULL; zero_head: zero the wrapped head

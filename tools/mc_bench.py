@@ -2,6 +2,10 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
+from full_waveform_inversion_b200 import _lib as _l
+import os as _os
+if _os.environ.get("FWI_VARIANT_LIB"):
+    _l.LIB_PATH = _os.environ["FWI_VARIANT_LIB"]
 from full_waveform_inversion_b200 import full_waveform_inversion as fw
 from oracle import mc_oracle as orc
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
