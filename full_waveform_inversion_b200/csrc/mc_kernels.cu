@@ -79,7 +79,7 @@ __device__ __forceinline__ void make_coef(float (&coef)[C * NM], const float (&m
 
 // ---------------------------------------------------------------------------------------------
 template <int C, int NM, int S, int MODE>
-__global__ void __launch_bounds__(256, MC_MIN_BLOCKS) mc_eval_kernel(EvalParams p) {
+__global__ void __launch_bounds__(S >= 8 ? 128 : 256, S >= 8 ? 3 : MC_MIN_BLOCKS) mc_eval_kernel(EvalParams p) {
     constexpr int CC = C * NM;
     constexpr int RW = row_width(CC);
     constexpr int RW4 = RW / 4;
@@ -1039,6 +1039,12 @@ static int launch_eval_t(const EvalParams& p, int nwarps, cudaStream_t st) {
 }
 template <int C, int NM, int MODE>
 static int launch_eval_s(const EvalParams& p, int S, int nwarps, cudaStream_t st) {
+    if constexpr (NM == 1 && MODE == MODE_SSE) {
+        // 8 samples per lane: every warp-uniform row load (the load/store unit moves 128 B per float and warp whatever
+        // the address pattern) then feeds twice the FMAs - the direct kernel is LSU-bound at 4 samples per lane
+        if (S == 8) return launch_eval_t<C, NM, 8, MODE>(p, (p.K % 3 == 0 || p.K < 4) ? std::min(3, p.K) : 4, st);
+    }
+    if (S == 8) S = 4;
     if (S == 4) return launch_eval_t<C, NM, (NM == 1 ? 4 : 2), MODE>(p, nwarps, st);
     if (S == 2) return launch_eval_t<C, NM, (NM == 1 ? 2 : 1), MODE>(p, nwarps, st);
     return launch_eval_t<C, NM, 1, MODE>(p, nwarps, st);
@@ -1215,6 +1221,8 @@ int fwi_mc_eval(fwi_mc_ctx* c, const float* M, int64_t ldm, const float* frac, i
     const int64_t full = (int64_t)c->sm_count * 2 * 128;
     if (N < full) S = 2;
     if (N < full / 4) S = 1;
+    if (S == 4 && c->NM == 1 && mode == MODE_SSE && N >= 4 * full && (size_t)c->K * 256 * 8 <= 64 * 1024) S = 8;
+    { const char* e = getenv("FWI_MC_S"); if (e && S > atoi(e) && atoi(e) >= 1) S = atoi(e); }     // tuning aid
     while (S > 1 && (size_t)c->K * nstat(mode) * 32 * (c->NM == 1 ? S : std::max(1, S / 2)) * 8 > 200 * 1024) S >>= 1;
     const int Seff = (c->NM == 1) ? S : std::max(1, S / 2);
     FWI_REQUIRE((size_t)c->K * nstat(mode) * 32 * Seff * 8 <= 220 * 1024, "fwi_mc_eval: K=%d traces exceed the shared-memory statistics buffer", c->K);
