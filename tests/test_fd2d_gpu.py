@@ -223,3 +223,25 @@ def test_argument_errors(ac):
     with pytest.raises(ValueError):
         ac.Propagator2D((20, 40), 10.0, -1.0)
     prop.close()
+
+
+@pytest.mark.parametrize("kw", [dict(tile=(32, 4)), dict(tb2=24)])
+def test_programmatic_dependent_launch_does_not_change_results(ac, monkeypatch, kw):
+    """Steps chained with programmatic dependent launch (default) vs plainly serialised launches (FWI_PDL=0, read when
+    the plan is created), with and without CUDA graphs: identical traces and gradients."""
+    v, h, dt, src, rec, wav = _case(90, 400, 121, seed=11)
+    obs = fo.Problem(v * 1.03, h, dt, src, rec, nabs=10).forward(wav)
+    out = []
+    for pdl, graphs in (("1", True), ("0", True), ("1", False)):
+        monkeypatch.setenv("FWI_PDL", pdl)
+        prop = ac.Propagator2D((90, 400), h, dt, nabs=10, graphs=graphs, **kw)
+        prop.set_model(v)
+        prop.set_geometry(src, rec)
+        tr = prop.forward(wav).cpu().numpy()
+        J, g, _ = prop.gradient(wav, obs)
+        out.append((tr, J, g.cpu().numpy()))
+        prop.close()
+    for tr, J, g in out[1:]:
+        assert np.array_equal(tr, out[0][0])
+        assert abs(J - out[0][1]) <= 1e-12 * abs(out[0][1])
+        assert np.array_equal(g, out[0][2])

@@ -257,3 +257,35 @@ def test_single_sample_generators(fw):
         assert a.shape == (rows, 1)
         assert abs(np.linalg.norm(a) - 1.0) < 1e-5
         assert np.array_equal(a, b) and not np.array_equal(a, c)
+
+
+@pytest.mark.parametrize("metric,simul", [("VR", False), ("VR", True), ("gau", True)])
+def test_eight_samples_per_lane_path(fw, monkeypatch, metric, simul):
+    """Batches of >= ~150 k un-normalised evaluations run 8 samples per lane (mc_eval_kernel<.., S = 8, ..>): same
+    numbers, bit for bit, as the 4-per-lane kernel, and the oracle's on a subset."""
+    K, C, T = 6, 9, 130
+    d, G, _ = orc.synthetic_inputs(K=K, C=C, T=T, seed=5)
+    prob = fw.SourceInversion(d, G)
+    N = 160_001                                     # odd tail on purpose
+    Ms = np.random.default_rng(2).standard_normal((N, C))
+    s8 = prob.similarity(Ms, metric, False, simul)
+    monkeypatch.setenv("FWI_MC_S", "4")
+    s4 = prob.similarity(Ms, metric, False, simul)
+    monkeypatch.delenv("FWI_MC_S")
+    assert np.array_equal(s8, s4)
+    pick = np.r_[0:40, N - 40:N]
+    want = orc.similarity_batch(d, G, Ms[pick], metric, False, simul)
+    np.testing.assert_allclose(s8[pick], want, rtol=0, atol=1e-6)
+    prob.close()
+
+
+def test_fp32_peak_probe(fw):
+    """fwi_diag_fp32_peak (the Track A roofline denominator): a plausible FP32 FMA rate for a B200-class GPU."""
+    import ctypes
+    from full_waveform_inversion_b200 import _lib
+    import torch
+    peak = ctypes.c_double(0.0)
+    _lib.check(_lib.require_gpu().fwi_diag_fp32_peak(torch.cuda.current_device(), ctypes.byref(peak)))
+    assert 20.0 < peak.value < 120.0
+    with pytest.raises(ValueError):
+        _lib.check(_lib.require_gpu().fwi_diag_fp32_peak(99, ctypes.byref(peak)))
