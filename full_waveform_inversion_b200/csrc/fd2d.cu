@@ -603,6 +603,7 @@ static int launch_step3(fwi_fd2d* p, int mode, int cur, float* oldnew, const Poi
     const size_t smem = ((size_t)k3NP * k3PlaneFloats + (size_t)k3NO * 2 * k3OmFloats) * sizeof(float);
     int oi = -1;
     for (int i = 0; i < 8; ++i) if (p->fld[i] == oldnew) oi = i;
+    // (programmatic dependent launch was measured on this kernel too: 2 % at 128^3, nothing from 256^3 up - not used)
     if (mode == STEP_FWD) fd3d_step_kernel<STEP_FWD><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
     else if (mode == STEP_FWD_SAVE) fd3d_step_kernel<STEP_FWD_SAVE><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
     else if (mode == STEP_ADJ2) fd3d_step_kernel<STEP_ADJ2><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
@@ -709,6 +710,7 @@ static int launch_tb2(fwi_fd2d* p, int mode, const State& s, int jc, int jd, con
 static int run_forward(fwi_fd2d* p, const float* wavelet, int n0, int n1, float* traces, bool save, size_t snap_base,
                        State& s, cudaStream_t st) {
     const size_t pl = p->plane();
+    p->pdl_chain = false;             // (segment of) a sweep starts behind memsets / checkpoint copies: full dependency
     int n = n0;
     if (p->variant == 2 && p->ny == 1) {
         for (; n + 1 < n1; n += 2) {
@@ -737,6 +739,7 @@ static int run_forward(fwi_fd2d* p, const float* wavelet, int n0, int n1, float*
 // adjoint steps for trace rows n1-1 down to n0 (fields fld[4..7])
 static int run_adjoint(fwi_fd2d* p, const float* resid, int n0, int n1, size_t snap_base, State& s, cudaStream_t st) {
     const size_t pl = p->plane();
+    p->pdl_chain = false;             // first adjoint step follows the residual kernel and the field memsets
     int n = n1 - 1;
     if (p->variant == 2 && p->ny == 1) {
         for (; n - 1 >= n0; n -= 2) {
@@ -831,6 +834,7 @@ static int record_gradient(fwi_fd2d* p, int nt, int seg, int nseg, cudaStream_t 
 // Run `record` either directly on the work stream or as a cached graph keyed by (kind, nt, nsrc, nrec, seg, nseg).
 template <typename F>
 static int run_cached(fwi_fd2d* p, int kind, int nt, int seg, int nseg, F&& record) {
+    p->pdl_chain = false;             // the first step of a sweep follows memsets / copies / foreign kernels: full dependency
     if (!p->use_graphs) return record(p->work);
     for (auto& g : p->graphs)
         if (g.kind == kind && g.nt == nt && g.nsrc == p->nsrc && g.nrec == p->nrec && g.seg == seg && g.nseg == nseg) {
@@ -1250,6 +1254,7 @@ int fwi_fd_step(fwi_fd2d* p, int mode, int cur, const float* inj_vals_dev, float
         p->slab_signal = ++p->step_base;
     }
     FWI_REQUIRE(mode >= 0 && mode <= 2 && (cur == 0 || cur == 1), "fwi_fd_step: bad mode / cur");
+    p->pdl_chain = false;             // caller-driven loop: other kernels (halo exchange, resets) sit between the steps
     FWI_REQUIRE(mode == 0 || (snap_index >= 0 && (size_t)(snap_index + 1) * p->plane() <= p->snap_steps), "fwi_fd_step: snapshot %lld not reserved", (long long)snap_index);
     DeviceGuard g(p->device);
     const int base = (mode == STEP_ADJ) ? 4 : 0;
