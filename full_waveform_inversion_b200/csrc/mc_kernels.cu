@@ -2,11 +2,12 @@
 //
 //   sample -> forward model -> misfit -> likelihood            (FWI:713-774)
 //
-// One warp owns one trace k at a time and streams that trace's prepared rows
-// [t][G_0..G_{CC-1}, d, d'] with warp-uniform 16-byte loads (one LDG.128 feeds four FMAs of
-// every lane); each lane owns S source samples whose coefficient vectors live in registers, so
-// the K*T*C contraction needs no cross-thread reduction at all.  Per-(trace,sample) statistics go
-// to shared memory and are folded into the similarity in float64 by one thread per sample.
+// A lane owns S source samples whose coefficient vectors live in registers; a warp walks the traces and streams each
+// trace's prepared rows [t][G_0..G_{CC-1}, d, d'] with warp-uniform 16-byte loads (one LDG.128 feeds four FMAs of
+// every lane), so the K*T*C contraction needs no cross-thread reduction at all.  After each trace the lane folds that
+// trace's statistics into running per-sample sums in float64 (warp-private shared memory), so the footprint does not
+// depend on K.  Big batches: every warp (pair) owns its own samples; small, latency-bound batches: the warps of a CTA
+// share one sample group and split the traces.
 // The path is FP32-FMA bound (G is ~0.4 MB and L2/L1 resident; ~40-80 B of HBM traffic per sample).
 #include "common.cuh"
 #include <cmath>
@@ -56,6 +57,7 @@ struct EvalParams {
     int nfrac;
     int64_t N;
     int K, Tv, metric, flags, boundary_fix;
+    int ks;                  // warps of a CTA that share one sample group and split the traces between them (1 = none)
     float* sim;
     float* like;
 };
@@ -78,20 +80,30 @@ __device__ __forceinline__ void make_coef(float (&coef)[C * NM], const float (&m
 }
 
 // ---------------------------------------------------------------------------------------------
+constexpr int kMcAcc = 5;      // running sums per sample: 3 accumulators + the two boundary-patch carries of flattened CC-shift
+
 template <int C, int NM, int S, int MODE>
 __global__ void __launch_bounds__(S >= 8 ? 128 : 256, S >= 8 ? 3 : MC_MIN_BLOCKS) mc_eval_kernel(EvalParams p) {
     constexpr int CC = C * NM;
     constexpr int RW = row_width(CC);
     constexpr int RW4 = RW / 4;
-    constexpr int NST = nstat(MODE);
-    constexpr int SPB = 32 * S;
+    constexpr int SPW = 32 * S;               // samples per warp
     constexpr int CHUNK = 64;
-    extern __shared__ double stats[];         // [K][NST][SPB] (float64: the fold below cancels terms)
+    extern __shared__ double fold_smem[];     // [warps][kMcAcc][SPW] float64, private to each warp (no block-level sync)
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
-    const int64_t base = (int64_t)blockIdx.x * SPB;
+    // Large batches: every warp owns its own SPW samples and walks all K traces (ks = 1, no block-level sync at all).
+    // Small batches are latency-bound, so ks warps share one sample group and take every ks-th trace each.
+    const int kw = warp % p.ks;
+    const int64_t base = ((int64_t)blockIdx.x * (nwarps / p.ks) + warp / p.ks) * SPW;
+    const bool active = base < p.N;           // warp-uniform
+    double* acc = fold_smem + (size_t)warp * kMcAcc * SPW + lane;          // acc[j * SPW + s * 32]
+#pragma unroll
+    for (int j = 0; j < kMcAcc; ++j)
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc[j * SPW + s * 32] = 0.0;
 
     float m[S][C];
     float fr[S][3];
@@ -108,7 +120,7 @@ __global__ void __launch_bounds__(S >= 8 ? 128 : 256, S >= 8 ? 3 : MC_MIN_BLOCKS
         }
     }
 
-    for (int k = warp; k < p.K; k += nwarps) {
+    for (int k = active ? kw : p.K; k < p.K; k += p.ks) {
         float coef[S][CC];
         float mu[S];
         const int ph = (NM == 2 && p.nfrac == 3 && p.phase) ? p.phase[k] : 0;
@@ -188,112 +200,107 @@ __global__ void __launch_bounds__(S >= 8 ? 128 : 256, S >= 8 ? 3 : MC_MIN_BLOCKS
 #pragma unroll
             for (int s = 0; s < S; ++s) { t0[s] += (double)a0[s]; t1[s] += (double)a1[s]; }
         }
+
+        // ---- fold trace k into the running per-sample sums (float64: the expressions cancel), each lane its own samples
+        const TraceConst tc = p.tc[k];
+        const bool simul = p.flags & FWI_FLAG_SIMULTANEOUS;
+        const bool vr_like = p.metric == FWI_METRIC_VR || p.metric == FWI_METRIC_GAU;
+        const double Tn = (double)p.Tv;
+        // CC-shift, normalised, flattened: np.interp runs across trace boundaries on the already-normalised flattened
+        // arrays (FWI:612, FWI:554-555); the rows hold the per-trace clamped interpolation, so the 3 points after each
+        // internal boundary are patched from the first / last synthetic value of the neighbouring traces.
+        const bool patch = MODE == MODE_MOM_MAX && !vr_like && simul && p.boundary_fix;
+        const float* rf = p.rows + (size_t)k * p.Tv * RW;
+        const float* rl = rf + (size_t)(p.Tv - 1) * RW;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            double* st = stats + (size_t)k * NST * SPB + s * 32 + lane;
-            st[0] = t0[s];
-            if (MODE != MODE_SSE) { st[SPB] = t1[s]; st[2 * SPB] = (double)mu[s]; }
-            if (MODE == MODE_MOM_MAX) st[3 * SPB] = fmax(fabs((double)vmax[s] + (double)mu[s]), fabs((double)vmin[s] + (double)mu[s]));
-        }
-    }
-    __syncthreads();
-
-    // ---- fold the per-trace statistics into the similarity, one thread per sample (float64)
-    for (int i = threadIdx.x; i < SPB; i += blockDim.x) {
-        const int64_t n = base + i;
-        if (n >= p.N) continue;
-        const bool norm = p.flags & FWI_FLAG_NORMALISED;
-        const bool simul = p.flags & FWI_FLAG_SIMULTANEOUS;
-        const double Tn = (double)p.Tv;
-        const double* st = stats + i;
-        double result;
-        if (p.metric == FWI_METRIC_VR || p.metric == FWI_METRIC_GAU) {
-            double acc = 0.0, tot_sse = 0.0, tot_dd = 0.0;
-            for (int k = 0; k < p.K; ++k) {
-                const TraceConst tc = p.tc[k];
-                const double* q = st + (size_t)k * NST * SPB;
+            double* q = acc + s * 32;
+            const double s2 = t0[s], sd = t1[s], mud = (double)mu[s];
+            double a = 1.0, b = 1.0;
+            if (MODE == MODE_MOM_MAX) {
+                a = 1.0 / fmax(fabs((double)vmax[s] + mud), fabs((double)vmin[s] + mud));      // FWI:598-599
+                b = 1.0 / tc.maxd;
+            }
+            if (vr_like) {
                 double sse, dd, sig = tc.sigma;
                 if (MODE == MODE_SSE) {
-                    sse = q[0];
+                    sse = s2;
                     dd = tc.sumd2;
                 } else {
-                    const double s2 = q[0], sd = q[SPB], mu = q[2 * SPB];
-                    const double a = 1.0 / (double)q[3 * SPB], b = 1.0 / tc.maxd;    // FWI:598-599
-                    const double Sss = (s2 + Tn * mu * mu) * a * a;
-                    const double Sds = (sd + Tn * tc.mean_d * mu) * a * b;
+                    const double Sss = (s2 + Tn * mud * mud) * a * a;
+                    const double Sds = (sd + Tn * tc.mean_d * mud) * a * b;
                     dd = tc.sumd2 * b * b;
                     sse = dd - 2.0 * Sds + Sss;
                     sig = tc.sigma * b;
                 }
-                tot_sse += sse;
-                tot_dd += dd;
-                if (p.metric == FWI_METRIC_VR) acc += fmax(0.0, 1.0 - sse / dd);      // FWI:515-519
-                else acc += exp(-sse / (2.0 * sig * sig));                             // FWI:581
-            }
-            if (simul) {
-                if (p.metric == FWI_METRIC_VR) result = fmax(0.0, 1.0 - tot_sse / tot_dd);
-                else { const double sg = p.fc.sigma[norm ? 1 : 0]; result = exp(-tot_sse / (2.0 * sg * sg)); }
+                q[SPW] += sse;
+                q[2 * SPW] += dd;
+                if (p.metric == FWI_METRIC_VR) q[0] += fmax(0.0, 1.0 - sse / dd);      // FWI:515-519
+                else q[0] += exp(-sse / (2.0 * sig * sig));                             // FWI:581
+            } else if (!simul) {
+                const double pcc = sd / sqrt(s2 * tc.ssd);                              // FWI:572-573
+                q[0] += (pcc < 0.0) ? 0.0 : pcc;                                        // FWI:574-575
             } else {
-                result = acc / p.K;                                                    // FWI:682
+                double A1 = a * Tn * mud, A2 = a * a * (s2 + Tn * mud * mud), A3 = a * b * (sd + Tn * tc.mean_d * mud);
+                if (patch) {
+                    double first = 0.0, last = 0.0;
+#pragma unroll
+                    for (int c = 0; c < CC; ++c) { first += (double)__ldg(rf + c) * coef[s][c]; last += (double)__ldg(rl + c) * coef[s][c]; }
+                    if (k > 0) {
+                        const double c_ = q[3 * SPW], cd = q[4 * SPW];
+                        const double dl = first * a - c_, dd = tc.d_first * b - cd;
+                        A1 += 1.5 * dl;
+                        A2 += 3.0 * c_ * dl + 0.875 * dl * dl;
+                        A3 += 1.5 * (cd * dl + c_ * dd) + 0.875 * dd * dl;
+                    }
+                    q[3 * SPW] = last * a;
+                    q[4 * SPW] = tc.d_last * b;
+                }
+                q[0] += A1; q[SPW] += A2; q[2 * SPW] += A3;
+            }
+        }
+    }
+
+    // ---- similarity and likelihood of this lane's samples (the first warp of a group adds its partners' sums first)
+    if (p.ks > 1) {
+        __syncthreads();
+        if (kw == 0) {
+            for (int w = 1; w < p.ks; ++w) {
+                const double* o = acc + (size_t)w * kMcAcc * SPW;
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+#pragma unroll
+                    for (int s = 0; s < S; ++s) acc[j * SPW + s * 32] += o[j * SPW + s * 32];
+            }
+        }
+    }
+    if (!active || kw != 0) return;
+    const bool norm = p.flags & FWI_FLAG_NORMALISED;
+    const bool simul = p.flags & FWI_FLAG_SIMULTANEOUS;
+    const bool vr_like = p.metric == FWI_METRIC_VR || p.metric == FWI_METRIC_GAU;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int64_t n = base + s * 32 + lane;
+        if (n >= p.N) continue;
+        const double* q = acc + s * 32;
+        double result;
+        if (vr_like) {
+            if (simul) {
+                if (p.metric == FWI_METRIC_VR) result = fmax(0.0, 1.0 - q[SPW] / q[2 * SPW]);
+                else { const double sg = p.fc.sigma[norm ? 1 : 0]; result = exp(-q[SPW] / (2.0 * sg * sg)); }
+            } else {
+                result = q[0] / p.K;                                                   // FWI:682
                 if (p.metric == FWI_METRIC_GAU && (p.flags & FWI_FLAG_STRICT_REF)) result = 0.0;   // quirk q1
             }
-        } else {   // CC, PCC, CC-shift: Pearson on the (possibly 4x interpolated) rows
-            if (!simul) {
-                double acc = 0.0;
-                for (int k = 0; k < p.K; ++k) {
-                    const double* q = st + (size_t)k * NST * SPB;
-                    const double pcc = (double)q[SPB] / sqrt((double)q[0] * p.tc[k].ssd);   // FWI:572-573
-                    acc += (pcc < 0.0) ? 0.0 : pcc;                                          // FWI:574-575
-                }
-                result = acc / p.K;
-            } else {
-                double A1 = 0.0, A2 = 0.0, A3 = 0.0;
-                for (int k = 0; k < p.K; ++k) {
-                    const TraceConst tc = p.tc[k];
-                    const double* q = st + (size_t)k * NST * SPB;
-                    const double s2 = q[0], sd = q[SPB], mu = q[2 * SPB];
-                    double a = 1.0, b = 1.0;
-                    if (MODE == MODE_MOM_MAX) { a = 1.0 / (double)q[3 * SPB]; b = 1.0 / tc.maxd; }
-                    A1 += a * Tn * mu;
-                    A2 += a * a * (s2 + Tn * mu * mu);
-                    A3 += a * b * (sd + Tn * tc.mean_d * mu);
-                }
-                if (MODE == MODE_MOM_MAX && p.boundary_fix) {
-                    // CC-shift, normalised, flattened: np.interp runs across trace boundaries on the
-                    // already-normalised flattened arrays (FWI:612, FWI:554-555); the rows hold the
-                    // per-trace clamped interpolation, so patch the 3 points after each internal boundary.
-                    float mm[C];
-                    for (int c = 0; c < C; ++c) mm[c] = __ldg(p.M + (int64_t)c * p.ldm + n);
-                    float ff[3] = {0.f, 0.f, 0.f};
-                    if (NM == 2) for (int j = 0; j < p.nfrac; ++j) ff[j] = __ldg(p.frac + (int64_t)j * p.ldm + n);
-                    double prev_c = 0.0, prev_cd = 0.0;
-                    for (int k = 0; k < p.K; ++k) {
-                        const TraceConst tc = p.tc[k];
-                        float coef[CC];
-                        const int ph = (NM == 2 && p.nfrac == 3 && p.phase) ? p.phase[k] : 0;
-                        make_coef<C, NM>(coef, mm, ff[ph]);
-                        const float* r0 = p.rows + ((size_t)k * p.Tv) * RW;
-                        const float* r1 = p.rows + ((size_t)k * p.Tv + p.Tv - 1) * RW;
-                        double first = 0.0, last = 0.0;
-                        for (int c = 0; c < CC; ++c) { first += (double)r0[c] * coef[c]; last += (double)r1[c] * coef[c]; }
-                        const double a = 1.0 / (double)st[((size_t)k * NST + 3) * SPB], b = 1.0 / tc.maxd;
-                        if (k > 0) {
-                            const double c_ = prev_c, cd = prev_cd;
-                            const double dl = first * a - c_, dd = tc.d_first * b - cd;
-                            A1 += 1.5 * dl;
-                            A2 += 3.0 * c_ * dl + 0.875 * dl * dl;
-                            A3 += 1.5 * (cd * dl + c_ * dd) + 0.875 * dd * dl;
-                        }
-                        prev_c = last * a;
-                        prev_cd = tc.d_last * b;
-                    }
-                }
-                const int ni = norm ? 1 : 0;
-                const double nn = p.fc.n, D1 = p.fc.D1[ni], D2 = p.fc.D2[ni];
-                const double cov = A3 - A1 * D1 / nn, vs = A2 - A1 * A1 / nn, vd = D2 - D1 * D1 / nn;
-                const double pcc = cov / sqrt(vs * vd);
-                result = (pcc < 0.0) ? 0.0 : pcc;
-            }
+        } else if (!simul) {
+            result = q[0] / p.K;
+        } else {
+            const int ni = norm ? 1 : 0;
+            const double A1 = q[0], A2 = q[SPW], A3 = q[2 * SPW];
+            const double nn = p.fc.n, D1 = p.fc.D1[ni], D2 = p.fc.D2[ni];
+            const double cov = A3 - A1 * D1 / nn, vs = A2 - A1 * A1 / nn, vd = D2 - D1 * D1 / nn;
+            const double pcc = cov / sqrt(vs * vd);
+            result = (pcc < 0.0) ? 0.0 : pcc;
         }
         p.sim[n] = (float)result;
         if (p.like) p.like[n] = (float)exp(-(1.0 - result) * 0.5);                   // FWI:774
@@ -1028,21 +1035,21 @@ static int build_rowset(fwi_mc_ctx* c, RowSet& rs, int variant) {
 
 template <int C, int NM, int S, int MODE>
 static int launch_eval_t(const EvalParams& p, int nwarps, cudaStream_t st) {
-    constexpr int SPB = 32 * S;
-    const size_t smem = (size_t)p.K * nstat(MODE) * SPB * sizeof(double);
+    constexpr int SPW = 32 * S;
+    const size_t smem = (size_t)nwarps * kMcAcc * SPW * sizeof(double);
     auto kern = mc_eval_kernel<C, NM, S, MODE>;
     if (smem > 48 * 1024) FWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t blocks = ceil_div(p.N, SPB);
+    const int64_t blocks = ceil_div(p.N, (int64_t)SPW * (nwarps / p.ks));
     kern<<<(unsigned)blocks, nwarps * 32, smem, st>>>(p);
     FWI_CUDA(cudaGetLastError());
     return FWI_OK;
 }
 template <int C, int NM, int MODE>
 static int launch_eval_s(const EvalParams& p, int S, int nwarps, cudaStream_t st) {
-    if constexpr (NM == 1 && MODE == MODE_SSE) {
+    if constexpr (NM == 1) {
         // 8 samples per lane: every warp-uniform row load (the load/store unit moves 128 B per float and warp whatever
         // the address pattern) then feeds twice the FMAs - the direct kernel is LSU-bound at 4 samples per lane
-        if (S == 8) return launch_eval_t<C, NM, 8, MODE>(p, (p.K % 3 == 0 || p.K < 4) ? std::min(3, p.K) : 4, st);
+        if (S == 8) return launch_eval_t<C, NM, 8, MODE>(p, std::min(nwarps, 4), st);
     }
     if (S == 8) S = 4;
     if (S == 4) return launch_eval_t<C, NM, (NM == 1 ? 4 : 2), MODE>(p, nwarps, st);
@@ -1216,17 +1223,23 @@ int fwi_mc_eval(fwi_mc_ctx* c, const float* M, int64_t ldm, const float* frac, i
         FWI_CUDA(cudaGetLastError());
         return FWI_OK;
     }
-    // samples per lane: 4 when there is enough work to fill the machine twice over, else fewer
+    // samples per lane: 4 when there is enough work to fill the machine twice over, else fewer; 8 for big un-normalised
+    // single-medium batches (see launch_eval_s)
     int S = 4;
     const int64_t full = (int64_t)c->sm_count * 2 * 128;
     if (N < full) S = 2;
     if (N < full / 4) S = 1;
-    if (S == 4 && c->NM == 1 && mode == MODE_SSE && N >= 4 * full && (size_t)c->K * 256 * 8 <= 64 * 1024) S = 8;
+    const bool big = N >= 4 * full;
+    if (big && c->NM == 1) S = 8;
     { const char* e = getenv("FWI_MC_S"); if (e && S > atoi(e) && atoi(e) >= 1) S = atoi(e); }     // tuning aid
-    while (S > 1 && (size_t)c->K * nstat(mode) * 32 * (c->NM == 1 ? S : std::max(1, S / 2)) * 8 > 200 * 1024) S >>= 1;
-    const int Seff = (c->NM == 1) ? S : std::max(1, S / 2);
-    FWI_REQUIRE((size_t)c->K * nstat(mode) * 32 * Seff * 8 <= 220 * 1024, "fwi_mc_eval: K=%d traces exceed the shared-memory statistics buffer", c->K);
-    const int nw = pick_warps(c->K);
+    // big batches: one sample group per warp, every warp walks all K traces (no block-level synchronisation);
+    // small batches are latency-bound: the warps of a CTA share one sample group and split the traces.  The
+    // cross-boundary patch of flattened CC-shift carries state from trace to trace, so it never splits.
+    int nw = (S == 8) ? 4 : 8, ks = 1;
+    if (!big && !boundary_fix) { nw = pick_warps(c->K); ks = nw; }
+    else if (!boundary_fix && S == 8) ks = 2;     // measured at N = 2e6 / 4e6: ks 1: 175, 2: 215, 4: 189 M samples/s (finer CTA tail)
+    { const char* e = getenv("FWI_MC_KS"); if (e && !boundary_fix && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) ks = atoi(e); }   // tuning aid
+    p.ks = ks;
     cudaStream_t st = (cudaStream_t)stream;
     if (c->NM == 1) {
         if (c->C == 3) return launch_eval_m<3, 1>(p, mode, S, nw, st);

@@ -184,7 +184,7 @@ def test_size_independent_properties_at_scale(ac):
     prop.close()
 
 
-@pytest.mark.parametrize("shape", [(100, 300), (1000, 3000), (2600, 3000)])
+@pytest.mark.parametrize("shape", [(100, 300), (33, 131), (1000, 3000), (2600, 3000), (2503, 3001)])
 def test_size_dependent_default_kernel_is_bit_identical_to_the_tile_kernel(ac, shape):
     """fwi_fd2d_create picks the step kernel by grid size (small / L2-resident / larger than L2); whatever it picks
     gives the tile kernel's traces and gradient bit for bit."""
