@@ -83,7 +83,7 @@ __device__ __forceinline__ void make_coef(float (&coef)[C * NM], const float (&m
 constexpr int kMcAcc = 5;      // running sums per sample: 3 accumulators + the two boundary-patch carries of flattened CC-shift
 
 template <int C, int NM, int S, int MODE>
-__global__ void __launch_bounds__(S >= 8 ? 128 : 256, S >= 8 ? 3 : MC_MIN_BLOCKS) mc_eval_kernel(EvalParams p) {
+__global__ void __launch_bounds__(S * NM >= 8 ? 128 : 256, S * NM >= 8 ? 3 : MC_MIN_BLOCKS) mc_eval_kernel(EvalParams p) {
     constexpr int CC = C * NM;
     constexpr int RW = row_width(CC);
     constexpr int RW4 = RW / 4;
@@ -1046,12 +1046,10 @@ static int launch_eval_t(const EvalParams& p, int nwarps, cudaStream_t st) {
 }
 template <int C, int NM, int MODE>
 static int launch_eval_s(const EvalParams& p, int S, int nwarps, cudaStream_t st) {
-    if constexpr (NM == 1) {
-        // 8 samples per lane: every warp-uniform row load (the load/store unit moves 128 B per float and warp whatever
-        // the address pattern) then feeds twice the FMAs - the direct kernel is LSU-bound at 4 samples per lane
-        if (S == 8) return launch_eval_t<C, NM, 8, MODE>(p, std::min(nwarps, 4), st);
-    }
-    if (S == 8) S = 4;
+    // "wide" kernels for big batches: 8 samples per lane (4 for two media: the coefficient vector is twice as long).
+    // Every warp-uniform row load (the load/store unit moves 128 B per float and warp whatever the address pattern)
+    // then feeds twice the FMAs - the direct kernel is LSU-bound at 4 samples per lane.  168 registers, 128 threads.
+    if (S == 8) return launch_eval_t<C, NM, (NM == 1 ? 8 : 4), MODE>(p, std::min(nwarps, 4), st);
     if (S == 4) return launch_eval_t<C, NM, (NM == 1 ? 4 : 2), MODE>(p, nwarps, st);
     if (S == 2) return launch_eval_t<C, NM, (NM == 1 ? 2 : 1), MODE>(p, nwarps, st);
     return launch_eval_t<C, NM, 1, MODE>(p, nwarps, st);
@@ -1230,7 +1228,7 @@ int fwi_mc_eval(fwi_mc_ctx* c, const float* M, int64_t ldm, const float* frac, i
     if (N < full) S = 2;
     if (N < full / 4) S = 1;
     const bool big = N >= 4 * full;
-    if (big && c->NM == 1) S = 8;
+    if (big) S = 8;                          // the wide kernels
     { const char* e = getenv("FWI_MC_S"); if (e && S > atoi(e) && atoi(e) >= 1) S = atoi(e); }     // tuning aid
     // big batches: one sample group per warp, every warp walks all K traces (no block-level synchronisation);
     // small batches are latency-bound: the warps of a CTA share one sample group and split the traces.  The

@@ -306,3 +306,28 @@ def test_many_traces(fw, metric, norm, simul):
     want = orc.similarity_batch(d, G, Ms, metric, norm, simul)
     np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
     prob.close()
+
+
+@pytest.mark.parametrize("metric,norm,simul,three", [("VR", False, False, False), ("PCC", True, True, True), ("CC-shift", True, True, False)])
+def test_wide_kernel_two_media(fw, monkeypatch, metric, norm, simul, three):
+    """Big two-media batches (FWI:715-731 mixing folded into the coefficients) run the wide kernel: same numbers as the
+    narrow one and as the oracle's explicit mixing."""
+    K, C, T = 5, 6, 96
+    d, G2, _ = orc.synthetic_inputs(K=K, C=C, T=T, seed=23, n_media=2)
+    phase_index = np.array([0, 1, 2, 0, 1]) if three else None
+    labels = [orc.PHASE_ORDER[i] for i in phase_index] if three else []
+    prob = fw.SourceInversion(d, G2, labels)
+    N = 155_000
+    rng = np.random.default_rng(4)
+    Ms = rng.standard_normal((N, C))
+    fr = rng.random((N, 3 if three else 1))
+    wide = prob.similarity(Ms, metric, norm, simul, media_frac=fr)
+    monkeypatch.setenv("FWI_MC_S", "4")
+    narrow = prob.similarity(Ms, metric, norm, simul, media_frac=fr)
+    monkeypatch.delenv("FWI_MC_S")
+    np.testing.assert_allclose(wide, narrow, rtol=0, atol=2e-7)
+    pick = np.r_[0:25, N - 25:N]
+    want = np.array([orc.compare_synth_to_real_waveforms(
+        d, orc.forward_model(orc.mix_media(G2, fr[i] if three else fr[i, 0], phase_index), Ms[i]), metric, norm, simul) for i in pick])
+    np.testing.assert_allclose(wide[pick], want, rtol=0, atol=2e-6)
+    prob.close()
