@@ -44,6 +44,11 @@ struct Step2DArgs {
     float* rec_out;
 };
 
+#ifndef FWI_PREFETCH_ROW0
+// rows of u_{n-1} / m requested before the dependency wait.  ms per 1000-step gradient at 1000x3000: 0 rows 17.0, 1 row
+// 16.2, 2 rows 16.0 (80 registers, still 6 CTAs per SM); prefetching the adjoint's snapshot row as well: 16.5 - 19.0
+#define FWI_PREFETCH_ROW0 2
+#endif
 #ifndef FWI_PDL_TRIGGER
 // Where a step lets its successor's CTAs become resident: 0 = implicit, when its own CTAs exit (default), 1 = top,
 // 2 = after the dense part, 3 = after the TMA wait.  Measured on the bench workload (ms per 5000-step gradient):
@@ -74,6 +79,17 @@ __global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constan
     float4 gx4 = make_float4(1.f, 1.f, 1.f, 1.f);
     if (col_ok) gx4 = ld4(a.gx + x);
     // (prefetching the adjoint's snapshot rows into L2 from here was measured: 17.3 vs 17.0 ms per 1000-step gradient, not kept)
+#if FWI_PREFETCH_ROW0
+    // u_{n-1} and m of this warp's first rows: neither is written by the step this launch is chained to (u_{n-1} is the
+    // output of step n-2, which completed before step n-1 passed its own wait), and requesting them here takes one L2
+    // round trip off the serial chain  TMA wait -> row loads -> compute
+    float4 o4p[FWI_PREFETCH_ROW0], m4p[FWI_PREFETCH_ROW0];
+#pragma unroll
+    for (int r = 0; r < FWI_PREFETCH_ROW0; ++r) {
+        o4p[r] = make_float4(0.f, 0.f, 0.f, 0.f); m4p[r] = o4p[r];
+        if (col_ok && zw + r < a.nz) { o4p[r] = ld4(a.oldnew + (size_t)(zw + r) * a.px + x); m4p[r] = ld4(a.m + (size_t)(zw + r) * a.px + x); }
+    }
+#endif
     griddep_wait();                 // step n complete and visible (no-op for a plain launch)
 #if FWI_PDL_TRIGGER == 1
     griddep_launch_dependents();    // every CTA of this grid is resident once all have passed here: step n+2's may queue up
@@ -110,8 +126,13 @@ __global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constan
 #pragma unroll
                 for (int k = 0; k < 9; ++k) { zc[k][0] = win[k].x; zc[k][1] = win[k].y; zc[k][2] = win[k].z; zc[k][3] = win[k].w; }
                 const size_t off = (size_t)z * a.px + x;
+#if FWI_PREFETCH_ROW0
+                const float4 o4 = (r < FWI_PREFETCH_ROW0) ? o4p[r < FWI_PREFETCH_ROW0 ? r : 0] : ld4(a.oldnew + off);
+                const float4 m4 = (r < FWI_PREFETCH_ROW0) ? m4p[r < FWI_PREFETCH_ROW0 ? r : 0] : ld4(a.m + off);
+#else
                 const float4 o4 = ld4(a.oldnew + off);
                 const float4 m4 = ld4(a.m + off);
+#endif
                 const float gzv = __ldg(a.gz + z);
                 const float ov[4] = {o4.x, o4.y, o4.z, o4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w};
                 const float gv[4] = {gx4.x * gzv, gx4.y * gzv, gx4.z * gzv, gx4.w * gzv};
@@ -725,6 +746,8 @@ static int run_forward(fwi_fd2d* p, const float* wavelet, int n0, int n1, float*
             s = State{jc, jd};
         }
     }
+    // a leftover single step behind a two-steps-per-pass launch reads u_{n-1} written by that very pass: no chaining
+    if (p->variant == 2 && p->ny == 1) p->pdl_chain = false;
     for (; n < n1; ++n) {
         float* snap = save ? p->snap + (size_t)(n - snap_base) * pl : nullptr;
         int rc = launch_step(p, save ? STEP_FWD_SAVE : STEP_FWD, s.c, p->fld[s.o], &p->src, wavelet + (size_t)n * p->nsrc,
@@ -764,6 +787,7 @@ static int run_adjoint(fwi_fd2d* p, const float* resid, int n0, int n1, size_t s
             s = State{s.o, s.c};
         }
     }
+    if (p->variant == 2 && p->ny == 1) p->pdl_chain = false;          // see run_forward: leftover step behind a two-step pass
     for (; n >= n0; --n) {
         int rc = launch_step(p, STEP_ADJ, s.c, p->fld[s.o], &p->rec, resid + (size_t)n * p->nrec, nullptr, nullptr,
                              p->snap + (size_t)(n - snap_base) * pl, st);
