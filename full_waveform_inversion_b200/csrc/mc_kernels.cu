@@ -1221,8 +1221,8 @@ int fwi_mc_eval(fwi_mc_ctx* c, const float* M, int64_t ldm, const float* frac, i
         FWI_CUDA(cudaGetLastError());
         return FWI_OK;
     }
-    // samples per lane: 4 when there is enough work to fill the machine twice over, else fewer; 8 for big un-normalised
-    // single-medium batches (see launch_eval_s)
+    // samples per lane: 4 when there is enough work to fill the machine twice over, else fewer; the wide kernels (8 per
+    // lane, 4 for two media) for big batches (see launch_eval_s)
     int S = 4;
     const int64_t full = (int64_t)c->sm_count * 2 * 128;
     if (N < full) S = 2;
@@ -1236,7 +1236,7 @@ int fwi_mc_eval(fwi_mc_ctx* c, const float* M, int64_t ldm, const float* frac, i
     int nw = (S == 8) ? 4 : 8, ks = 1;
     if (!big && !boundary_fix) { nw = pick_warps(c->K); ks = nw; }
     else if (!boundary_fix && S == 8) ks = 2;     // measured at N = 2e6 / 4e6: ks 1: 175, 2: 215, 4: 189 M samples/s (finer CTA tail)
-    { const char* e = getenv("FWI_MC_KS"); if (e && !boundary_fix && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) ks = atoi(e); }   // tuning aid
+    { const char* e = getenv("FWI_MC_KS"); if (e && big && !boundary_fix && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) ks = atoi(e); }   // tuning aid (nw = 4 or 8 here)
     p.ks = ks;
     cudaStream_t st = (cudaStream_t)stream;
     if (c->NM == 1) {
