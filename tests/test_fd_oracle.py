@@ -131,3 +131,26 @@ def test_c_port_matches_numpy_oracle(ndim):
     assert np.linalg.norm(old3 - old0) / np.linalg.norm(old0) < 1e-12
     assert ws3.shape == (wav.shape[0],) + v.shape
     assert foc.num_threads() >= 1
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_adjoint_dot_product_identity_of_the_specification(ndim):
+    """<L w, d> = <w, L^T d>: with q = m g lambda the adjoint recursion is the forward step itself (B3), so L^T is forward
+    modelling with sources and receivers swapped and time reversed.  Exact to rounding in float64; the same identity is
+    checked through the CUDA kernels in tests/test_fd_scale_gpu.py."""
+    rng = np.random.default_rng(0)
+    shape = (40, 60) if ndim == 2 else (18, 16, 24)
+    nt = 120 if ndim == 2 else 50
+    v = 2000.0 + 500.0 * rng.random(shape)
+    h = 10.0
+    dt = fo.stable_dt(v.max(), h, ndim)
+    if ndim == 2:
+        src, rec = [(5, 10), (20, 30)], [(4, x) for x in range(3, 57, 5)] + [(39, 59), (0, 0)]
+    else:
+        src, rec = [(5, 6, 7), (10, 3, 20)], [(4, y, x) for y in (2, 9) for x in range(1, 23, 4)] + [(17, 15, 23), (0, 0, 0)]
+    w = rng.standard_normal((nt, len(src)))
+    d = rng.standard_normal((nt, len(rec)))
+    Lw = fo.Problem(v, h, dt, src, rec, nabs=6).forward(w)
+    LTd = fo.Problem(v, h, dt, rec, src, nabs=6).forward(d[::-1])[::-1]
+    lhs, rhs = float(np.sum(Lw * d)), float(np.sum(w * LTd))
+    assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
