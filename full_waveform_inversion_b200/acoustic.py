@@ -27,7 +27,6 @@ _lib.register({
     "fwi_fd2d_create": (c_int, [c_int, c_int, c_int, c_float, c_float, c_int, c_float, POINTER(c_void_p)]),
     "fwi_fd2d_destroy": (c_int, [c_void_p]),
     "fwi_fd2d_set_tile": (c_int, [c_void_p, c_int, c_int]),
-    "fwi_fd2d_set_stream": (c_int, [c_void_p, c_int, c_int]),
     "fwi_fd2d_set_graphs": (c_int, [c_void_p, c_int]),
     "fwi_fd2d_set_tb2": (c_int, [c_void_p, c_int]),
     "fwi_fd2d_set_memory_limit": (c_int, [c_void_p, c_uint64]),
@@ -49,6 +48,9 @@ _lib.register({
     "fwi_fd_slab_info": (c_int, [c_void_p, c_void_p, c_void_p]),
     "fwi_fd_slab_connect": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "fwi_fd_slab_error": (c_int, [c_void_p, POINTER(c_int)]),
+    "fwi_fd_slab_set_timeout": (c_int, [c_void_p, c_double]),
+    "fwi_fd_slab_clear_error": (c_int, [c_void_p]),
+    "fwi_fd_slab_connect_local": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "fwi_fd_misfit": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_double), c_void_p]),
     "fwi_fd_model_update": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_void_p]),
     "fwi_fd_absmax": (c_int, [c_void_p, c_int64, POINTER(c_float), c_void_p]),
@@ -85,7 +87,7 @@ class Propagator:
     """One GPU's propagator plan (wraps ``fwi_fd2d``; 2-D or 3-D by the length of `shape`): model, sponge,
     wavefields, TMA descriptors, cached CUDA graphs."""
 
-    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=None, tile=None, memory_limit=0, stream=None, graphs=True, tb2=None):
+    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=None, tile=None, memory_limit=0, graphs=True, tb2=None):
         self._lib = _lib.require_gpu()
         self.shape = tuple(int(n) for n in shape)
         self.ndim = len(self.shape)
@@ -103,8 +105,6 @@ class Propagator:
                                             float(alpha), ctypes.byref(self._h)))
         if tile is not None:
             check(self._lib.fwi_fd2d_set_tile(self._h, int(tile[0]), int(tile[1])))
-        if stream is not None:
-            check(self._lib.fwi_fd2d_set_stream(self._h, int(stream[0]), int(stream[1])))
         if tb2 is not None:
             check(self._lib.fwi_fd2d_set_tb2(self._h, int(tb2)))
         if memory_limit:
@@ -149,7 +149,7 @@ class Propagator:
             w = w[:, None].expand(-1, self.nsrc).contiguous()
         if w.shape[1] != self.nsrc:
             raise ValueError("wavelet has %d columns but the shot has %d sources" % (w.shape[1], self.nsrc))
-        return w
+        return w if w.is_contiguous() else w.contiguous()
 
     def forward(self, wavelet, out=None):
         """nt leapfrog steps from rest -> traces (nt, nrec) device tensor (fd_oracle.Problem.forward)."""
@@ -242,16 +242,19 @@ class SlabPropagator:
     """Large grids split into z slabs over the ranks of the default process group (BASELINE config 4).
 
     Every rank owns a contiguous range of z planes plus a 4-plane ghost zone towards each neighbour.
-    3-D (default, `p2p`): compute and halo exchange are ONE kernel - the neighbours' wavefield arenas are mapped with
-    CUDA IPC, the step kernel computes the owned planes, stores its 4 boundary planes straight into the neighbours'
-    ghost planes over NVLink and publishes a step id (system-scope release) that the neighbours' next launch
-    acquires; no collective call per step.  Fallback / 2-D (`p2p=False`): the ordinary step kernel runs on the local
-    grid and the boundary planes are exchanged with NCCL send/recv, the whole loop captured as a CUDA graph.
-    Either way the owned planes are bit-identical to a single-GPU run.  One `fwi_fd_step` per step."""
+    3-D (default, `p2p`): compute and halo exchange are ONE kernel.  The neighbours' wavefield arenas are mapped with
+    CUDA IPC; the step kernel computes the owned planes and stores its 4 boundary planes straight into the neighbours'
+    ghost planes over NVLink.  Both boundaries are computed in the first iterations of their CTAs (the last z chunk
+    marches downwards), so the transfer and the neighbours' wait hide behind the interior planes.  Step ids live in
+    device memory, so the whole forward / gradient time loop of a rank is one CUDA-graph replay of the plan's ordinary
+    `forward` / `gradient` (same checkpointing when the snapshots do not fit, per rank); no collective per step.
+    Fallback / 2-D (`p2p=False`): the ordinary step kernel runs on the local grid and the boundary planes are exchanged
+    with NCCL send/recv, the loop captured as a CUDA graph (every w_n held in HBM).
+    Either way the owned planes are bit-identical to a single-GPU run."""
 
     HALO = 4
 
-    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=None, use_graphs=True, p2p=None):
+    def __init__(self, shape, h, dt, nabs=20, alpha=0.3, device=None, use_graphs=True, p2p=None, memory_limit=0):
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("SlabPropagator needs an initialised torch.distributed process group")
@@ -269,16 +272,17 @@ class SlabPropagator:
         self.down = self.HALO if self.rank < self.world - 1 else 0
         self.local_shape = (self.n_own + self.up + self.down,) + self.shape[1:]
         device = torch.cuda.current_device() if device is None else device
-        self.prop = Propagator(self.local_shape, h, dt, nabs, alpha, device, graphs=False)
+        # 3-D slabs default to the fused mode (boundary planes pushed over NVLink peer memory by the step kernel
+        # itself); p2p=False forces the NCCL send/recv exchange, which is also the fallback if IPC mapping fails.
+        self.p2p = (p2p is None or bool(p2p)) and len(self.shape) == 3 and self.world > 1
+        self.prop = Propagator(self.local_shape, h, dt, nabs, alpha, device, graphs=bool(use_graphs and self.p2p),
+                               memory_limit=memory_limit)
         gz = sponge_profile(nz, nabs, alpha)[self.z0 - self.up: self.z0 + self.n_own + self.down]
         self.prop.set_profiles(gz=gz)
         self.fields = [self.prop.field_view(i) for i in range(8)]
         self.nsrc = self.nrec = 0
         self.use_graphs = use_graphs
         self._graphs = {}
-        # 3-D slabs default to the fused mode (boundary planes pushed over NVLink peer memory by the step kernel
-        # itself); p2p=False forces the NCCL send/recv exchange, which is also the fallback if IPC mapping fails.
-        self.p2p = (p2p is None or bool(p2p)) and len(self.shape) == 3 and self.world > 1
         if self.p2p:
             ok = torch.ones(1, device=self.prop.torch_device)
             try:
@@ -290,6 +294,11 @@ class SlabPropagator:
             self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)
             if ok.item() == 0:
                 raise RuntimeError("peer-memory slab mode could not be set up on every rank; pass p2p=False to use NCCL")
+
+    @property
+    def local_range(self):
+        """(lo, hi): the global z planes this rank keeps (owned + ghosts) - what `set_model(..., local=True)` expects."""
+        return self.z0 - self.up, self.z0 + self.n_own + self.down
 
     def _connect_peers(self):
         """Fused mode: map the neighbours' wavefield arenas (CUDA IPC over NVLink) so that the step kernel itself stores
@@ -318,16 +327,26 @@ class SlabPropagator:
                                       None if uh is None else ctypes.cast(uh, c_void_p), None if uo is None else ctypes.cast(uo, c_void_p),
                                       up_ghost_z,
                                       None if dh is None else ctypes.cast(dh, c_void_p), None if do is None else ctypes.cast(do, c_void_p)))
-        self.use_graphs = False          # step ids are kernel arguments: the loop is issued eagerly (no NCCL in it anyway)
         self.dist.barrier()
 
+    def set_timeout(self, milliseconds):
+        """Bound on a step kernel's wait for its neighbour (fused mode; default 2 s)."""
+        check(self.prop._lib.fwi_fd_slab_set_timeout(self.prop._h, float(milliseconds)))
+
     def check_peers(self):
-        """Raise if a launch timed out waiting for a neighbour (fused mode)."""
-        if self.p2p:
-            e = c_int(0)
-            check(self.prop._lib.fwi_fd_slab_error(self.prop._h, ctypes.byref(e)))
-            if e.value:
-                raise RuntimeError("slab halo exchange: a step kernel timed out waiting for its neighbour")
+        """Fused mode: raise ON EVERY RANK if any rank's launch timed out waiting for a neighbour (the kernels then
+        returned without computing, so results are invalid); the flag is cleared so the propagator can be reused."""
+        if not self.p2p:
+            return
+        e = c_int(0)
+        check(self.prop._lib.fwi_fd_slab_error(self.prop._h, ctypes.byref(e)))
+        flag = torch.tensor([float(e.value)], device=self.prop.torch_device)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX)
+        if flag.item():
+            check(self.prop._lib.fwi_fd_slab_clear_error(self.prop._h))
+            self.dist.barrier()
+            raise RuntimeError("slab halo exchange: a step kernel timed out waiting for its neighbour (rank %d saw it: %s); "
+                               "the results of this call are invalid" % (self.rank, bool(e.value)))
 
     def close(self):
         # captured graphs hold NCCL work: drop them (and drain the device) BEFORE the process group goes away,
@@ -335,16 +354,24 @@ class SlabPropagator:
         torch.cuda.synchronize()
         self._graphs = {}
         torch.cuda.synchronize()
+        if self.p2p:
+            self.dist.barrier()          # nobody unmaps an arena a neighbour's kernel may still be writing into
         self.prop.close()
 
     @property
     def own(self):
         return slice(self.up, self.up + self.n_own)
 
-    def set_model(self, v):
-        """v: the GLOBAL velocity grid (host or device); every rank keeps its slab (+ ghosts)."""
-        lo, hi = self.z0 - self.up, self.z0 + self.n_own + self.down
-        self.prop.set_model(v[lo:hi])
+    def set_model(self, v, local=False):
+        """v: the GLOBAL velocity grid (host or device), of which every rank keeps its slab (+ ghosts); or, with
+        `local=True`, just this rank's planes `local_range` - grids that need slabs do not fit one GPU or one host array."""
+        if local:
+            if tuple(v.shape) != self.local_shape:
+                raise ValueError("local model %s does not match this rank's slab %s" % (tuple(v.shape), self.local_shape))
+            self.prop.set_model(v)
+        else:
+            lo, hi = self.local_range
+            self.prop.set_model(v[lo:hi])
 
     def set_geometry(self, src, rec):
         ndim = len(self.shape)
@@ -363,9 +390,7 @@ class SlabPropagator:
         self._graphs = {}                               # captured loops hold the old list sizes
 
     def _exchange(self, idx):
-        """Refresh the ghost planes of wavefield buffer idx from the neighbours' boundary planes."""
-        if self.p2p:
-            return                        # the step kernel already pushed them over NVLink
+        """NCCL mode: refresh the ghost planes of wavefield buffer idx from the neighbours' boundary planes."""
         f, H, ops = self.fields[idx], self.HALO, []
         n = f.shape[0]
         P2P = self.dist.P2POp
@@ -381,20 +406,13 @@ class SlabPropagator:
         w = _dev_f32(wavelet, self.prop.torch_device)
         if w.ndim == 1:
             w = w[:, None].expand(-1, self.nsrc_global)
+        if self.p2p:
+            return w[:, torch.as_tensor(self.src_ids, device=w.device)].contiguous()          # (nt, 0) on a rank without sources
         return w[:, torch.as_tensor(self.src_ids, device=w.device)].contiguous() if len(self.src_ids) else \
             torch.zeros((w.shape[0], 1), dtype=torch.float32, device=w.device)
 
     def _loop(self, nt, mode, pair, inj, out, snap_offset, reverse):
-        if self.p2p:
-            # neighbours write into this GPU's ghost planes: nobody may still be pushing the previous loop's data when
-            # the fields are zeroed, and nobody may push new data before they are
-            torch.cuda.synchronize()
-            self.dist.barrier()
-            self.prop.reset(pair)
-            torch.cuda.synchronize()
-            self.dist.barrier()
-        else:
-            self.prop.reset(pair)
+        self.prop.reset(pair)
         cur = 0
         for k in range(nt):
             n = nt - 1 - k if reverse else k
@@ -405,7 +423,7 @@ class SlabPropagator:
             self._exchange(4 * pair + cur)
 
     def _run(self, nt, mode, pair, inj, out, snap_offset=0, reverse=False):
-        """nt steps + halo exchanges.  The whole loop (step kernels and NCCL send/recv) is captured once per
+        """NCCL mode: nt steps + halo exchanges.  The whole loop (step kernels and NCCL send/recv) is captured once per
         (nt, mode) into a CUDA graph over persistent staging buffers and replayed, which removes the ~0.4 ms of
         host + NCCL launch latency per step; falls back to eager stepping if capture is not possible."""
         if not self.use_graphs:
@@ -440,25 +458,36 @@ class SlabPropagator:
         self.dist.all_reduce(full)
         return full
 
-    def forward(self, wavelet):
-        """Traces (nt, nrec) of the whole survey on every rank."""
+    def forward(self, wavelet, gather=True):
+        """Traces (nt, nrec) of the whole survey on every rank (`gather=False`: this rank's receivers only)."""
         w = self._wavelet_local(wavelet)
         nt = w.shape[0]
-        local = torch.zeros((nt, len(self.rec_ids)), dtype=torch.float32, device=w.device)
-        self._run(nt, 0, 0, w, local)
-        return self._gather_traces(local, nt)
+        if self.p2p:
+            local = self.prop.forward(w)
+            self.check_peers()
+        else:
+            local = torch.zeros((nt, len(self.rec_ids)), dtype=torch.float32, device=w.device)
+            self._run(nt, 0, 0, w, local)
+        return self._gather_traces(local, nt) if gather else local
 
-    def gradient(self, wavelet, observed):
-        """(J, gradient of this rank's own planes (n_own, ...), traces) - every w_n of the slab is held in HBM."""
+    def gradient(self, wavelet, observed, gather=True):
+        """(J, gradient of this rank's own planes (n_own, ...), traces).  Fused mode: the plan's ordinary gradient on the
+        slab - w_n held in HBM, or checkpointed per rank when `memory_limit` / free memory says so."""
         w = self._wavelet_local(wavelet)
         nt = w.shape[0]
         dev = w.device
+        obs = _dev_f32(observed, dev)
+        mine = obs[:, torch.as_tensor(self.rec_ids, device=dev)].contiguous()       # gather = data movement only
+        if self.p2p:
+            Jl, grad, local = self.prop.gradient(w, mine, want_traces=True)
+            self.check_peers()
+            J = torch.tensor([Jl], dtype=torch.float64, device=dev)
+            self.dist.all_reduce(J)
+            return float(J.item()), grad[self.own], (self._gather_traces(local, nt) if gather else local)
         self.prop.reserve_snapshots(nt)
         local = torch.zeros((nt, max(1, len(self.rec_ids))), dtype=torch.float32, device=dev)[:, : len(self.rec_ids)].contiguous()
         self._run(nt, 1, 0, w, local)
-        obs = _dev_f32(observed, dev)
         if len(self.rec_ids):
-            mine = obs[:, torch.as_tensor(self.rec_ids, device=dev)].contiguous()       # gather = data movement only
             res = torch.empty_like(local)
             Jl = c_double(0.0)
             with torch.cuda.device(dev):
@@ -471,7 +500,7 @@ class SlabPropagator:
         self._run(nt, 2, 1, res, None, reverse=True)
         grad = torch.zeros(self.local_shape, dtype=torch.float32, device=dev)
         self.prop.finalize_gradient(grad)
-        return float(J.item()), grad[self.own], self._gather_traces(local, nt)
+        return float(J.item()), grad[self.own], (self._gather_traces(local, nt) if gather else local)
 
 
 # ------------------------------------------------------------------------------------------------ entry points
@@ -545,10 +574,10 @@ def gradient(v, h, dt, shots, wavelet, observed, nabs=20, alpha=0.3, device=None
             j, _, _ = prop.gradient(wavelet, obs, grad=grad)
             J += j
         if dist:
-            packed = torch.cat([grad.reshape(-1).double(), torch.tensor([J], dtype=torch.float64, device=grad.device)])
-            dist.all_reduce(packed)
-            grad = packed[:-1].float().reshape(grad.shape)
-            J = float(packed[-1].item())
+            dist.all_reduce(grad)                       # the one collective of an FWI gradient: fp32, in place over NCCL
+            Jt = torch.tensor([J], dtype=torch.float64, device=grad.device)
+            dist.all_reduce(Jt)                         # + the misfit (one float64 scalar)
+            J = float(Jt.item())
         return J, grad
     finally:
         if propagator is None:

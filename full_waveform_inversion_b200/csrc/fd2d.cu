@@ -24,7 +24,6 @@ namespace fwi {
 
 enum { STEP_FWD = 0, STEP_FWD_SAVE = 1, STEP_ADJ = 2, STEP_ADJ2 = 3 };   // ADJ2: image this step AND the previous one (deferred)
 }  // namespace fwi
-#include "fd2d_stream.cuh"
 #include "fd3d.cuh"
 #include "fd2d_tb2.cuh"
 namespace fwi {
@@ -328,17 +327,15 @@ struct fwi_fd2d {
     size_t peer_fld_off[2][8] = {};             // byte offsets of the neighbours' wavefield buffers in their arenas
     size_t peer_flags_off[2] = {0, 0};
     int peer_up_z = 0;
-    int* sync_area = nullptr;                   // [0..1] flags_local, [2] done counter, [3] error flag (inside the arena)
-    int step_base = 0;                          // monotonically increasing step ids across runs
-    int slab_wait = 0, slab_signal = 0;         // ids of the launch being issued
+    bool peer_ipc[2] = {false, false};          // opened with cudaIpcOpenMemHandle (else: another plan of this process)
+    int* sync_area = nullptr;                   // SlabSync words (fd3d.cuh) inside the arena; the step id lives there
+    int last_desc = 0;                          // the last z chunk marches downwards (slab with a lower neighbour)
+    long long slab_timeout_cycles = 4000000000LL;   // bounded spin on a neighbour's flag (~2 s; FWI_SLAB_TIMEOUT_MS)
+    bool peers() const { return peer_arena[0] || peer_arena[1]; }
     int bz = 32, nw = 4;              // tiled variant: tile rows / warps per CTA (tunable)
     int tiles_x = 0, tiles_z = 0;
-    int variant = 0;                  // 0 = one-tile-per-CTA kernel (default), 1 = persistent streaming kernel
-    int sm_count = 148, snw = 8, snc = 4;   // streaming variant: warps per CTA, pipeline slots
-    int nstrips = 0, W = 0;
-    int* d_u0 = nullptr;
-    std::vector<int> h_u0;
-    CUtensorMap tm_cur_s[8], tm_old_s[8], tm_m_s;
+    int variant = 0;                  // 0 = one-tile-per-CTA kernel, 2 = two-steps-per-pass kernel (temporal blocking)
+    int sm_count = 148;
     CUtensorMap tb_cur[8], tb_old[8], tb_m;     // temporally blocked kernel (variant 2)
     int cz = 32, tiles_x2 = 0, tiles_z2 = 0;
     float *m = nullptr, *vp = nullptr, *gx = nullptr, *gz = nullptr;
@@ -366,7 +363,12 @@ struct fwi_fd2d {
     bool defer_imaging = true;        // tile variant: image two adjoint steps per accumulator update
     int64_t launches = 0;
     cudaStream_t work = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_geom = nullptr;
+    bool geom_pending = false;        // set_geometry queued uploads on `work` that a caller-driven step has not yet waited for
+    // pinned host staging for the point lists: three slots used in turn, so set_geometry never waits for the shot that
+    // is still running (its uploads are queued behind that shot's graph) and never reads freed pageable memory
+    struct Stage { int* host = nullptr; size_t cap = 0, used = 0; cudaEvent_t done = nullptr; bool busy = false; } stage[3];
+    int stage_cur = 0;
     std::vector<GraphEntry> graphs;
     int rows() const { return nz * ny; }
     size_t plane() const { return (size_t)nz * ny * px; }
@@ -375,30 +377,6 @@ struct fwi_fd2d {
 static void drop_graphs(fwi_fd2d* p) {
     for (auto& g : p->graphs) cudaGraphExecDestroy(g.exec);
     p->graphs.clear();
-}
-
-static int make_stream_partition(fwi_fd2d* p) {
-    if (p->ny > 1) return FWI_OK;
-    p->nstrips = (p->nx + 127) / 128;
-    p->W = p->sm_count * p->snw;
-    const int64_t U = (int64_t)p->nstrips * p->nz;
-    p->h_u0.resize(p->W + 1);
-    for (int w = 0; w <= p->W; ++w) p->h_u0[w] = (int)(U * w / p->W);
-    if (p->d_u0) cudaFree(p->d_u0);
-    p->d_u0 = nullptr;
-    FWI_CUDA(cudaMalloc(&p->d_u0, (p->W + 1) * sizeof(int)));
-    FWI_CUDA(cudaMemcpy(p->d_u0, p->h_u0.data(), (p->W + 1) * sizeof(int), cudaMemcpyHostToDevice));
-    const uint64_t dims[2] = {(uint64_t)p->nx, (uint64_t)p->nz};
-    const uint64_t dims_p[2] = {(uint64_t)p->px, (uint64_t)p->nz};
-    const uint64_t strides[1] = {(uint64_t)p->px * sizeof(float)};
-    const uint32_t box_c[2] = {(uint32_t)kSCW, (uint32_t)kSR}, box_r[2] = {128u, (uint32_t)kSR};
-    for (int i = 0; i < 8; ++i) {
-        int rc = encode_tiled_f32(&p->tm_cur_s[i], p->fld[i], 2, dims, strides, box_c);
-        if (rc) return rc;
-        rc = encode_tiled_f32(&p->tm_old_s[i], p->fld[i], 2, dims_p, strides, box_r);
-        if (rc) return rc;
-    }
-    return encode_tiled_f32(&p->tm_m_s, p->m, 2, dims_p, strides, box_r);
 }
 
 static int make_tmaps3(fwi_fd2d* p) {
@@ -411,15 +389,21 @@ static int make_tmaps3(fwi_fd2d* p) {
         int best = 1;
         double best_cost = 1e300;
         const int nzo = (p->z_own1 > 0 ? p->z_own1 : p->nz) - p->z_own0;
-        for (int nzch = 1; nzch <= std::max(1, nzo / 8); ++nzch) {
+        // peer-memory slabs: with a lower neighbour the last chunk marches downwards, so that both boundaries are pushed
+        // early - that needs at least two chunks; and a 4-plane boundary must not straddle two chunks
+        const int min_ch = (p->peer_arena[1] && nzo >= 4 * kHalo) ? 2 : 1;
+        for (int nzch = min_ch; nzch <= std::max(min_ch, nzo / 8); ++nzch) {
             const int zc = (nzo + nzch - 1) / nzch;
             const int real = (nzo + zc - 1) / zc;
+            if (real < min_ch) continue;
+            if (p->peers() && nzo - (real - 1) * zc < kHalo) continue;
             const double waves = std::ceil((double)txy * real / p->sm_count);
             const double cost = waves * (zc + 2 * kHalo);
             if (cost < best_cost - 1e-9) { best_cost = cost; best = nzch; }
         }
         p->zchunk = (nzo + best - 1) / best;
         p->nzch = (nzo + p->zchunk - 1) / p->zchunk;
+        p->last_desc = (p->peer_arena[1] && p->nzch >= 2) ? 1 : 0;
     }
     for (int i = 0; i < 8; ++i) {
         const uint64_t dims[3] = {(uint64_t)p->nx, (uint64_t)p->ny, (uint64_t)p->nz};
@@ -467,13 +451,49 @@ static int make_tmaps(fwi_fd2d* p) {
 // bin that owns grid point (z, x): the CTA tile (tiled variant) or the warp whose row-unit range holds it
 static int owner_bin(const fwi_fd2d* p, int z, int y, int x) {
     if (p->ny > 1) return ((std::max(0, z - p->z_own0) / p->zchunk) * p->tiles_y + y / k3BY) * p->tiles_x + x / k3BX;
-    if (p->variant != 1) return (z / p->bz) * p->tiles_x + x / kBX;
-    const int u = (x / 128) * p->nz + z;
-    return (int)(std::upper_bound(p->h_u0.begin(), p->h_u0.end(), u) - p->h_u0.begin()) - 1;
+    return (z / p->bz) * p->tiles_x + x / kBX;
+}
+
+// ---- pinned staging of the point lists ---------------------------------------------------------------------------
+static int stage_begin(fwi_fd2d* p, size_t need_ints) {
+    p->stage_cur = (p->stage_cur + 1) % 3;
+    auto& sl = p->stage[p->stage_cur];
+    if (!sl.done) FWI_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    if (sl.busy) { FWI_CUDA(cudaEventSynchronize(sl.done)); sl.busy = false; }      // uploads of three set_geometry calls ago
+    if (sl.cap < need_ints) {
+        if (sl.host) cudaFreeHost(sl.host);
+        sl.host = nullptr; sl.cap = 0;
+        const size_t cap = need_ints + need_ints / 2 + 1024;
+        FWI_CUDA(cudaMallocHost(&sl.host, cap * sizeof(int)));
+        sl.cap = cap;
+    }
+    sl.used = 0;
+    return FWI_OK;
+}
+static int stage_upload(fwi_fd2d* p, int* dst_dev, const int* src, size_t n) {
+    auto& sl = p->stage[p->stage_cur];
+    if (sl.used + n > sl.cap) {          // (bound computed by set_geometry was too small: fall back to a synchronous copy)
+        FWI_CUDA(cudaStreamSynchronize(p->work));
+        FWI_CUDA(cudaMemcpy(dst_dev, src, n * sizeof(int), cudaMemcpyHostToDevice));
+        return FWI_OK;
+    }
+    int* h = sl.host + sl.used;
+    memcpy(h, src, n * sizeof(int));
+    sl.used += n;
+    FWI_CUDA(cudaMemcpyAsync(dst_dev, h, n * sizeof(int), cudaMemcpyHostToDevice, p->work));
+    return FWI_OK;
+}
+static int stage_end(fwi_fd2d* p) {
+    auto& sl = p->stage[p->stage_cur];
+    FWI_CUDA(cudaEventRecord(sl.done, p->work));
+    sl.busy = true;
+    FWI_CUDA(cudaEventRecord(p->ev_geom, p->work));
+    p->geom_pending = true;
+    return FWI_OK;
 }
 
 static int build_point_list(fwi_fd2d* p, PointList& pl, int n, const int* iz, const int* iy, const int* ix, const char* what) {
-    const int nbins = (p->ny > 1) ? p->tiles_x * p->tiles_y * p->nzch : ((p->variant != 1) ? p->tiles_x * p->tiles_z : p->W);
+    const int nbins = (p->ny > 1) ? p->tiles_x * p->tiles_y * p->nzch : p->tiles_x * p->tiles_z;
     std::vector<int> tile_ptr(nbins + 1, 0), off(std::max(n, 1)), id(std::max(n, 1));
     for (int i = 0; i < n; ++i) {
         const int yy = iy ? iy[i] : 0;
@@ -498,13 +518,10 @@ static int build_point_list(fwi_fd2d* p, PointList& pl, int n, const int* iz, co
         pl.cap = cap; pl.nbins = nbins;
     }
     // contents are rewritten in place on the work stream, ordered after the previous shot's graph
-    FWI_CUDA(cudaMemcpyAsync(pl.d_tile_ptr, tile_ptr.data(), (nbins + 1) * sizeof(int), cudaMemcpyHostToDevice, p->work));
-    FWI_CUDA(cudaMemcpyAsync(pl.d_off, off.data(), std::max(n, 1) * sizeof(int), cudaMemcpyHostToDevice, p->work));
-    FWI_CUDA(cudaMemcpyAsync(pl.d_id, id.data(), std::max(n, 1) * sizeof(int), cudaMemcpyHostToDevice, p->work));
-    // Pageable sources of <= 64 KB are staged by the driver before cudaMemcpyAsync returns, so the host vectors may go
-    // out of scope without waiting for the previous shot's graph (the CPU can then enqueue the next shot while the GPU
-    // still runs this one); larger lists must wait.
-    if ((size_t)std::max(nbins + 1, n) * sizeof(int) > 48 * 1024) FWI_CUDA(cudaStreamSynchronize(p->work));
+    int rc = stage_upload(p, pl.d_tile_ptr, tile_ptr.data(), nbins + 1);
+    if (!rc) rc = stage_upload(p, pl.d_off, off.data(), std::max(n, 1));
+    if (!rc) rc = stage_upload(p, pl.d_id, id.data(), std::max(n, 1));
+    if (rc) return rc;
     pl.n = n;
     return FWI_OK;
 }
@@ -536,10 +553,10 @@ static int build_point_list_tb2(fwi_fd2d* p, PointList& pl, int n, const int* iz
         FWI_CUDA(cudaMalloc(&pl.d_id, cap * sizeof(int)));
         pl.cap = cap; pl.nbins = nbins;
     }
-    FWI_CUDA(cudaMemcpyAsync(pl.d_tile_ptr, tile_ptr.data(), (nbins + 1) * sizeof(int), cudaMemcpyHostToDevice, p->work));
-    FWI_CUDA(cudaMemcpyAsync(pl.d_off, off.data(), tot * sizeof(int), cudaMemcpyHostToDevice, p->work));
-    FWI_CUDA(cudaMemcpyAsync(pl.d_id, id.data(), tot * sizeof(int), cudaMemcpyHostToDevice, p->work));
-    if ((size_t)std::max(nbins + 1, tot) * sizeof(int) > 48 * 1024) FWI_CUDA(cudaStreamSynchronize(p->work));
+    int rc = stage_upload(p, pl.d_tile_ptr, tile_ptr.data(), nbins + 1);
+    if (!rc) rc = stage_upload(p, pl.d_off, off.data(), tot);
+    if (!rc) rc = stage_upload(p, pl.d_id, id.data(), tot);
+    if (rc) return rc;
     pl.n = tile_ptr[nbins];
     return FWI_OK;
 }
@@ -572,33 +589,6 @@ static int launch_step_cfg(fwi_fd2d* p, int mode, int cur, float* oldnew, const 
     return FWI_OK;
 }
 
-template <int NW, int NC>
-static int stream_attrs() {
-    const size_t smem = (size_t)NW * NC * (kStageBytes + 8);
-    FWI_CUDA(cudaFuncSetAttribute(fd2d_stream_kernel<NW, NC, STEP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FWI_CUDA(cudaFuncSetAttribute(fd2d_stream_kernel<NW, NC, STEP_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FWI_CUDA(cudaFuncSetAttribute(fd2d_stream_kernel<NW, NC, STEP_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return FWI_OK;
-}
-
-template <int NW, int NC>
-static int launch_stream_cfg(fwi_fd2d* p, int mode, int cur, int oldidx, const PointList* inj, const float* inj_vals,
-                             const PointList* rec, float* rec_out, float* snap, cudaStream_t st) {
-    Stream2DArgs a{};
-    a.oldnew = p->fld[oldidx]; a.gx = p->gx; a.gz = p->gz; a.m = p->m; a.snap = snap; a.acc = p->acc;
-    a.nx = p->nx; a.nz = p->nz; a.px = p->px; a.nstrips = p->nstrips; a.warp_u0 = p->d_u0;
-    a.inj = (inj && inj->n) ? inj->dev() : PointListDev{nullptr, nullptr, nullptr};
-    a.inj_vals = inj_vals;
-    a.rec = (rec && rec->n) ? rec->dev() : PointListDev{nullptr, nullptr, nullptr};
-    a.rec_out = rec_out;
-    const size_t smem = (size_t)NW * NC * (kStageBytes + 8);
-    const dim3 grid(p->sm_count), block(NW * 32);
-    if (mode == STEP_FWD) fd2d_stream_kernel<NW, NC, STEP_FWD><<<grid, block, smem, st>>>(p->tm_cur_s[cur], p->tm_old_s[oldidx], p->tm_m_s, a);
-    else if (mode == STEP_FWD_SAVE) fd2d_stream_kernel<NW, NC, STEP_FWD_SAVE><<<grid, block, smem, st>>>(p->tm_cur_s[cur], p->tm_old_s[oldidx], p->tm_m_s, a);
-    else fd2d_stream_kernel<NW, NC, STEP_ADJ><<<grid, block, smem, st>>>(p->tm_cur_s[cur], p->tm_old_s[oldidx], p->tm_m_s, a);
-    return FWI_OK;
-}
-
 static int launch_step3(fwi_fd2d* p, int mode, int cur, float* oldnew, const PointList* inj, const float* inj_vals,
                         const PointList* rec, float* rec_out, float* snap, cudaStream_t st, const float* snap_prev) {
     Step3DArgs a{};
@@ -609,21 +599,19 @@ static int launch_step3(fwi_fd2d* p, int mode, int cur, float* oldnew, const Poi
     a.rec = (rec && rec->n) ? rec->dev() : PointListDev{nullptr, nullptr, nullptr};
     a.rec_out = rec_out;
     a.z_own0 = p->z_own0; a.z_own1 = p->z_own1 > 0 ? p->z_own1 : p->nz;
-    {
-        int oi_ = -1;
-        for (int i = 0; i < 8; ++i) if (p->fld[i] == oldnew) oi_ = i;
-        a.peer_up = p->peer_arena[0] ? (float*)((char*)p->peer_arena[0] + p->peer_fld_off[0][oi_]) : nullptr;
-        a.peer_dn = p->peer_arena[1] ? (float*)((char*)p->peer_arena[1] + p->peer_fld_off[1][oi_]) : nullptr;
-        a.peer_up_z = p->peer_up_z;
-        a.flags_local = p->sync_area; a.done_counter = (unsigned int*)(p->sync_area + 2); a.error_flag = p->sync_area + 3;
-        a.flag_peer_up = p->peer_arena[0] ? (int*)((char*)p->peer_arena[0] + p->peer_flags_off[0]) + 1 : nullptr;   // I am its lower neighbour
-        a.flag_peer_dn = p->peer_arena[1] ? (int*)((char*)p->peer_arena[1] + p->peer_flags_off[1]) + 0 : nullptr;   // I am its upper neighbour
-        a.wait_id = p->slab_wait; a.signal_id = p->slab_signal;
-    }
-    const dim3 grid(p->tiles_x, p->tiles_y, p->nzch), block((k3CW + k3Prod) * 32);
-    const size_t smem = ((size_t)k3NP * k3PlaneFloats + (size_t)k3NO * 2 * k3OmFloats) * sizeof(float);
     int oi = -1;
     for (int i = 0; i < 8; ++i) if (p->fld[i] == oldnew) oi = i;
+    FWI_REQUIRE(oi >= 0, "fd3d: output buffer is not one of the plan's wavefields");
+    a.last_desc = p->last_desc;
+    a.peer_up = p->peer_arena[0] ? (float*)((char*)p->peer_arena[0] + p->peer_fld_off[0][oi]) : nullptr;
+    a.peer_dn = p->peer_arena[1] ? (float*)((char*)p->peer_arena[1] + p->peer_fld_off[1][oi]) : nullptr;
+    a.peer_up_z = p->peer_up_z;
+    a.sync = p->sync_area;
+    a.flag_peer_up = p->peer_arena[0] ? (int*)((char*)p->peer_arena[0] + p->peer_flags_off[0]) + kSyncFlagDn : nullptr;   // I am its lower neighbour
+    a.flag_peer_dn = p->peer_arena[1] ? (int*)((char*)p->peer_arena[1] + p->peer_flags_off[1]) + kSyncFlagUp : nullptr;   // I am its upper neighbour
+    a.timeout_cycles = p->slab_timeout_cycles;
+    const dim3 grid(p->tiles_x, p->tiles_y, p->nzch), block((k3CW + k3Prod) * 32);
+    const size_t smem = ((size_t)k3NP * k3PlaneFloats + (size_t)k3NO * 2 * k3OmFloats) * sizeof(float);
     // (programmatic dependent launch was measured on this kernel too: 2 % at 128^3, nothing from 256^3 up - not used)
     if (mode == STEP_FWD) fd3d_step_kernel<STEP_FWD><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
     else if (mode == STEP_FWD_SAVE) fd3d_step_kernel<STEP_FWD_SAVE><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
@@ -636,19 +624,8 @@ static int launch_step(fwi_fd2d* p, int mode, int cur, float* oldnew, const Poin
                        const PointList* rec, float* rec_out, float* snap, cudaStream_t st, const float* snap_prev = nullptr) {
     p->launches++;
     if (p->ny > 1) return launch_step3(p, mode, cur, oldnew, inj, inj_vals, rec, rec_out, snap, st, snap_prev);
-    if (p->variant == 1) {
-        int oldidx = -1;
-        for (int i = 0; i < 8; ++i) if (p->fld[i] == oldnew) oldidx = i;
-        if (p->snw == 8 && p->snc == 4) return launch_stream_cfg<8, 4>(p, mode, cur, oldidx, inj, inj_vals, rec, rec_out, snap, st);
-        if (p->snw == 4 && p->snc == 8) return launch_stream_cfg<4, 8>(p, mode, cur, oldidx, inj, inj_vals, rec, rec_out, snap, st);
-        if (p->snw == 6 && p->snc == 5) return launch_stream_cfg<6, 5>(p, mode, cur, oldidx, inj, inj_vals, rec, rec_out, snap, st);
-        if (p->snw == 8 && p->snc == 3) return launch_stream_cfg<8, 3>(p, mode, cur, oldidx, inj, inj_vals, rec, rec_out, snap, st);
-        if (p->snw == 12 && p->snc == 3) return launch_stream_cfg<12, 3>(p, mode, cur, oldidx, inj, inj_vals, rec, rec_out, snap, st);
-        set_error("fd2d: unsupported streaming configuration nw=%d nc=%d", p->snw, p->snc);
-        return FWI_EINVAL;
-    }
 #define CFG(BZV, NWV) if (p->bz == BZV && p->nw == NWV) return launch_step_cfg<BZV, NWV>(p, mode, cur, oldnew, inj, inj_vals, rec, rec_out, snap, st, snap_prev)
-    CFG(16, 2); CFG(32, 4); CFG(32, 8); CFG(16, 4); CFG(64, 8); CFG(64, 4); CFG(24, 4); CFG(24, 2); CFG(24, 3); CFG(40, 4); CFG(48, 4);
+    CFG(32, 4); CFG(64, 8); CFG(16, 2);      // the sweep's winner (default), and one taller / one flatter tile for tests
 #undef CFG
     set_error("fd2d: unsupported tile configuration bz=%d nw=%d", p->bz, p->nw);
     return FWI_EINVAL;
@@ -721,7 +698,7 @@ static int launch_tb2(fwi_fd2d* p, int mode, const State& s, int jc, int jd, con
                       cudaStream_t st) {
     p->launches++;
 #define TB(CZV) if (p->cz == CZV) return launch_tb2_cfg<CZV, 8>(p, mode, s, jc, jd, inj_ext, inj_own, inj1, inj2, rec, rec1, rec2, snap1, snap2, st)
-    TB(32); TB(24); TB(16); TB(56);
+    TB(32); TB(24); TB(16);
 #undef TB
     set_error("fd2d: unsupported temporal-blocking tile cz=%d", p->cz);
     return FWI_EINVAL;
@@ -798,11 +775,45 @@ static int run_adjoint(fwi_fd2d* p, const float* resid, int n0, int n1, size_t s
     return FWI_OK;
 }
 
+// ---- peer-memory slabs: what may be overwritten when ---------------------------------------------------------------
+// A neighbour stores its boundary planes of launch k into THIS GPU's ghost planes of the buffer launch k writes.  Before a
+// run (or a checkpointed segment) rewrites wavefields, a one-thread kernel waits until the neighbours have pushed
+// everything up to the current step id, so no late push of the previous sweep lands on freshly written planes; and the
+// ghost planes of the buffer that holds u_{n-1} are never written locally, because the neighbours' FIRST launch of the
+// new sweep pushes into exactly those planes and may run ahead of this GPU's memset / restore.
+static int slab_fence(fwi_fd2d* p, cudaStream_t st) {
+    if (!p->peers()) return FWI_OK;
+    fd3d_slab_sync_kernel<<<1, 32, 0, st>>>(p->sync_area, p->peer_arena[0] != nullptr, p->peer_arena[1] != nullptr, p->slab_timeout_cycles);
+    FWI_CUDA(cudaGetLastError());
+    return FWI_OK;
+}
+static void own_range(const fwi_fd2d* p, size_t& off, size_t& n) {      // floats of the planes a rank may write itself
+    if (p->peers()) { off = (size_t)p->z_own0 * p->ny * p->px; n = (size_t)(p->z_own1 - p->z_own0) * p->ny * p->px; }
+    else { off = 0; n = p->plane(); }
+}
+static int zero_state(fwi_fd2d* p, int cur, int old, cudaStream_t st) {
+    int rc = slab_fence(p, st);
+    if (rc) return rc;
+    size_t off, n;
+    own_range(p, off, n);
+    FWI_CUDA(cudaMemsetAsync(p->fld[cur], 0, p->plane() * sizeof(float), st));
+    FWI_CUDA(cudaMemsetAsync(p->fld[old] + off, 0, n * sizeof(float), st));
+    return FWI_OK;
+}
+static int restore_state(fwi_fd2d* p, const State& c, const float* ck_cur, const float* ck_old, cudaStream_t st) {
+    int rc = slab_fence(p, st);
+    if (rc) return rc;
+    size_t off, n;
+    own_range(p, off, n);
+    FWI_CUDA(cudaMemcpyAsync(p->fld[c.c], ck_cur, p->plane() * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    FWI_CUDA(cudaMemcpyAsync(p->fld[c.o] + off, ck_old + off, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return FWI_OK;
+}
+
 // The forward pass as a sequence of stream operations on `st` (captured into a graph or run directly).
 static int record_forward(fwi_fd2d* p, int nt, cudaStream_t st) {
-    const size_t pl = p->plane();
-    FWI_CUDA(cudaMemsetAsync(p->fld[0], 0, pl * sizeof(float), st));
-    FWI_CUDA(cudaMemsetAsync(p->fld[1], 0, pl * sizeof(float), st));
+    int rc = zero_state(p, 0, 1, st);
+    if (rc) return rc;
     State s{0, 1};
     return run_forward(p, p->wav, 0, nt, p->nrec ? p->syn : nullptr, false, 0, s, st);
 }
@@ -812,29 +823,30 @@ static int record_forward(fwi_fd2d* p, int nt, cudaStream_t st) {
 static int record_gradient(fwi_fd2d* p, int nt, int seg, int nseg, cudaStream_t st) {
     const size_t pl = p->plane();
     const size_t ntr = (size_t)nt * p->nrec;
-    FWI_CUDA(cudaMemsetAsync(p->fld[0], 0, pl * sizeof(float), st));
-    FWI_CUDA(cudaMemsetAsync(p->fld[1], 0, pl * sizeof(float), st));
-    int rc;
+    int rc = zero_state(p, 0, 1, st);
+    if (rc) return rc;
     State fs{0, 1};
     std::vector<State> seg_state(nseg, fs);
     if (nseg == 1) {
-        rc = run_forward(p, p->wav, 0, nt, p->syn, true, 0, fs, st);
+        rc = run_forward(p, p->wav, 0, nt, p->nrec ? p->syn : nullptr, true, 0, fs, st);
         if (rc) return rc;
     } else {
         for (int s = 0; s < nseg; ++s) {
+            if ((rc = slab_fence(p, st))) return rc;       // the ghost planes of u_n must have arrived before they are saved
             FWI_CUDA(cudaMemcpyAsync(p->ckpt + (size_t)(2 * s) * pl, p->fld[fs.c], pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
             FWI_CUDA(cudaMemcpyAsync(p->ckpt + (size_t)(2 * s + 1) * pl, p->fld[fs.o], pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
             seg_state[s] = fs;
-            rc = run_forward(p, p->wav, s * seg, std::min(nt, (s + 1) * seg), p->syn, false, 0, fs, st);
+            rc = run_forward(p, p->wav, s * seg, std::min(nt, (s + 1) * seg), p->nrec ? p->syn : nullptr, false, 0, fs, st);
             if (rc) return rc;
         }
     }
     FWI_CUDA(cudaMemsetAsync(p->d_J, 0, sizeof(double), st));
-    fd_residual_kernel<<<(unsigned)std::min<size_t>(1024, (ntr + 255) / 256), 256, 0, st>>>(p->syn, p->obs, (int64_t)ntr, p->resid, p->d_J);
-    FWI_CUDA(cudaGetLastError());
-    p->launches += 1;
-    FWI_CUDA(cudaMemsetAsync(p->fld[4], 0, pl * sizeof(float), st));
-    FWI_CUDA(cudaMemsetAsync(p->fld[5], 0, pl * sizeof(float), st));
+    if (ntr) {
+        fd_residual_kernel<<<(unsigned)std::min<size_t>(1024, (ntr + 255) / 256), 256, 0, st>>>(p->syn, p->obs, (int64_t)ntr, p->resid, p->d_J);
+        FWI_CUDA(cudaGetLastError());
+        p->launches += 1;
+    }
+    if ((rc = zero_state(p, 4, 5, st))) return rc;
     FWI_CUDA(cudaMemsetAsync(p->acc, 0, pl * sizeof(float), st));
     State as{4, 5};
     if (nseg == 1) {
@@ -844,8 +856,7 @@ static int record_gradient(fwi_fd2d* p, int nt, int seg, int nseg, cudaStream_t 
         for (int s = nseg - 1; s >= 0; --s) {
             const int n0 = s * seg, n1 = std::min(nt, (s + 1) * seg);
             State c = seg_state[s];
-            FWI_CUDA(cudaMemcpyAsync(p->fld[c.c], p->ckpt + (size_t)(2 * s) * pl, pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            FWI_CUDA(cudaMemcpyAsync(p->fld[c.o], p->ckpt + (size_t)(2 * s + 1) * pl, pl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            if ((rc = restore_state(p, c, p->ckpt + (size_t)(2 * s) * pl, p->ckpt + (size_t)(2 * s + 1) * pl, st))) return rc;
             rc = run_forward(p, p->wav, n0, n1, nullptr, true, n0, c, st);     // recompute w_n for this segment
             if (rc) return rc;
             rc = run_adjoint(p, p->resid, n0, n1, n0, as, st);
@@ -928,6 +939,7 @@ static int init_plan(fwi_fd2d* p, int device, int nz, int ny, int nx, float h, f
     FWI_CUDA(cudaStreamCreateWithFlags(&p->work, cudaStreamNonBlocking));
     FWI_CUDA(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
     FWI_CUDA(cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming));
+    FWI_CUDA(cudaEventCreateWithFlags(&p->ev_geom, cudaEventDisableTiming));
     // one arena for everything the step kernels re-read every step, hottest first, so that a single L2
     // access-policy window can keep it resident while the snapshots stream past:
     //   [m, acc, fld0, fld1, fld4, fld5 | fld2, fld3, fld6, fld7, vp]
@@ -985,10 +997,7 @@ static int init_plan(fwi_fd2d* p, int device, int nz, int ny, int nx, float h, f
     cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
     int rc = make_tmaps(p);
     if (rc) return rc;
-    rc = make_stream_partition(p);
-    if (rc) return rc;
-    if ((rc = stream_attrs<8, 4>()) || (rc = stream_attrs<4, 8>()) || (rc = stream_attrs<6, 5>()) || (rc = stream_attrs<8, 3>()) || (rc = stream_attrs<12, 3>())) return rc;
-    if ((rc = tb2_attrs<32, 8>()) || (rc = tb2_attrs<24, 8>()) || (rc = tb2_attrs<16, 8>()) || (rc = tb2_attrs<56, 8>())) return rc;
+    if ((rc = tb2_attrs<32, 8>()) || (rc = tb2_attrs<24, 8>()) || (rc = tb2_attrs<16, 8>())) return rc;
     const int smem3 = (k3NP * k3PlaneFloats + k3NO * 2 * k3OmFloats) * (int)sizeof(float);
     FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
@@ -1004,7 +1013,7 @@ int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, flo
     //   250x3000 12.8 vs 7.8 | 500x3000 14.6 vs 11.5 | 1000x3000 18.0 vs 19.6 | 2000x3000 41.9 vs 42.7 | 3000x3000 79.7 vs 60.4
     // Small grids are launch-bound (half the launches wins), grids whose fields leave the L2 are HBM-bound (12.7 instead
     // of 17 B per step wins); in between the one-step tile kernel streams from L2 faster than tb2 can compute.
-    // fwi_fd2d_set_tile / set_stream / set_tb2 override this.
+    // fwi_fd2d_set_tile / set_tb2 override this.
     const char* e = getenv("FWI_FD2D_VARIANT");
     const bool force_tile = e && !strcmp(e, "tile");
     const double pts = (double)nz * nx;
@@ -1035,32 +1044,19 @@ int fwi_fd2d_destroy(fwi_fd2d* p) {
     if (p->wav) cudaFree(p->wav);
     p->src.release(); p->rec.release();
     p->src_ext2.release(); p->src_own2.release(); p->rec_ext2.release(); p->rec_own2.release();
-    for (int s = 0; s < 2; ++s) if (p->peer_arena[s]) cudaIpcCloseMemHandle(p->peer_arena[s]);
-    if (p->d_u0) cudaFree(p->d_u0);
+    for (int s = 0; s < 2; ++s) if (p->peer_arena[s] && p->peer_ipc[s]) cudaIpcCloseMemHandle(p->peer_arena[s]);
     if (p->ev_in) cudaEventDestroy(p->ev_in);
     if (p->ev_out) cudaEventDestroy(p->ev_out);
+    if (p->ev_geom) cudaEventDestroy(p->ev_geom);
+    for (auto& sl : p->stage) { if (sl.host) cudaFreeHost(sl.host); if (sl.done) cudaEventDestroy(sl.done); }
     if (p->work) cudaStreamDestroy(p->work);
     delete p;
     return FWI_OK;
 }
 
-int fwi_fd2d_set_stream(fwi_fd2d* p, int nw, int nc) {
-    FWI_REQUIRE(p, "fwi_fd2d_set_stream: NULL plan");
-    const bool ok = (nw == 8 && nc == 4) || (nw == 4 && nc == 8) || (nw == 6 && nc == 5) || (nw == 8 && nc == 3) || (nw == 12 && nc == 3);
-    FWI_REQUIRE(ok, "fwi_fd2d_set_stream: unsupported (nw=%d, nc=%d)", nw, nc);
-    FWI_REQUIRE(p->ny == 1, "fwi_fd2d_set_stream: 2-D plans only");
-    DeviceGuard g(p->device);
-    FWI_CUDA(cudaStreamSynchronize(p->work));
-    drop_graphs(p);
-    p->variant = 1; p->snw = nw; p->snc = nc;
-    p->src.release(); p->rec.release(); p->nsrc = p->nrec = 0;
-    return make_stream_partition(p);
-}
-
 int fwi_fd2d_set_tile(fwi_fd2d* p, int bz, int nw) {
     FWI_REQUIRE(p, "fwi_fd2d_set_tile: NULL plan");
-    const bool ok = (bz == 32 && (nw == 4 || nw == 8)) || (bz == 16 && (nw == 4 || nw == 2)) || (bz == 64 && (nw == 8 || nw == 4)) ||
-                    (bz == 24 && (nw == 4 || nw == 2 || nw == 3)) || (bz == 40 && nw == 4) || (bz == 48 && nw == 4);
+    const bool ok = (bz == 32 && nw == 4) || (bz == 64 && nw == 8) || (bz == 16 && nw == 2);
     FWI_REQUIRE(ok, "fwi_fd2d_set_tile: unsupported (bz=%d, nw=%d)", bz, nw);
     FWI_REQUIRE(p->ny == 1, "fwi_fd2d_set_tile: 2-D plans only");
     DeviceGuard g(p->device);
@@ -1074,7 +1070,7 @@ int fwi_fd2d_set_tile(fwi_fd2d* p, int bz, int nw) {
 
 int fwi_fd2d_set_tb2(fwi_fd2d* p, int cz) {
     FWI_REQUIRE(p, "fwi_fd2d_set_tb2: NULL plan");
-    FWI_REQUIRE(cz == 16 || cz == 24 || cz == 32 || cz == 56, "fwi_fd2d_set_tb2: unsupported core rows %d (16, 24, 32, 56)", cz);
+    FWI_REQUIRE(cz == 16 || cz == 24 || cz == 32, "fwi_fd2d_set_tb2: unsupported core rows %d (16, 24, 32)", cz);
     FWI_REQUIRE(p->ny == 1, "fwi_fd2d_set_tb2: 2-D plans only");
     DeviceGuard g(p->device);
     FWI_CUDA(cudaStreamSynchronize(p->work));
@@ -1117,7 +1113,10 @@ static int set_geometry(fwi_fd2d* p, int nsrc, const int* src_z, const int* src_
     FWI_REQUIRE(nsrc >= 0 && nrec >= 0 && (nsrc == 0 || (src_z && src_x)) && (nrec == 0 || (rec_z && rec_x)), "fwi_fd_set_geometry: bad arguments");
     DeviceGuard g(p->device);
     if (nsrc != p->nsrc || nrec != p->nrec) drop_graphs(p);
-    int rc = build_point_list(p, p->src, nsrc, src_z, src_y, src_x, "source");
+    const size_t bins = (size_t)std::max({p->tiles_x * p->tiles_y * p->nzch, p->tiles_x * p->tiles_z, p->tiles_x2 * p->tiles_z2}) + 1;
+    int rc = stage_begin(p, 6 * bins + 2 * 10 * ((size_t)nsrc + nrec + 16));      // 2 + 4 lists; a tb2 point sits in <= 4 tiles
+    if (rc) return rc;
+    rc = build_point_list(p, p->src, nsrc, src_z, src_y, src_x, "source");
     if (rc) return rc;
     rc = build_point_list(p, p->rec, nrec, rec_z, rec_y, rec_x, "receiver");
     if (rc) return rc;
@@ -1128,7 +1127,7 @@ static int set_geometry(fwi_fd2d* p, int nsrc, const int* src_z, const int* src_
         if ((rc = build_point_list_tb2(p, p->rec_own2, nrec, rec_z, rec_x, false))) return rc;
     }
     p->nsrc = nsrc; p->nrec = nrec;
-    return FWI_OK;
+    return stage_end(p);
 }
 
 int fwi_fd2d_set_geometry(fwi_fd2d* p, int nsrc, const int* src_z, const int* src_x, int nrec, const int* rec_z,
@@ -1178,8 +1177,8 @@ int fwi_fd2d_wavefield(fwi_fd2d* p, int which, float* out_dev, void* stream) {
 int fwi_fd2d_gradient(fwi_fd2d* p, const float* wavelet_dev, const float* obs_dev, int nt, float* grad_dev,
                       float* traces_dev, double* misfit_host, void* stream) {
     FWI_REQUIRE(p && p->model_set, "fwi_fd2d_gradient: set the model first");
-    FWI_REQUIRE(wavelet_dev && obs_dev && grad_dev && nt >= 1, "fwi_fd2d_gradient: NULL argument or nt < 1");
-    FWI_REQUIRE(p->nsrc >= 1 && p->nrec >= 1, "fwi_fd2d_gradient: geometry needs at least one source and one receiver");
+    FWI_REQUIRE((wavelet_dev || p->nsrc == 0) && (obs_dev || p->nrec == 0) && grad_dev && nt >= 1, "fwi_fd2d_gradient: NULL argument or nt < 1");
+    FWI_REQUIRE((p->nsrc >= 1 && p->nrec >= 1) || p->z_own1 > 0, "fwi_fd2d_gradient: geometry needs at least one source and one receiver");
     DeviceGuard g(p->device);
     cudaStream_t user = (cudaStream_t)stream;
     const size_t pl = p->plane();
@@ -1215,8 +1214,8 @@ int fwi_fd2d_gradient(fwi_fd2d* p, const float* wavelet_dev, const float* obs_de
     p->split_nt = nt; p->split_limit = p->mem_limit; p->split_seg = seg; p->split_nseg = nseg;      // buffers exist now
 
     if ((rc = enter(p, user))) return rc;
-    FWI_CUDA(cudaMemcpyAsync(p->wav, wavelet_dev, (size_t)nt * p->nsrc * sizeof(float), cudaMemcpyDeviceToDevice, p->work));
-    FWI_CUDA(cudaMemcpyAsync(p->obs, obs_dev, ntr * sizeof(float), cudaMemcpyDeviceToDevice, p->work));
+    if (nt * p->nsrc) FWI_CUDA(cudaMemcpyAsync(p->wav, wavelet_dev, (size_t)nt * p->nsrc * sizeof(float), cudaMemcpyDeviceToDevice, p->work));
+    if (ntr) FWI_CUDA(cudaMemcpyAsync(p->obs, obs_dev, ntr * sizeof(float), cudaMemcpyDeviceToDevice, p->work));
     rc = run_cached(p, 1, nt, seg, nseg, [&](cudaStream_t st) { return record_gradient(p, nt, seg, nseg, st); });
     if (rc) return rc;
     { State fs = advance_state(p, State{0, 1}, 0, nt); p->fwd_c = fs.c; p->fwd_o = fs.o; }
@@ -1224,7 +1223,7 @@ int fwi_fd2d_gradient(fwi_fd2d* p, const float* wavelet_dev, const float* obs_de
     fd_grad_finalize_kernel<<<grid, 128, 0, p->work>>>(p->acc, p->vp, p->rows(), p->nx, p->px, grad_dev);
     FWI_CUDA(cudaGetLastError());
     p->launches += 1;
-    if (traces_dev) FWI_CUDA(cudaMemcpyAsync(traces_dev, p->syn, ntr * sizeof(float), cudaMemcpyDeviceToDevice, p->work));
+    if (traces_dev && ntr) FWI_CUDA(cudaMemcpyAsync(traces_dev, p->syn, ntr * sizeof(float), cudaMemcpyDeviceToDevice, p->work));
     if (misfit_host) FWI_CUDA(cudaMemcpyAsync(misfit_host, p->d_J, sizeof(double), cudaMemcpyDeviceToHost, p->work));
     if ((rc = leave(p, user))) return rc;
     if (misfit_host) FWI_CUDA(cudaStreamSynchronize(p->work));
@@ -1273,14 +1272,11 @@ int fwi_fd_reset(fwi_fd2d* p, int pair, void* stream) {
 // rec_out_dev: this step's trace row (modes 0/1, nullable).
 int fwi_fd_step(fwi_fd2d* p, int mode, int cur, const float* inj_vals_dev, float* rec_out_dev, int64_t snap_index, void* stream) {
     FWI_REQUIRE(p && p->model_set, "fwi_fd_step: set the model first");
-    if (p->peer_arena[0] || p->peer_arena[1]) {      // peer-memory slab mode: step ids order the launches across GPUs
-        p->slab_wait = p->step_base;
-        p->slab_signal = ++p->step_base;
-    }
     FWI_REQUIRE(mode >= 0 && mode <= 2 && (cur == 0 || cur == 1), "fwi_fd_step: bad mode / cur");
     p->pdl_chain = false;             // caller-driven loop: other kernels (halo exchange, resets) sit between the steps
     FWI_REQUIRE(mode == 0 || (snap_index >= 0 && (size_t)(snap_index + 1) * p->plane() <= p->snap_steps), "fwi_fd_step: snapshot %lld not reserved", (long long)snap_index);
     DeviceGuard g(p->device);
+    if (p->geom_pending) { FWI_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, p->ev_geom, 0)); p->geom_pending = false; }
     const int base = (mode == STEP_ADJ) ? 4 : 0;
     float* snap = (mode == 0) ? nullptr : p->snap + (size_t)snap_index * p->plane();
     int rc = launch_step(p, mode, base + cur, p->fld[base + (cur ^ 1)], mode == STEP_ADJ ? &p->rec : &p->src, inj_vals_dev,
@@ -1304,6 +1300,13 @@ int fwi_fd_slab_info(fwi_fd2d* p, void* ipc_handle_out /*64 bytes*/, uint64_t* o
     return FWI_OK;
 }
 
+static int slab_finish_connect(fwi_fd2d* p, int z_own0, int z_own1, int up_ghost_z) {
+    p->z_own0 = z_own0; p->z_own1 = z_own1; p->peer_up_z = up_ghost_z;
+    if (const char* e = getenv("FWI_SLAB_TIMEOUT_MS")) { const double ms = atof(e); if (ms > 0) p->slab_timeout_cycles = (long long)(ms * 1.9e6); }
+    p->src.release(); p->rec.release(); p->nsrc = p->nrec = 0;         // z chunking (and so the point binning) changes
+    return make_tmaps(p);
+}
+
 // own planes [z_own0, z_own1) of the local grid; neighbour handles (null = no neighbour on that side); up_ghost_z = first
 // ghost plane index, in the upper neighbour's local grid, that receives this rank's first four owned planes.
 int fwi_fd_slab_connect(fwi_fd2d* p, int z_own0, int z_own1, const void* up_handle, const uint64_t* up_offsets, int up_ghost_z,
@@ -1321,18 +1324,53 @@ int fwi_fd_slab_connect(fwi_fd2d* p, int z_own0, int z_own1, const void* up_hand
         cudaIpcMemHandle_t h;
         memcpy(&h, hs[s], sizeof(h));
         FWI_CUDA(cudaIpcOpenMemHandle(&p->peer_arena[s], h, cudaIpcMemLazyEnablePeerAccess));
+        p->peer_ipc[s] = true;
         for (int i = 0; i < 8; ++i) p->peer_fld_off[s][i] = (size_t)offs[s][i];
         p->peer_flags_off[s] = (size_t)offs[s][8];
     }
-    p->z_own0 = z_own0; p->z_own1 = z_own1; p->peer_up_z = up_ghost_z;
-    p->src.release(); p->rec.release(); p->nsrc = p->nrec = 0;         // z chunking (and so the point binning) changes
-    return make_tmaps(p);
+    return slab_finish_connect(p, z_own0, z_own1, up_ghost_z);
+}
+
+// Same protocol between plans of ONE process (peers are other plans on this or a peer-accessible device): used by the
+// single-GPU protocol test, where two small plans run on two streams of the same GPU.
+int fwi_fd_slab_connect_local(fwi_fd2d* p, int z_own0, int z_own1, fwi_fd2d* up, int up_ghost_z, fwi_fd2d* dn) {
+    FWI_REQUIRE(p && p->ny > 1, "fwi_fd_slab_connect_local: needs a 3-D plan");
+    FWI_REQUIRE(z_own0 >= 0 && z_own1 <= p->nz && z_own1 - z_own0 >= 2 * kHalo, "fwi_fd_slab_connect_local: owned range [%d, %d) invalid for nz=%d", z_own0, z_own1, p->nz);
+    DeviceGuard g(p->device);
+    FWI_CUDA(cudaStreamSynchronize(p->work));
+    drop_graphs(p);
+    fwi_fd2d* nb[2] = {up, dn};
+    for (int s = 0; s < 2; ++s) {
+        if (!nb[s]) continue;
+        FWI_REQUIRE(nb[s]->ny == p->ny && nb[s]->px == p->px, "fwi_fd_slab_connect_local: neighbour has a different plane shape");
+        p->peer_arena[s] = nb[s]->arena;
+        p->peer_ipc[s] = false;
+        for (int i = 0; i < 8; ++i) p->peer_fld_off[s][i] = (size_t)((char*)nb[s]->fld[i] - (char*)nb[s]->arena);
+        p->peer_flags_off[s] = (size_t)((char*)nb[s]->sync_area - (char*)nb[s]->arena);
+    }
+    return slab_finish_connect(p, z_own0, z_own1, up_ghost_z);
+}
+
+int fwi_fd_slab_set_timeout(fwi_fd2d* p, double milliseconds) {
+    FWI_REQUIRE(p && milliseconds > 0, "fwi_fd_slab_set_timeout: bad arguments");
+    p->slab_timeout_cycles = (long long)(milliseconds * 1.9e6);      // clock64 ticks at ~1.9 GHz
+    drop_graphs(p);                                                   // the timeout is a kernel argument
+    return FWI_OK;
+}
+
+// Clears the error flag after the caller has dealt with a timeout (all ranks together, with the device idle).
+int fwi_fd_slab_clear_error(fwi_fd2d* p) {
+    FWI_REQUIRE(p, "fwi_fd_slab_clear_error: NULL plan");
+    DeviceGuard g(p->device);
+    FWI_CUDA(cudaDeviceSynchronize());
+    FWI_CUDA(cudaMemset(p->sync_area + kSyncError, 0, sizeof(int)));
+    return FWI_OK;
 }
 
 int fwi_fd_slab_error(fwi_fd2d* p, int* error_out) {
     FWI_REQUIRE(p && error_out, "fwi_fd_slab_error: bad arguments");
     DeviceGuard g(p->device);
-    FWI_CUDA(cudaMemcpy(error_out, p->sync_area + 3, sizeof(int), cudaMemcpyDeviceToHost));
+    FWI_CUDA(cudaMemcpy(error_out, p->sync_area + kSyncError, sizeof(int), cudaMemcpyDeviceToHost));
     return FWI_OK;
 }
 

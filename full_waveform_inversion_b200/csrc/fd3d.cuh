@@ -57,16 +57,25 @@ struct Step3DArgs {
     float* rec_out;
     // ---- slab decomposition over NVLink peer memory (all null / zero for a single-GPU plan) -----------------------
     int z_own0, z_own1;        // owned plane range of the local grid (ghost planes lie outside and are never computed)
+    int last_desc;             // 1: the last z chunk marches downwards, so that the lower boundary planes come first
     float* peer_up;            // the upper / lower neighbour's copy of `oldnew` (peer-mapped), or null
     float* peer_dn;
     int peer_up_z;             // first ghost plane (in the upper neighbour's local grid) that receives my first 4 owned planes
-    int* flags_local;          // [0] written by the upper neighbour, [1] by the lower one: "my step k is complete"
-    int* flag_peer_up;         // where I announce completion to the upper / lower neighbour (their flags_local slots)
+    int* sync;                 // this GPU's sync words (SlabSync below)
+    int* flag_peer_up;         // where I announce "boundary planes of launch k pushed" to the upper / lower neighbour
     int* flag_peer_dn;
-    int wait_id, signal_id;    // this launch needs neighbours' flags >= wait_id and publishes signal_id
-    unsigned int* done_counter;
-    int* error_flag;
+    long long timeout_cycles;  // bounded spin on a neighbour's flag
 };
+
+// sync words of one plan (ints inside its arena; the neighbours write [0] / [1] through their peer mapping)
+enum SlabSync { kSyncFlagUp = 0,   // written by the upper neighbour: its launch k has pushed my upper ghost planes
+                kSyncFlagDn = 1,   // same from the lower neighbour
+                kSyncDoneAll = 2,  // CTAs of the running launch that have finished
+                kSyncError = 3,    // a wait timed out: every later launch returns at once, the host raises
+                kSyncStep = 4,     // launches completed so far - the step id lives on the device, so the time loop
+                                   // can be replayed from a CUDA graph
+                kSyncDoneUp = 5,   // CTAs that have pushed their share of the upper / lower boundary planes
+                kSyncDoneDn = 6 };
 
 __device__ __forceinline__ int ld_acquire_sys(const int* p) {
     int v;
@@ -77,6 +86,34 @@ __device__ __forceinline__ void st_release_sys(int* p, int v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// ---- slab protocol helpers -----------------------------------------------------------------------------------------
+// One consumer warp / the whole CTA reports that its share of a boundary side is in the neighbour's memory; the last
+// reporter of the side publishes the step id there (system-scope release).  Callers have fenced their peer stores.
+__device__ __forceinline__ void slab_side_done(const Step3DArgs& a, int side, unsigned ctas_on_side, int signal_id) {
+    unsigned int* cnt = (unsigned int*)(a.sync + (side == 0 ? kSyncDoneUp : kSyncDoneDn));
+    __threadfence();
+    if (atomicAdd(cnt, 1u) == ctas_on_side - 1) {
+        *cnt = 0;
+        __threadfence_system();
+        st_release_sys(side == 0 ? a.flag_peer_up : a.flag_peer_dn, signal_id);
+    }
+}
+
+// Waits (one thread) until the neighbours have pushed everything up to launch `need`; used before a run's memsets /
+// checkpoint restores so that no late push of the previous run lands on freshly written ghost planes.
+__global__ void fd3d_slab_sync_kernel(int* sync, int has_up, int has_dn, long long timeout_cycles) {
+    if (threadIdx.x != 0 || sync[kSyncError]) return;
+    const int need = sync[kSyncStep];
+    for (int side = 0; side < 2; ++side) {
+        if ((side == 0 && !has_up) || (side == 1 && !has_dn)) continue;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(sync + side) < need) {
+            if (clock64() - t0 > timeout_cycles) { atomicExch(sync + kSyncError, 1); return; }
+            __nanosleep(200);
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(const __grid_constant__ CUtensorMap tm_cur,
                                                                        const __grid_constant__ CUtensorMap tm_old,
@@ -84,26 +121,48 @@ __global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(cons
     extern __shared__ __align__(128) float ring[];                   // [NP][SY][SX] u_n planes, then [NO][2][BY][BX] u_{n-1} / m planes
     float* om_ring = ring + (size_t)k3NP * k3PlaneFloats;
     __shared__ __align__(8) uint64_t full_bar[k3NP], empty_bar[k3NP], om_full[k3NO], om_empty[k3NO];
+    __shared__ int slab_state[4];                  // [0] step id of this launch, [1] abort, [2]/[3] consumer warps done with the upper / lower boundary
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x0 = blockIdx.x * k3BX, y0 = blockIdx.y * k3BY;
     const int zc0 = a.z_own0 + blockIdx.z * a.zchunk, zc1 = min(a.z_own1, zc0 + a.zchunk);
     const int nout = zc1 - zc0;                   // output planes of this CTA
     const int nplanes = nout + 2 * kHalo;         // planes zc0-4 .. zc1+3
+    // march direction: upwards in z, except the last chunk of a slab with a lower neighbour, which marches downwards so
+    // that BOTH boundaries of the slab are computed (and pushed to the neighbours) in the first four iterations of
+    // their CTAs and the NVLink transfer + the neighbours' wait hide behind the interior planes.  The stencil is
+    // symmetric in z, so the register window works unchanged in either direction.
+    const bool desc = a.last_desc && blockIdx.z == gridDim.z - 1;
+    const int zbeg = desc ? zc1 - 1 : zc0, zstep = desc ? -1 : 1;       // output plane j is z = zbeg + zstep * j
+    const bool slab = a.peer_up != nullptr || a.peer_dn != nullptr;
+    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const int i0 = a.inj.tile_ptr ? a.inj.tile_ptr[cta] : 0, i1 = a.inj.tile_ptr ? a.inj.tile_ptr[cta + 1] : 0;
+    const int r0 = a.rec.tile_ptr ? a.rec.tile_ptr[cta] : 0, r1 = a.rec.tile_ptr ? a.rec.tile_ptr[cta + 1] : 0;
+    // which boundary sides this CTA owns (zchunk >= 8 in slab mode, so a 4-plane boundary never straddles two chunks)
+    const bool own_up = a.peer_up && blockIdx.z == 0, own_dn = a.peer_dn && blockIdx.z == gridDim.z - 1;
+    // CTAs with injection points report their sides only after the sparse fix-ups (a source may sit in a boundary plane)
+    const bool early = i1 == i0;
 
     if (threadIdx.x == 0) {
-        // slab mode: the ghost planes of u_n are written by the neighbours' previous launch straight into this GPU's
-        // memory; wait until both have announced it (bounded spin: a dead neighbour raises error_flag instead of hanging)
-        // Only the first / last z chunk reads (and later pushes to) the upper / lower ghost planes, so only those CTAs wait.
-        if (a.wait_id > 0) {
-            for (int side = 0; side < 2; ++side) {
-                if ((side == 0 && !a.peer_up) || (side == 1 && !a.peer_dn)) continue;
-                if ((side == 0 && blockIdx.z != 0) || (side == 1 && blockIdx.z != gridDim.z - 1)) continue;
-                const long long t0 = clock64();
-                while (ld_acquire_sys(a.flags_local + side) < a.wait_id) {
-                    if (clock64() - t0 > 6000000000LL) { atomicExch(a.error_flag, 1); break; }      // ~3 s
-                    __nanosleep(200);
+        slab_state[0] = 0; slab_state[1] = 0; slab_state[2] = 0; slab_state[3] = 0;
+        if (slab) {
+            // The step id lives on the device (launches completed so far): this launch needs the neighbours' pushes of
+            // launch `id` and publishes `id + 1`.  Ghost planes of u_n are written by the neighbours straight into this
+            // GPU's memory; only the CTAs that read them wait (bounded spin: a dead neighbour raises the error flag).
+            const int id = a.sync[kSyncStep];
+            slab_state[0] = id;
+            if (a.sync[kSyncError]) slab_state[1] = 1;
+            else {
+                for (int side = 0; side < 2; ++side) {
+                    if (!(side == 0 ? own_up : own_dn)) continue;
+                    const long long t0 = clock64();
+                    while (ld_acquire_sys(a.sync + side) < id) {
+                        if (clock64() - t0 > a.timeout_cycles) { atomicExch(a.sync + kSyncError, 1); slab_state[1] = 1; break; }
+                        __nanosleep(100);
+                    }
                 }
+                // peer GPUs wrote the ghost planes with generic-proxy stores; TMA reads them through the async proxy
+                asm volatile("fence.proxy.async;" ::: "memory");
             }
         }
 #pragma unroll
@@ -114,6 +173,9 @@ __global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(cons
         fence_proxy_async();
     }
     __syncthreads();
+    if (slab_state[1]) return;                     // a neighbour is gone: do not compute on stale ghosts, do not spin again
+    const int signal_id = slab_state[0] + 1;
+    const unsigned ctas_per_side = gridDim.x * gridDim.y;
 
     if (warp >= k3CW) {
         // ---------------- producer warp(s): one lane feeds the u_n plane ring, one the u_{n-1} / m ring
@@ -125,7 +187,7 @@ __global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(cons
                     const int slot = t % k3NP;
                     if (t >= k3NP) mbar_wait(&empty_bar[slot], ((t / k3NP) - 1) & 1);
                     mbar_expect_tx(&full_bar[slot], k3PlaneFloats * (uint32_t)sizeof(float));
-                    tma_load_3d(ring + (size_t)slot * k3PlaneFloats, &tm_cur, x0 - kHalo, y0 - kHalo, zc0 - kHalo + t, &full_bar[slot]);
+                    tma_load_3d(ring + (size_t)slot * k3PlaneFloats, &tm_cur, x0 - kHalo, y0 - kHalo, zbeg + zstep * (t - kHalo), &full_bar[slot]);
                 }
                 const int j = t - k3OmLead;
                 if (do_om && j >= 0 && j < nout) {
@@ -133,8 +195,8 @@ __global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(cons
                     if (j >= k3NO) mbar_wait(&om_empty[slot], ((j / k3NO) - 1) & 1);
                     float* dst = om_ring + (size_t)slot * 2 * k3OmFloats;
                     mbar_expect_tx(&om_full[slot], 2 * k3OmFloats * (uint32_t)sizeof(float));
-                    tma_load_3d(dst, &tm_old, x0, y0, zc0 + j, &om_full[slot]);
-                    tma_load_3d(dst + k3OmFloats, &tm_m, x0, y0, zc0 + j, &om_full[slot]);
+                    tma_load_3d(dst, &tm_old, x0, y0, zbeg + zstep * j, &om_full[slot]);
+                    tma_load_3d(dst + k3OmFloats, &tm_m, x0, y0, zbeg + zstep * j, &om_full[slot]);
                 }
             }
         }
@@ -153,7 +215,8 @@ __global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(cons
         auto own = [&](int p, int r) {                 // this lane's element of row r in ring plane p
             return ld4(ring + (size_t)(p % k3NP) * k3PlaneFloats + (yl + r + kHalo) * k3SX + kHalo + 4 * lane);
         };
-        // prime with planes 0..7 (z = zc0-4 .. zc0+3); planes 0..3 are never centre planes -> release them
+        // prime with planes 0..7 (the four behind the first output plane and the first four); planes 0..3 are never
+        // centre planes -> release them
         for (int p = 0; p < 2 * kHalo; ++p) {
             mbar_wait(&full_bar[p % k3NP], (p / k3NP) & 1);
 #pragma unroll
@@ -163,8 +226,11 @@ __global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(cons
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[p % k3NP])) : "memory");
             }
         }
+        // byte distance from a point of `oldnew` to its copy in the neighbour's ghost planes
+        const long long dup = a.peer_up ? (long long)((char*)(a.peer_up + (size_t)(a.peer_up_z - a.z_own0) * a.ny * a.px) - (char*)a.oldnew) : 0;
+        const long long ddn = a.peer_dn ? (long long)((char*)a.peer_dn - (char*)(a.oldnew + (size_t)(a.z_own1 - kHalo) * a.ny * a.px)) : 0;
         for (int iz = 0; iz < nout; ++iz) {
-            const int z = zc0 + iz;
+            const int z = zbeg + zstep * iz;
             const int ptop = iz + 2 * kHalo, pmid = iz + kHalo;
             // global operands first: their latency overlaps the barrier wait and the shared-memory reads
             float4 o4[k3RPW], m4[k3RPW], s4[k3RPW], c4[k3RPW], sp4[k3RPW];
@@ -194,6 +260,8 @@ __global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(cons
                 for (int k = 0; k < 8; ++k) win[r][k] = win[r][k + 1];
                 win[r][8] = own(ptop, r);
             }
+            // slab mode: the 4 owned planes next to a neighbour are also stored straight into its ghost planes (NVLink)
+            const bool bu = a.peer_up && z < a.z_own0 + kHalo, bd = a.peer_dn && z >= a.z_own1 - kHalo;
             const float* mid = ring + (size_t)(pmid % k3NP) * k3PlaneFloats;
             float4 yc[8 + k3RPW];                        // rows yl-4 .. yl+3+RPW of the centre plane, this lane's float4
 #pragma unroll
@@ -221,7 +289,10 @@ __global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(cons
                     nv[q] = gv[q] * fmaf(mv[q], lap, fmaf(-gv[q], ov[q], 2.0f * c));
                 }
                 if (ok[r]) {
-                    st4(a.oldnew + off[r], make_float4(nv[0], nv[1], nv[2], nv[3]));
+                    const float4 n4 = make_float4(nv[0], nv[1], nv[2], nv[3]);
+                    st4(a.oldnew + off[r], n4);
+                    if (bu) st4((float*)((char*)(a.oldnew + off[r]) + dup), n4);
+                    if (bd) st4((float*)((char*)(a.oldnew + off[r]) + ddn), n4);
                     if (MODE == STEP_FWD_SAVE) st4_stream(a.snap + off[r], make_float4(wv[0], wv[1], wv[2], wv[3]));
                     if (MODE == STEP_ADJ || MODE == STEP_ADJ2) {
                         float4 c = c4[r];
@@ -241,13 +312,24 @@ __global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(cons
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[pmid % k3NP])) : "memory");
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&om_empty[iz % k3NO])) : "memory");
             }
+            // a boundary side is complete for this warp after its 4th plane: the last consumer warp of the CTA reports the
+            // CTA, the last CTA of the side publishes the step id to the neighbour - long before the march ends
+            if (bu || bd) {
+                // (the chunk that owns the upper boundary always marches upwards)
+                const bool fin_up = bu && z == a.z_own0 + kHalo - 1, fin_dn = bd && z == (desc ? a.z_own1 - kHalo : a.z_own1 - 1);
+                if (early && (fin_up || fin_dn)) {
+                    __threadfence_system();            // every lane: its peer stores are visible system-wide
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (fin_up && atomicAdd(&slab_state[2], 1) == k3CW - 1) slab_side_done(a, 0, ctas_per_side, signal_id);
+                        if (fin_dn && atomicAdd(&slab_state[3], 1) == k3CW - 1) slab_side_done(a, 1, ctas_per_side, signal_id);
+                    }
+                }
+            }
         }
     }
 
     // ---- sparse fix-ups for the points this CTA owns: injection, then receiver sampling -------------------
-    const int tid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    const int i0 = a.inj.tile_ptr ? a.inj.tile_ptr[tid] : 0, i1 = a.inj.tile_ptr ? a.inj.tile_ptr[tid + 1] : 0;
-    const int r0 = a.rec.tile_ptr ? a.rec.tile_ptr[tid] : 0, r1 = a.rec.tile_ptr ? a.rec.tile_ptr[tid + 1] : 0;
     if (i1 > i0 || r1 > r0) {
         __syncthreads();
         for (int e = i0 + threadIdx.x; e < i1; e += blockDim.x) {
@@ -260,42 +342,39 @@ __global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(cons
             if (MODE == STEP_FWD_SAVE) atomicAdd(a.snap + off, val);
             if (MODE == STEP_ADJ || MODE == STEP_ADJ2) atomicAdd(a.acc + off, gm * val * a.snap[off]);
         }
-        if (r1 > r0) {
+        if (r1 > r0 || (slab && i1 > i0)) __syncthreads();
+        for (int e = r0 + threadIdx.x; e < r1; e += blockDim.x) a.rec_out[a.rec.id[e]] = __ldcg(a.oldnew + a.rec.off[e]);
+        if (slab && i1 > i0) {
+            // injected cells inside a boundary plane: refresh the neighbour's ghost copy with the final value, then report
+            // the sides this CTA owns (it did not report them during the march)
+            for (int e = i0 + threadIdx.x; e < i1; e += blockDim.x) {
+                const int off = a.inj.off[e];
+                const int zy = off / a.px, xx = off - zy * a.px;
+                const int z = zy / a.ny, y = zy - z * a.ny;
+                const float v = __ldcg(a.oldnew + off);
+                if (a.peer_up && z < a.z_own0 + kHalo) a.peer_up[((size_t)(a.peer_up_z + z - a.z_own0) * a.ny + y) * a.px + xx] = v;
+                if (a.peer_dn && z >= a.z_own1 - kHalo) a.peer_dn[((size_t)(z - (a.z_own1 - kHalo)) * a.ny + y) * a.px + xx] = v;
+            }
+            __threadfence_system();
             __syncthreads();
-            for (int e = r0 + threadIdx.x; e < r1; e += blockDim.x) a.rec_out[a.rec.id[e]] = __ldcg(a.oldnew + a.rec.off[e]);
+            if (threadIdx.x == 0) {
+                if (own_up) slab_side_done(a, 0, ctas_per_side, signal_id);
+                if (own_dn) slab_side_done(a, 1, ctas_per_side, signal_id);
+            }
         }
     }
 
-    // ---- slab mode: push this CTA's share of the 4 boundary planes into the neighbours' ghost planes over NVLink
-    //      (plain stores to peer-mapped pointers), then the last CTA of the grid publishes the step id -------------
-    if (a.peer_up || a.peer_dn) {
-        __syncthreads();                                   // dense stores and fix-ups of this CTA are done
-        bool pushed = false;
-        for (int side = 0; side < 2; ++side) {
-            float* peer = side == 0 ? a.peer_up : a.peer_dn;
-            if (!peer) continue;
-            const int zb0 = side == 0 ? a.z_own0 : a.z_own1 - kHalo;            // my 4 boundary planes
-            const int zdst0 = side == 0 ? a.peer_up_z : 0;                      // where they land in the neighbour's grid
-            for (int z = max(zb0, zc0); z < min(zb0 + kHalo, zc1); ++z) {
-                pushed = true;
-                for (int i = threadIdx.x; i < k3BY * (k3BX / 4); i += blockDim.x) {
-                    const int yy = y0 + i / (k3BX / 4), xx = x0 + 4 * (i % (k3BX / 4));
-                    if (yy < a.ny && xx < a.px) {
-                        const float4 v = __ldcg(reinterpret_cast<const float4*>(a.oldnew + ((size_t)z * a.ny + yy) * a.px + xx));
-                        *reinterpret_cast<float4*>(peer + ((size_t)(zdst0 + z - zb0) * a.ny + yy) * a.px + xx) = v;
-                    }
-                }
-            }
-        }
-        if (pushed) __threadfence_system();                // block-uniform: make the peer stores visible before counting in
+    // ---- slab mode: the last CTA of the launch advances the device-resident step id --------------------------------
+    if (slab) {
         __syncthreads();
         if (threadIdx.x == 0) {
+            unsigned int* done = (unsigned int*)(a.sync + kSyncDoneAll);
             const unsigned total = gridDim.x * gridDim.y * gridDim.z;
-            if (atomicAdd(a.done_counter, 1u) == total - 1) {
-                *a.done_counter = 0;
-                __threadfence_system();
-                if (a.flag_peer_up) st_release_sys(a.flag_peer_up, a.signal_id);
-                if (a.flag_peer_dn) st_release_sys(a.flag_peer_dn, a.signal_id);
+            __threadfence();
+            if (atomicAdd(done, 1u) == total - 1) {
+                *done = 0;
+                a.sync[kSyncStep] = signal_id;
+                __threadfence();
             }
         }
     }

@@ -161,13 +161,10 @@ typedef struct fwi_fd2d fwi_fd2d;
  * accumulator and the TMA descriptors. */
 int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, float alpha, fwi_fd2d** out);
 int fwi_fd2d_destroy(fwi_fd2d* plan);
-/* Select the one-tile-per-CTA step kernel with bz tile rows and nw warps per CTA (default: 16 x 2).
- * Clears the geometry. */
+/* Select the one-tile-per-CTA step kernel with bz tile rows and nw warps per CTA: (32, 4) [the sweep's winner and the
+ * default for L2-resident grids], (64, 8) or (16, 2).  Clears the geometry. */
 int fwi_fd2d_set_tile(fwi_fd2d* plan, int bz, int nw);
-/* Select the persistent streaming step kernel with nw warps per SM and nc TMA pipeline slots per warp.
- * Clears the geometry. */
-int fwi_fd2d_set_stream(fwi_fd2d* plan, int nw, int nc);
-/* Select the temporally blocked kernel: two leapfrog steps per pass on 120 x cz core tiles (cz in 16, 24, 32, 56);
+/* Select the temporally blocked kernel: two leapfrog steps per pass on 120 x cz core tiles (cz in 16, 24, 32);
  * an odd leftover step runs the one-step tile kernel.  Clears the geometry. */
 int fwi_fd2d_set_tb2(fwi_fd2d* plan, int cz);
 /* Replay the time loops as cached CUDA graphs (default on) or as individual launches (0). */
@@ -219,13 +216,22 @@ int fwi_fd_finalize_gradient(fwi_fd2d* plan, float* grad_dev, void* stream);   /
 /* Slab decomposition over NVLink peer memory (3-D plans, one process per GPU): every rank exports its arena
  * (fwi_fd_slab_info: a cudaIpcMemHandle_t plus the byte offsets of the 8 wavefield buffers and of the sync area),
  * the host layer swaps them between neighbours (torch.distributed), and fwi_fd_slab_connect maps the neighbours'
- * memory.  From then on fwi_fd_step computes only the owned planes [z_own0, z_own1), stores its 4 boundary planes
+ * memory.  From then on a step computes only the owned planes [z_own0, z_own1), stores its 4 boundary planes
  * straight into the neighbours' ghost planes from inside the step kernel and publishes a step id that the
  * neighbours' next launch waits for - compute and halo exchange are one kernel, no collective call per step. */
 int fwi_fd_slab_info(fwi_fd2d* plan, void* ipc_handle_out, uint64_t* offsets_out);
 int fwi_fd_slab_connect(fwi_fd2d* plan, int z_own0, int z_own1, const void* up_handle, const uint64_t* up_offsets, int up_ghost_z,
                         const void* dn_handle, const uint64_t* dn_offsets);
 int fwi_fd_slab_error(fwi_fd2d* plan, int* error_out);       /* 1 if a launch timed out waiting for a neighbour */
+/* Once connected, the ordinary fwi_fd2d_forward / fwi_fd2d_gradient entry points run the slab: step ids live in device
+ * memory (so the time loops replay from CUDA graphs), both boundaries are computed and pushed in the first four
+ * iterations of their CTAs (the last z chunk marches downwards), the gradient checkpoints per rank when the
+ * snapshots do not fit, and a rank without sources or receivers is allowed.  After a timeout every later launch
+ * returns at once until fwi_fd_slab_clear_error (all ranks, device idle). */
+int fwi_fd_slab_set_timeout(fwi_fd2d* plan, double milliseconds);      /* bounded spin on a neighbour's flag (default 2 s) */
+int fwi_fd_slab_clear_error(fwi_fd2d* plan);
+/* The same protocol between plans of one process (peers = other plans; null = no neighbour on that side). */
+int fwi_fd_slab_connect_local(fwi_fd2d* plan, int z_own0, int z_own1, fwi_fd2d* up, int up_ghost_z, fwi_fd2d* dn);
 
 /* residual = syn - obs, J = 1/2 sum residual^2 (fd_oracle.misfit). Synchronises. */
 int fwi_fd_misfit(const float* syn_dev, const float* obs_dev, int64_t n, float* resid_dev, double* misfit_host,

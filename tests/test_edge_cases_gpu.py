@@ -86,7 +86,7 @@ def _grid(nz=37, nx=131, seed=0):
     return v, h, fo.stable_dt(v.max(), h, 2)
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(tb2=16), dict(stream=(8, 4))])
+@pytest.mark.parametrize("kw", [dict(), dict(tb2=16), dict(tile=(16, 2))])
 @pytest.mark.parametrize("nt", [1, 2, 3, 37])
 def test_short_and_odd_step_counts(mods, kw, nt):
     """nt = 1 and odd nt: the two-steps-per-pass kernel must hand its leftover step to the one-step kernel, the
@@ -108,7 +108,7 @@ def test_short_and_odd_step_counts(mods, kw, nt):
     prop.close()
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(tb2=16), dict(stream=(8, 4))])
+@pytest.mark.parametrize("kw", [dict(), dict(tb2=16), dict(tile=(16, 2))])
 def test_corner_duplicate_and_colocated_points(mods, kw):
     """Sources in the grid corners, two sources on the same cell, a receiver on the source cell, duplicated
     receivers, points on tile boundaries (x = 119/120/127/128, z = 15/16/31/32)."""

@@ -63,12 +63,10 @@ def test_forward_traces_and_wavefield(ac, nz, nx, nt, nsrc, kw):
     prop.close()
 
 
-@pytest.mark.parametrize("kind,cfg", [("tile", (32, 4)), ("tile", (32, 8)), ("tile", (16, 4)), ("tile", (64, 8)),
-                                      ("tile", (16, 2)), ("tile", (64, 4)), ("stream", (8, 4)), ("stream", (4, 8)),
-                                      ("stream", (6, 5)), ("stream", (8, 3)), ("stream", (12, 3)), ("graphs", False),
-                                      ("tb2", 32), ("tb2", 16), ("tb2", 24), ("tb2", 56)])
+@pytest.mark.parametrize("kind,cfg", [("tile", (32, 4)), ("tile", (64, 8)), ("tile", (16, 2)), ("graphs", False),
+                                      ("tb2", 32), ("tb2", 16), ("tb2", 24)])
 def test_kernel_variants_agree(ac, kind, cfg):
-    """Every step-kernel variant (one-tile-per-CTA and persistent streaming) gives the oracle's traces and gradient."""
+    """Every step-kernel variant (one-tile-per-CTA shapes, two-steps-per-pass, plain launches) gives the oracle's traces and gradient."""
     v, h, dt, src, rec, wav = _case(75, 300, 150, seed=3)
     obs = fo.Problem(v * 1.03, h, dt, src, rec, nabs=10).forward(wav)
     J_want, g_want, tr_want = fo.Problem(v, h, dt, src, rec, nabs=10).misfit_and_gradient(wav, obs)

@@ -131,3 +131,147 @@ def test_slab_owned_range_logic_on_one_gpu(ac):
     assert np.array_equal(np.concatenate([upper, lower]), want_field)
     for p in plans:
         p.close()
+
+
+def _local_slabs(ac, shape, h, dt, nabs, nslab, v, src, rec, **kw):
+    """What SlabPropagator builds per rank, for `nslab` plans living on ONE GPU and connected with
+    fwi_fd_slab_connect_local (the peer-memory protocol without IPC)."""
+    from full_waveform_inversion_b200 import _lib
+    lib = _lib.load()
+    H, nz = 4, shape[0]
+    base, rem = divmod(nz, nslab)
+    counts = [base + (1 if r < rem else 0) for r in range(nslab)]
+    gz = ac.sponge_profile(nz, nabs, 0.3)
+    slabs = []
+    for r in range(nslab):
+        z0 = sum(counts[:r])
+        up, down = (H if r else 0), (H if r < nslab - 1 else 0)
+        lo, hi = z0 - up, z0 + counts[r] + down
+        p = ac.Propagator((hi - lo,) + shape[1:], h, dt, nabs=nabs, **kw)
+        p.set_profiles(gz=gz[lo:hi])
+        slabs.append(dict(p=p, z0=z0, n=counts[r], up=up, lo=lo, hi=hi))
+    for r, s in enumerate(slabs):
+        upp = slabs[r - 1] if r else None
+        dnp = slabs[r + 1] if r < nslab - 1 else None
+        _lib.check(lib.fwi_fd_slab_connect_local(s["p"]._h, s["up"], s["up"] + s["n"], upp["p"]._h if upp else None,
+                                                 (upp["hi"] - upp["lo"] - H) if upp else 0, dnp["p"]._h if dnp else None))
+    for s in slabs:
+        s["p"].set_model(v[s["lo"]:s["hi"]])
+        s["src_ids"] = [i for i, q in enumerate(src) if s["z0"] <= q[0] < s["z0"] + s["n"]]
+        s["rec_ids"] = [i for i, q in enumerate(rec) if s["z0"] <= q[0] < s["z0"] + s["n"]]
+        loc = lambda ids, pts: np.array([(pts[i][0] - s["lo"], pts[i][1], pts[i][2]) for i in ids], dtype=np.int64).reshape(-1, 3)
+        s["p"].set_geometry(loc(s["src_ids"], src), loc(s["rec_ids"], rec))
+    return slabs
+
+
+def _run_ranks(slabs, fn):
+    """One host thread and one CUDA stream per emulated rank (the kernels of neighbouring slabs wait for each other)."""
+    import threading
+    import torch
+    out, err = [None] * len(slabs), []
+
+    def work(r):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                out[r] = fn(r, slabs[r])
+                torch.cuda.current_stream().synchronize()
+        except Exception as exc:                                  # noqa: BLE001
+            err.append(exc)
+    th = [threading.Thread(target=work, args=(r,)) for r in range(len(slabs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if err:
+        raise err[0]
+    return out
+
+
+@pytest.mark.parametrize("nslab,graphs,limit_planes", [(2, True, 0), (3, True, 0), (3, False, 0), (3, True, 34), (2, True, 30)])
+def test_peer_memory_slab_protocol_on_one_gpu(ac, nslab, graphs, limit_planes):
+    """The fused compute + halo-push protocol (device-resident step ids, early boundary pushes with the last chunk marching
+    downwards, fence kernel before memsets / checkpoint restores, CUDA-graph replay, per-slab checkpointing, slabs without
+    sources) between plans of one process on one GPU.  Traces and owned gradient planes equal a single-plan run bit for bit
+    when every w_n is held; with checkpointing the deferred-imaging pairs differ (as on a single plan): <= 1e-6."""
+    import ctypes
+    import torch
+    from full_waveform_inversion_b200 import _lib
+    shape, nt = (72, 20, 140), 60
+    v, h, dt, _, _, wav = _case(shape, nt, seed=21)
+    src = [(6, 10, 40), (40, 8, 100), (23, 5, 17)]                # (23, ..) and (24, ..) straddle the 3-slab boundary at z = 24
+    rec = [(5, y, x) for y in (3, 9, 15) for x in range(4, 136, 12)] + [(44, 10, 70), (24, 5, 17), (47, 19, 139), (48, 0, 0), (71, 10, 10)]
+    wav = np.stack([wav[:, 0], wav[:, 1], 0.5 * wav[:, 0]], 1)
+    full = ac.Propagator(shape, h, dt, nabs=6)
+    full.set_model(v * 1.03)
+    full.set_geometry(src, rec)
+    obs = full.forward(wav).clone()
+    full.set_model(v)
+    want_tr = full.forward(wav).cpu().numpy()
+    J_want, g_want, _ = full.gradient(wav, obs)
+    g_want = g_want.cpu().numpy()
+    full.close()
+
+    slabs = _local_slabs(ac, shape, h, dt, 6, nslab, v, src, rec, graphs=graphs)
+    plane = shape[1] * 160 * 4
+    if limit_planes:
+        for s in slabs:
+            s["p"].set_memory_limit(limit_planes * (s["hi"] - s["lo"]) * plane)      # 60 snapshots do not fit -> segments of 11
+    wav_t, obs_t = torch.tensor(wav, dtype=torch.float32, device="cuda"), obs
+
+    def fwd(r, s):
+        return s["p"].forward(wav_t[:, s["src_ids"]].contiguous()).cpu().numpy()
+
+    def grad(r, s):
+        J, g, tr = s["p"].gradient(wav_t[:, s["src_ids"]].contiguous(), obs_t[:, s["rec_ids"]].contiguous(), want_traces=True, want_misfit=False)
+        return g.cpu().numpy(), tr.cpu().numpy()
+
+    for rep in range(2):                                           # second pass replays the cached graphs
+        got = np.zeros_like(want_tr)
+        for s, tr in zip(slabs, _run_ranks(slabs, fwd)):
+            got[:, s["rec_ids"]] = tr
+        assert np.array_equal(got, want_tr)
+        res = _run_ranks(slabs, grad)
+        got = np.zeros_like(want_tr)
+        g_got = np.concatenate([g[s["up"]: s["up"] + s["n"]] for s, (g, _) in zip(slabs, res)])
+        for s, (_, tr) in zip(slabs, res):
+            got[:, s["rec_ids"]] = tr
+        assert np.array_equal(got, want_tr)
+        if limit_planes:
+            assert rel_l2(g_got, g_want) <= 1e-6
+        else:
+            assert np.array_equal(g_got, g_want)
+    lib = _lib.load()
+    for s in slabs:
+        e = ctypes.c_int(0)
+        _lib.check(lib.fwi_fd_slab_error(s["p"]._h, ctypes.byref(e)))
+        assert e.value == 0
+    torch.cuda.synchronize()
+    for s in slabs:
+        s["p"].close()
+
+
+def test_peer_memory_slab_timeout_is_reported_not_hung(ac):
+    """A slab whose neighbour never launches: the step kernels give up after the (shortened) timeout, every later launch
+    returns at once, and the error flag is raised instead of computing on stale ghost planes."""
+    import ctypes
+    import time
+    import torch
+    from full_waveform_inversion_b200 import _lib
+    shape, nt = (48, 20, 140), 40
+    v, h, dt, _, _, wav = _case(shape, nt, seed=3)
+    slabs = _local_slabs(ac, shape, h, dt, 6, 2, v, [(6, 10, 40)], [(5, 9, 30), (40, 9, 30)])
+    lib = _lib.load()
+    p = slabs[0]["p"]
+    _lib.check(lib.fwi_fd_slab_set_timeout(p._h, 50.0))
+    t0 = time.perf_counter()
+    p.forward(torch.tensor(wav[:, :1], dtype=torch.float32, device="cuda"))       # rank 1 never runs
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 5.0                          # one timeout, not one per step
+    e = ctypes.c_int(0)
+    _lib.check(lib.fwi_fd_slab_error(p._h, ctypes.byref(e)))
+    assert e.value == 1
+    _lib.check(lib.fwi_fd_slab_clear_error(p._h))
+    _lib.check(lib.fwi_fd_slab_error(p._h, ctypes.byref(e)))
+    assert e.value == 0
+    for s in slabs:
+        s["p"].close()

@@ -20,7 +20,7 @@ def time_forward(nz, nx, nt, **kw):
     prop.close()
     return e0.elapsed_time(e1) * 1e3 / nt     # us per step
 
-variants = [("tile", (16, 2)), ("stream", (8, 4)), ("tile", (32, 4)), ("tile", (16, 4))]
+variants = [("tile", (16, 2)), ("tile", (32, 4)), ("tile", (64, 8))]
 if len(sys.argv) > 1:
     variants = []
     for a in sys.argv[1:]:
