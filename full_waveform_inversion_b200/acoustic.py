@@ -42,6 +42,7 @@ _lib.register({
     "fwi_fd_field_ptr": (c_void_p, [c_void_p, c_int]),
     "fwi_fd_pitch": (c_int, [c_void_p]),
     "fwi_fd_reserve_snapshots": (c_int, [c_void_p, c_int]),
+    "fwi_fd_reserve": (c_int, [c_void_p, c_int, c_int]),
     "fwi_fd_reset": (c_int, [c_void_p, c_int, c_void_p]),
     "fwi_fd_step": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "fwi_fd_finalize_gradient": (c_int, [c_void_p, c_void_p, c_void_p]),
@@ -199,6 +200,10 @@ class Propagator:
                                         "data": (int(self._lib.fwi_fd_field_ptr(self._h, idx)), False)}
         with torch.cuda.device(self.device):
             return torch.as_tensor(raw, device=self.torch_device)
+
+    def reserve(self, nt, gradient=True):
+        """Allocate the buffers of a forward / gradient over nt steps now (allocations synchronise the device)."""
+        check(self._lib.fwi_fd_reserve(self._h, int(nt), 1 if gradient else 0))
 
     def reserve_snapshots(self, nsteps):
         check(self._lib.fwi_fd_reserve_snapshots(self._h, int(nsteps)))

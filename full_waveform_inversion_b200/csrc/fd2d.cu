@@ -866,17 +866,11 @@ static int record_gradient(fwi_fd2d* p, int nt, int seg, int nseg, cudaStream_t 
     return FWI_OK;
 }
 
-// Run `record` either directly on the work stream or as a cached graph keyed by (kind, nt, nsrc, nrec, seg, nseg).
+// Cached graph of a time loop, keyed by (kind, nt, nsrc, nrec, seg, nseg); captured and instantiated on first use.
 template <typename F>
-static int run_cached(fwi_fd2d* p, int kind, int nt, int seg, int nseg, F&& record) {
-    p->pdl_chain = false;             // the first step of a sweep follows memsets / copies / foreign kernels: full dependency
-    if (!p->use_graphs) return record(p->work);
+static int get_graph(fwi_fd2d* p, int kind, int nt, int seg, int nseg, F&& record, GraphEntry** out) {
     for (auto& g : p->graphs)
-        if (g.kind == kind && g.nt == nt && g.nsrc == p->nsrc && g.nrec == p->nrec && g.seg == seg && g.nseg == nseg) {
-            FWI_CUDA(cudaGraphLaunch(g.exec, p->work));
-            p->launches += g.kernels;
-            return FWI_OK;
-        }
+        if (g.kind == kind && g.nt == nt && g.nsrc == p->nsrc && g.nrec == p->nrec && g.seg == seg && g.nseg == nseg) { *out = &g; return FWI_OK; }
     cudaGraph_t graph = nullptr;
     FWI_CUDA(cudaStreamBeginCapture(p->work, cudaStreamCaptureModeThreadLocal));
     const int64_t l0 = p->launches;
@@ -892,8 +886,20 @@ static int run_cached(fwi_fd2d* p, int kind, int nt, int seg, int nseg, F&& reco
     if (e != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return FWI_ECUDA; }
     if (p->graphs.size() >= 6) { cudaGraphExecDestroy(p->graphs.front().exec); p->graphs.erase(p->graphs.begin()); }
     p->graphs.push_back(GraphEntry{kind, nt, p->nsrc, p->nrec, seg, nseg, exec, kernels});
-    FWI_CUDA(cudaGraphLaunch(exec, p->work));
-    p->launches += kernels;
+    *out = &p->graphs.back();
+    return FWI_OK;
+}
+
+// Run `record` either directly on the work stream or as a cached graph.
+template <typename F>
+static int run_cached(fwi_fd2d* p, int kind, int nt, int seg, int nseg, F&& record) {
+    p->pdl_chain = false;             // the first step of a sweep follows memsets / copies / foreign kernels: full dependency
+    if (!p->use_graphs) return record(p->work);
+    GraphEntry* g = nullptr;
+    int rc = get_graph(p, kind, nt, seg, nseg, record, &g);
+    if (rc) return rc;
+    FWI_CUDA(cudaGraphLaunch(g->exec, p->work));
+    p->launches += g->kernels;
     return FWI_OK;
 }
 
@@ -1174,18 +1180,12 @@ int fwi_fd2d_wavefield(fwi_fd2d* p, int which, float* out_dev, void* stream) {
     return leave(p, user);
 }
 
-int fwi_fd2d_gradient(fwi_fd2d* p, const float* wavelet_dev, const float* obs_dev, int nt, float* grad_dev,
-                      float* traces_dev, double* misfit_host, void* stream) {
-    FWI_REQUIRE(p && p->model_set, "fwi_fd2d_gradient: set the model first");
-    FWI_REQUIRE((wavelet_dev || p->nsrc == 0) && (obs_dev || p->nrec == 0) && grad_dev && nt >= 1, "fwi_fd2d_gradient: NULL argument or nt < 1");
-    FWI_REQUIRE((p->nsrc >= 1 && p->nrec >= 1) || p->z_own1 > 0, "fwi_fd2d_gradient: geometry needs at least one source and one receiver");
-    DeviceGuard g(p->device);
-    cudaStream_t user = (cudaStream_t)stream;
+// Storage decision and buffers of a gradient over nt steps (no launches).  Every w_n in HBM if it fits, else two-level
+// checkpointing.  The decision is cached per (nt, limit): cudaMemGetInfo takes a driver-wide lock and was measured
+// stalling the host for 5 - 90 ms every few calls, which showed up as sporadic slow shots.
+static int prepare_gradient(fwi_fd2d* p, int nt, int& seg, int& nseg) {
     const size_t pl = p->plane();
-    // ---- choose between holding every w_n in HBM and two-level checkpointing --------------------------
-    // The decision is cached per (nt, limit): cudaMemGetInfo takes a driver-wide lock and was measured stalling the
-    // host for 5 - 90 ms every few calls, which showed up as sporadic slow shots.
-    int seg = nt, nseg = 1;
+    seg = nt; nseg = 1;
     if (p->split_nt == nt && p->split_limit == p->mem_limit) {
         seg = p->split_seg; nseg = p->split_nseg;
     } else {
@@ -1212,6 +1212,43 @@ int fwi_fd2d_gradient(fwi_fd2d* p, const float* wavelet_dev, const float* obs_de
     if ((rc = ensure_floats(p, &p->obs, &p->obs_cap, ntr))) return rc;
     if ((rc = ensure_floats(p, &p->wav, &p->wav_cap, (size_t)nt * p->nsrc))) return rc;
     p->split_nt = nt; p->split_limit = p->mem_limit; p->split_seg = seg; p->split_nseg = nseg;      // buffers exist now
+    return FWI_OK;
+}
+
+// Allocate everything fwi_fd2d_forward (gradient = 0) or fwi_fd2d_gradient (1) over nt steps with the current geometry
+// will need, without launching anything: keeps allocations (which synchronise the device) out of timed regions and out
+// of the way of kernels that wait for another plan.
+int fwi_fd_reserve(fwi_fd2d* p, int nt, int gradient) {
+    FWI_REQUIRE(p && nt >= 1, "fwi_fd_reserve: bad arguments");
+    DeviceGuard g(p->device);
+    int rc, seg = 0, nseg = 0;
+    if (gradient) { if ((rc = prepare_gradient(p, nt, seg, nseg))) return rc; }
+    else {
+        if ((rc = ensure_floats(p, &p->wav, &p->wav_cap, (size_t)nt * p->nsrc))) return rc;
+        if ((rc = ensure_floats(p, &p->syn, &p->syn_cap, (size_t)nt * p->nrec))) return rc;
+    }
+    if (p->use_graphs && p->model_set) {          // capture, instantiate and upload the time loop now as well
+        GraphEntry* g = nullptr;
+        p->pdl_chain = false;
+        if (gradient) rc = get_graph(p, 1, nt, seg, nseg, [&](cudaStream_t st) { return record_gradient(p, nt, seg, nseg, st); }, &g);
+        else rc = get_graph(p, 0, nt, 0, 0, [&](cudaStream_t st) { return record_forward(p, nt, st); }, &g);
+        if (rc) return rc;
+        FWI_CUDA(cudaGraphUpload(g->exec, p->work));
+        FWI_CUDA(cudaStreamSynchronize(p->work));
+    }
+    return FWI_OK;
+}
+
+int fwi_fd2d_gradient(fwi_fd2d* p, const float* wavelet_dev, const float* obs_dev, int nt, float* grad_dev,
+                      float* traces_dev, double* misfit_host, void* stream) {
+    FWI_REQUIRE(p && p->model_set, "fwi_fd2d_gradient: set the model first");
+    FWI_REQUIRE((wavelet_dev || p->nsrc == 0) && (obs_dev || p->nrec == 0) && grad_dev && nt >= 1, "fwi_fd2d_gradient: NULL argument or nt < 1");
+    FWI_REQUIRE((p->nsrc >= 1 && p->nrec >= 1) || p->z_own1 > 0, "fwi_fd2d_gradient: geometry needs at least one source and one receiver");
+    DeviceGuard g(p->device);
+    cudaStream_t user = (cudaStream_t)stream;
+    int seg = nt, nseg = 1, rc;
+    if ((rc = prepare_gradient(p, nt, seg, nseg))) return rc;
+    const size_t ntr = (size_t)nt * p->nrec;
 
     if ((rc = enter(p, user))) return rc;
     if (nt * p->nsrc) FWI_CUDA(cudaMemcpyAsync(p->wav, wavelet_dev, (size_t)nt * p->nsrc * sizeof(float), cudaMemcpyDeviceToDevice, p->work));

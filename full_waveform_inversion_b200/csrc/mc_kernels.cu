@@ -10,6 +10,7 @@
 // share one sample group and split the traces.
 // The path is FP32-FMA bound (G is ~0.4 MB and L2/L1 resident; ~40-80 B of HBM traffic per sample).
 #include "common.cuh"
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -688,10 +689,14 @@ __global__ void mc_prepare_kernel(const double* __restrict__ raw, int K, int C, 
     double v = 0.0;
     if (t >= 0 && t < T) {
         const int sh = shift ? shift[k] : 0;
-        int src = (t - sh) % T;                                     // np.roll(x, sh)[t] = x[(t - sh) mod T]   (FWI:97)
-        if (src < 0) src += T;
-        v = raw[(((int64_t)k * C + c) * T + src) * NM + med];
-        if (shift && zero_head && t < sh) v = 0.0;                  // FWI:98-99
+        if (sh == INT_MIN) v = 0.0;                                 // fewer shifts than traces: FWI:95-96 fills only the given ones
+        else {
+            int src = (t - sh) % T;                                 // np.roll(x, sh)[t] = x[(t - sh) mod T]   (FWI:97)
+            if (src < 0) src += T;
+            v = raw[(((int64_t)k * C + c) * T + src) * NM + med];
+            // FWI:98-99 zeroes the slice [0:sh]; for a negative shift that slice is everything but the last |sh| samples
+            if (shift && zero_head && t < (sh >= 0 ? sh : max(0, T + sh))) v = 0.0;
+        }
     }
     if (scale1 != 1.0) v *= scale1;
     if (scale2 != 1.0) v *= scale2;

@@ -35,10 +35,10 @@ def prepare_green_functions(raw, manual_indices_time_shift=(), cut_phase_start_v
     raw_d = torch.from_numpy(raw).to(dev)
     shift_d = cut_d = None
     if len(manual_indices_time_shift) > 0:
-        sh = np.zeros(K, dtype=np.int32)
-        sh[: len(manual_indices_time_shift)] = np.asarray(manual_indices_time_shift, dtype=np.int32)   # FWI:96 loops over the given shifts
-        if len(manual_indices_time_shift) < K:
-            raise ValueError("manual_indices_time_shift must have one entry per trace (got %d for %d traces)" % (len(manual_indices_time_shift), K))
+        if len(manual_indices_time_shift) > K:
+            raise IndexError("manual_indices_time_shift has %d entries for %d traces (FWI:97 indexes past the array)" % (len(manual_indices_time_shift), K))
+        sh = np.full(K, np.iinfo(np.int32).min, dtype=np.int32)     # sentinel: trace left zero, as FWI:95-96 does for missing shifts
+        sh[: len(manual_indices_time_shift)] = np.asarray(manual_indices_time_shift, dtype=np.int32)
         shift_d = torch.from_numpy(sh).to(dev)
     Tout = T
     if len(cut_phase_start_vals) > 0:

@@ -191,6 +191,9 @@ int fwi_fd2d_wavefield(fwi_fd2d* plan, int which, float* out_dev, void* stream);
 int fwi_fd2d_gradient(fwi_fd2d* plan, const float* wavelet_dev, const float* obs_dev, int nt, float* grad_dev,
                       float* traces_dev, double* misfit_host, void* stream);
 int64_t fwi_fd2d_launch_count(fwi_fd2d* plan);
+/* Allocate what fwi_fd2d_forward (gradient = 0) or fwi_fd2d_gradient (1) over nt steps will need with the current
+ * geometry, without launching anything (allocations synchronise the device: keep them out of timed regions). */
+int fwi_fd_reserve(fwi_fd2d* plan, int nt, int gradient);
 
 /* 3-D plans (nz x ny x nx, x contiguous; fd_oracle works in any dimension).  A 3-D plan is used with the same
  * fwi_fd2d_set_model / _forward / _gradient / _wavefield / _set_memory_limit / _set_graphs / _destroy entry points

@@ -239,6 +239,10 @@ def main():
             "prep_d": dict(itype="DC", kw=dict(manual_indices_time_shift_MT=sh_mt, cut_phase_start_vals=cuts, cut_phase_length=25,
                                                invert_for_ratio_of_multiple_media_greens_func_switch=True, green_func_fnames_split_index=K)),
             "prep_e": dict(itype="DC_single_force_no_coupling", kw=dict()),
+            # loader quirks (FWI:94-101): a negative shift zeroes [0:shift] = everything but the last |shift| samples; fewer
+            # shifts than traces leaves the remaining traces' Green's functions zero
+            "prep_f": dict(itype="full_mt", kw=dict(manual_indices_time_shift_MT=[-3, 0, 5, -2, 7])),
+            "prep_g": dict(itype="single_force", kw=dict(manual_indices_time_shift_SF=[3, 1])),
         }
         for key, c in cases.items():
             multi = c["kw"].get("invert_for_ratio_of_multiple_media_greens_func_switch", False)

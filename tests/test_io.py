@@ -32,6 +32,9 @@ CASES = {
                                     cut_phase_length=25, invert_for_ratio_of_multiple_media_greens_func_switch=True,
                                     green_func_fnames_split_index=5)),
     "prep_e": ("DC_single_force_no_coupling", lambda g: dict()),
+    # loader quirks (FWI:94-101): negative shifts zero all but the last |shift| samples; missing shifts leave zero traces
+    "prep_f": ("full_mt", lambda g: dict(manual_indices_time_shift_MT=[-3, 0, 5, -2, 7])),
+    "prep_g": ("single_force", lambda g: dict(manual_indices_time_shift_SF=[3, 1])),
 }
 
 
@@ -49,6 +52,10 @@ def test_oracle_preparation_matches_reference(golden_a):
     mt2 = np.stack([mt, np.transpose(g["prep_file_mt2"], (0, 2, 1))], -1)
     d = orc.prepare_green_functions(mt2, g["prep_sh_mt"], g["prep_cuts"], 25, scale1=1e3, scale2=1e7)
     assert np.array_equal(d, g["prep_d_G"])
+    f = orc.prepare_green_functions(mt, [-3, 0, 5, -2, 7], scale1=1e3, scale2=1e7)
+    assert np.array_equal(f, g["prep_f_G"]) and np.count_nonzero(f[0, :, :-3]) == 0 and np.count_nonzero(f[0, :, -3:]) > 0
+    gg = orc.prepare_green_functions(sf, [3, 1], scale2=1e7)
+    assert np.array_equal(gg, g["prep_g_G"]) and np.count_nonzero(gg[2:]) == 0
 
 
 HYP = """NLLOC "loc" "LOCATED" "Location completed."
@@ -147,3 +154,53 @@ def test_run_end_to_end(golden_a, tmp_path):
     want = orc.forward_model(G * 1e7, best)                      # the loaders' unit factors: files hold G (MT / 1e3), loaded = G * 1e7
     got = np.stack([wfs[lab]["synth_wf"] for lab in labels])
     assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_phase_labels", [False, True])
+def test_run_multi_medium_inversion_end_to_end(tmp_path, with_phase_labels):
+    """`run_multi_medium_inversion` (FWI:1037-1158): two sets of Green's-function files -> (K,C,T,2) -> LSQ on the 50/50 mix
+    (FWI:1059-1063) -> Monte-Carlo with media-ratio rows -> files; the most likely waveforms use the sample's own ratio(s)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from full_waveform_inversion_b200 import io as fio
+    K, T = 6, 96
+    d, G2, _ = orc.synthetic_inputs(K=K, C=9, T=T, seed=9, n_media=2)
+    G2 = G2 * 1e-7
+    data_dir = tmp_path / "data"
+    data_dir.mkdir()
+    names = {"real": [], "mt": [], "sf": []}
+    for k in range(K):
+        np.savetxt(data_dir / ("real_%d.txt" % k), d[k], fmt="%.17e")
+        names["real"].append("real_%d.txt" % k)
+    for medium in (0, 1):                                        # medium-1 file names first, then medium 2 (split index = K)
+        for k in range(K):
+            np.savetxt(data_dir / ("mt_%d_m%d.txt" % (k, medium)), (G2[k, :6, :, medium] / 1e3).T, fmt="%.17e")
+            np.savetxt(data_dir / ("sf_%d_m%d.txt" % (k, medium)), G2[k, 6:, :, medium].T, fmt="%.17e")
+            names["mt"].append("mt_%d_m%d.txt" % (k, medium))
+            names["sf"].append("sf_%d_m%d.txt" % (k, medium))
+    hyp = tmp_path / "loc.hyp"
+    hyp.write_text(HYP)
+    out = tmp_path / "out"
+    labels = ["S%d, Z" % k for k in range(K)]
+    phases = ["P", "S", "surface", "P", "S", "S"] if with_phase_labels else []
+    itype = "single_force_crack_no_coupling"
+    MTs, MTp, MTp_abs = fio.run_multi_medium_inversion(
+        str(data_dir), str(out), names["real"], names["mt"], names["sf"], labels, itype, False, False, 3000, "VR", [], [], str(hyp),
+        return_absolute_similarity_values_switch=True, green_func_fnames_split_index=K, green_func_phase_labels=phases, seed=5)
+    nfrac = 3 if with_phase_labels else 1
+    assert MTs.shape == (9 + 1 + nfrac, 3000) and abs(MTp.sum() - 1.0) < 1e-5
+    uid = "20180214185538216400"
+    assert os.path.exists(out / (uid + "_FW_%s.pkl" % itype)) and os.path.exists(out / ("least_squares_result/" + uid + "_FW_%s.pkl" % itype))
+    j = int(np.argmax(MTp))
+    fr = MTs[10:, j]
+    G_loaded = G2 * 1e7
+    pidx = np.array([("P", "S", "surface").index(x) for x in phases]) if with_phase_labels else None
+    want = orc.forward_model(orc.mix_media(G_loaded, fr if with_phase_labels else fr[0], pidx), MTs[:9, j])
+    wfs = pickle.load(open(out / (uid + "_FW_%s.wfs" % itype), "rb"))
+    got = np.stack([wfs[lab]["synth_wf"] for lab in labels])
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-5
+    # the sample's likelihood is what the oracle gives for that source and those ratios
+    s = orc.compare_synth_to_real_waveforms(d, want, "VR", False, False)
+    assert abs(MTp_abs[j] - orc.likelihood(s)) <= 2e-5

@@ -331,3 +331,70 @@ def test_wide_kernel_two_media(fw, monkeypatch, metric, norm, simul, three):
         d, orc.forward_model(orc.mix_media(G2, fr[i] if three else fr[i, 0], phase_index), Ms[i]), metric, norm, simul) for i in pick])
     np.testing.assert_allclose(wide[pick], want, rtol=0, atol=2e-6)
     prob.close()
+
+
+@pytest.mark.parametrize("three", [False, True])
+@pytest.mark.parametrize("itype", ["full_mt", "single_force_crack_no_coupling"])
+def test_monte_carlo_driver_two_media(fw, itype, three):
+    """Row a14 through the PUBLIC entry point (FWI:786 with invert_for_ratio...=True): on-device media-fraction draws
+    (FWI:715-731), appended row order C source rows | amp-frac row (combined types, FWI:851-852) | 1 or 3 media-ratio
+    rows (FWI:853-862, P / S / surface order of FWI:719-721); every sample re-scored by the oracle's explicit mixing."""
+    C = orc.N_COMPONENTS[itype]
+    K, T = 9, 96
+    d, G2, _ = orc.synthetic_inputs(K=K, C=C, T=T, seed=5, n_media=2)
+    labels = (["P", "S", "surface"] * 3) if three else []
+    phase_index = np.array([("P", "S", "surface").index(x) for x in labels]) if three else None
+    amp = float(np.linalg.norm(orc.perform_inversion(d, 0.5 * G2[..., 0] + 0.5 * G2[..., 1])))
+    N = 1501
+    MTs, MTp, L = fw.perform_monte_carlo_sampled_waveform_inversion(
+        d, G2, N, amp, itype, "VR", False, False, 1, return_absolute_similarity_values_switch=True,
+        invert_for_ratio_of_multiple_media_greens_func_switch=True, green_func_phase_labels=labels,
+        num_phase_types_for_media_ratios=3 if three else 0, seed=77)
+    combined = itype in orc.COMBINED_TYPES
+    nfrac = 3 if three else 1
+    rows = C + (1 if combined else 0) + nfrac
+    assert MTs.shape == (rows, N) and MTp.shape == (N,) and L.shape == (N,)
+    fr = MTs[rows - nfrac:]                                               # the media-ratio rows come last
+    assert fr.min() >= 0.0 and fr.max() < 1.0 and np.all(np.abs(fr.mean(1) - 0.5) < 0.04)
+    if three:                                                             # three independent draws per sample (FWI:719-721)
+        assert abs(np.corrcoef(fr)[0, 1]) < 0.1 and abs(np.corrcoef(fr)[1, 2]) < 0.1
+    if combined:
+        f = MTs[C]
+        assert 0.0 < f.min() and f.max() < 1.0 and abs(f.mean() - 0.5) < 0.04
+    sim = np.empty(N)
+    for i in range(N):
+        Gi = orc.mix_media(G2, fr[:, i] if three else fr[0, i], phase_index)
+        sim[i] = orc.compare_synth_to_real_waveforms(d, orc.forward_model(Gi, MTs[:C, i]), "VR", False, False)
+    np.testing.assert_allclose(L, orc.likelihood(sim), rtol=2e-5)
+    np.testing.assert_allclose(MTp, orc.bayes_normalise(orc.likelihood(sim)), rtol=4e-5)
+    assert abs(MTp.sum() - 1.0) < 1e-5
+    # the most likely sample is re-synthesised with its own ratio(s) (FWI:974-1020)
+    j = int(np.argmax(MTp))
+    best = fw.get_synth_forward_model_most_likely_result(MTs, MTp, G2, itype, True, labels, 3 if three else 0)
+    want = orc.forward_model(orc.mix_media(G2, fr[:, j] if three else fr[0, j], phase_index), MTs[:C, j])
+    assert np.linalg.norm(best - want) / np.linalg.norm(want) <= 1e-5
+
+
+def test_per_call_entry_points_reuse_their_device_context(fw):
+    """The reference calls forward_model / compare_synth_to_real_waveforms once per sample (FWI:752-755): the drop-in
+    shims keep the device context of the last (G, d) they saw, so such a loop costs well under a millisecond a call."""
+    import time
+    d, G, _ = orc.synthetic_inputs(K=21, C=9, T=128, seed=2)
+    Ms = np.random.default_rng(0).standard_normal((1000, 9))
+    fw.forward_model(G, Ms[0]); fw.get_unnormallised_prob_for_specific_soln(d, G, Ms[0], "VR", False, False)
+    t0 = time.perf_counter()
+    out = [fw.get_unnormallised_prob_for_specific_soln(d, G, Ms[i], "VR", False, False) for i in range(1000)]
+    t_unp = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    syn = [fw.forward_model(G, Ms[i]) for i in range(300)]
+    t_fwd = time.perf_counter() - t0
+    assert t_unp < 1.0, t_unp
+    assert t_fwd < 1.0, t_fwd
+    np.testing.assert_allclose(out, orc.similarity_batch(d, G, Ms, "VR", False, False), atol=1e-6)
+    assert np.linalg.norm(syn[7] - orc.forward_model(G, Ms[7])) / np.linalg.norm(syn[7]) <= 1e-6
+    # a changed array must not hit the cache: same object, new contents
+    G2 = G.copy()
+    a = fw.forward_model(G2, Ms[0])
+    G2 *= 2.0
+    b = fw.forward_model(G2, Ms[0])
+    assert np.linalg.norm(b - 2.0 * a) / np.linalg.norm(b) <= 1e-6
