@@ -167,8 +167,9 @@ class Propagator:
             check(self._lib.fwi_fd2d_wavefield(self._h, which, ptr(out), current_stream()))
         return out
 
-    def gradient(self, wavelet, observed, grad=None, want_traces=False, want_misfit=True):
-        """One shot: (J, grad (nz,nx) accumulated into `grad`, traces|None)  (fd_oracle.Problem.misfit_and_gradient)."""
+    def gradient(self, wavelet, observed, grad=None, want_traces=False, want_misfit=True, traces_out=None):
+        """One shot: (J, grad (nz,nx) accumulated into `grad`, traces|None)  (fd_oracle.Problem.misfit_and_gradient).
+        `traces_out`: caller-owned (nt, nrec) float32 buffer for the synthetics (no allocation inside the call)."""
         w = self._wavelet(wavelet)
         nt = w.shape[0]
         obs = _dev_f32(observed, self.torch_device)
@@ -176,7 +177,8 @@ class Propagator:
             raise ValueError("observed traces %s do not match (nt=%d, nrec=%d)" % (tuple(obs.shape), nt, self.nrec))
         if grad is None:
             grad = torch.zeros(self.shape, dtype=torch.float32, device=self.torch_device)
-        traces = torch.empty((nt, self.nrec), dtype=torch.float32, device=self.torch_device) if want_traces else None
+        traces = traces_out if traces_out is not None else \
+            (torch.empty((nt, self.nrec), dtype=torch.float32, device=self.torch_device) if want_traces else None)
         J = c_double(0.0)
         with torch.cuda.device(self.device):
             check(self._lib.fwi_fd2d_gradient(self._h, ptr(w), ptr(obs), nt, ptr(grad), ptr(traces),

@@ -165,16 +165,19 @@ def _local_slabs(ac, shape, h, dt, nabs, nslab, v, src, rec, **kw):
 
 
 def _run_ranks(slabs, fn):
-    """One host thread and one CUDA stream per emulated rank (the kernels of neighbouring slabs wait for each other)."""
+    """One host thread and one CUDA stream per emulated rank (the kernels of neighbouring slabs wait for each other).
+    `fn` must not allocate device memory: in ONE process cudaMalloc (also torch's caching allocator growing a pool)
+    can wait for the device, i.e. for a neighbour's kernel that is itself waiting for this thread's launch.  Ranks of a
+    real run are separate processes on separate GPUs."""
     import threading
     import torch
-    out, err = [None] * len(slabs), []
+    err = []
 
     def work(r):
         try:
-            with torch.cuda.stream(torch.cuda.Stream()):
-                out[r] = fn(r, slabs[r])
-                torch.cuda.current_stream().synchronize()
+            with torch.cuda.stream(slabs[r]["stream"]):
+                fn(r, slabs[r])
+                slabs[r]["stream"].synchronize()
         except Exception as exc:                                  # noqa: BLE001
             err.append(exc)
     th = [threading.Thread(target=work, args=(r,)) for r in range(len(slabs))]
@@ -184,7 +187,6 @@ def _run_ranks(slabs, fn):
         t.join()
     if err:
         raise err[0]
-    return out
 
 
 @pytest.mark.parametrize("nslab,graphs,limit_planes,edge_rec", [(2, True, 0, True), (3, True, 0, True), (3, False, 0, True), (3, True, 34, True),
@@ -223,30 +225,43 @@ def test_peer_memory_slab_protocol_on_one_gpu(ac, nslab, graphs, limit_planes, e
         s["p"].reserve(nt, gradient=False)     # i.e. for a neighbour's kernel that is itself waiting for this plan's launch
         s["p"].reserve(nt, gradient=True)      # (ranks of a real run are separate processes on separate GPUs)
     wav_t, obs_t = torch.tensor(wav, dtype=torch.float32, device="cuda"), obs
+    for s in slabs:                   # every buffer the ranks touch exists before they start (see _run_ranks)
+        s["stream"] = torch.cuda.Stream()
+        s["w"] = wav_t[:, s["src_ids"]].contiguous()
+        s["obs"] = obs_t[:, s["rec_ids"]].contiguous()
+        s["tr"] = torch.zeros((nt, len(s["rec_ids"])), dtype=torch.float32, device="cuda")
+        s["g"] = torch.zeros(s["p"].shape, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
 
     def fwd(r, s):
-        return s["p"].forward(wav_t[:, s["src_ids"]].contiguous()).cpu().numpy()
+        s["p"].forward(s["w"], out=s["tr"])
 
     def grad(r, s):
-        J, g, tr = s["p"].gradient(wav_t[:, s["src_ids"]].contiguous(), obs_t[:, s["rec_ids"]].contiguous(), want_traces=True, want_misfit=False)
-        return g.cpu().numpy(), tr.cpu().numpy()
+        s["g"].zero_()
+        s["p"].gradient(s["w"], s["obs"], grad=s["g"], traces_out=s["tr"], want_misfit=False)
 
     lib = _lib.load()
-    for rep in range(2):                                           # second pass replays the cached graphs
-        got = np.zeros_like(want_tr)
-        for s, tr in zip(slabs, _run_ranks(slabs, fwd)):
-            got[:, s["rec_ids"]] = tr
-        assert np.array_equal(got, want_tr)
-        res = _run_ranks(slabs, grad)
-        got = np.zeros_like(want_tr)
-        g_got = np.concatenate([g[s["up"]: s["up"] + s["n"]] for s, (g, _) in zip(slabs, res)])
-        for s, (_, tr) in zip(slabs, res):
-            got[:, s["rec_ids"]] = tr
-        assert np.array_equal(got, want_tr)
+
+    def no_timeouts():
         for s in slabs:
             e = ctypes.c_int(0)
             _lib.check(lib.fwi_fd_slab_error(s["p"]._h, ctypes.byref(e)))
             assert e.value == 0, "a step kernel timed out waiting for its neighbour"
+
+    for rep in range(2):                                           # second pass replays the cached graphs
+        got = np.zeros_like(want_tr)
+        _run_ranks(slabs, fwd)
+        no_timeouts()
+        for s in slabs:
+            got[:, s["rec_ids"]] = s["tr"].cpu().numpy()
+        assert np.array_equal(got, want_tr)
+        _run_ranks(slabs, grad)
+        no_timeouts()
+        got = np.zeros_like(want_tr)
+        g_got = np.concatenate([s["g"][s["up"]: s["up"] + s["n"]].cpu().numpy() for s in slabs])
+        for s in slabs:
+            got[:, s["rec_ids"]] = s["tr"].cpu().numpy()
+        assert np.array_equal(got, want_tr)
         if limit_planes:
             assert rel_l2(g_got, g_want) <= 1e-6
         else:
