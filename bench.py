@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--cpu-sample-nt", type=int, default=600)
+    ap.add_argument("--force-dist", action="store_true", help="diagnostic: initialise NCCL even with one rank")
     return ap.parse_args()
 
 
@@ -204,7 +205,7 @@ def track_a_numbers(device, dist=None, cpu=True):
     dev = torch.device("cuda", device)
     # ---- N GPUs: contiguous sample ranges per rank (FWI:833-834 order), one all-reduce of sum L (FWI:847)
     if dist:
-        N = 4_000_000
+        N = 16_000_000
         tot = torch.zeros(1, dtype=torch.float64, device=dev)
 
         def shard(r):
@@ -460,8 +461,14 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    if world > 1 or args.force_dist:
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            dist.init_process_group("nccl", device_id=dev, rank=0, world_size=1)
+            dist.all_reduce(torch.zeros(1, device=dev))         # force communicator creation
+        else:
+            dist.init_process_group("nccl", device_id=dev)
     D = dist if world > 1 else None
 
     w = workload(args)
@@ -530,9 +537,12 @@ def run_b200(args):
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     e1 = torch.cuda.Event(enable_timing=True)
     marks[0].record()
+    sync_each = os.environ.get("FWI_BENCH_SYNC") == "1"        # diagnostic: drain the GPU after every shot
     for k, i in enumerate(range(args.warmup, nrun)):
         one_step(i, False)
         marks[k + 1].record()                       # per-shot marks (no synchronisation: the CPU keeps enqueueing)
+        if sync_each:
+            torch.cuda.synchronize(dev)
     if world > 1:
         dist.all_reduce(grad)                       # one FWI gradient = sum over every rank's shots
     e1.record()

@@ -1313,7 +1313,13 @@ int fwi_fd_step(fwi_fd2d* p, int mode, int cur, const float* inj_vals_dev, float
     p->pdl_chain = false;             // caller-driven loop: other kernels (halo exchange, resets) sit between the steps
     FWI_REQUIRE(mode == 0 || (snap_index >= 0 && (size_t)(snap_index + 1) * p->plane() <= p->snap_steps), "fwi_fd_step: snapshot %lld not reserved", (long long)snap_index);
     DeviceGuard g(p->device);
-    if (p->geom_pending) { FWI_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, p->ev_geom, 0)); p->geom_pending = false; }
+    if (p->geom_pending) {
+        // (not while the caller captures a graph: it synchronised before starting the capture, and an event recorded
+        // outside a capture must not be waited for inside it)
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        FWI_CUDA(cudaStreamIsCapturing((cudaStream_t)stream, &cs));
+        if (cs == cudaStreamCaptureStatusNone) { FWI_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, p->ev_geom, 0)); p->geom_pending = false; }
+    }
     const int base = (mode == STEP_ADJ) ? 4 : 0;
     float* snap = (mode == 0) ? nullptr : p->snap + (size_t)snap_index * p->plane();
     int rc = launch_step(p, mode, base + cur, p->fld[base + (cur ^ 1)], mode == STEP_ADJ ? &p->rec : &p->src, inj_vals_dev,
@@ -1422,16 +1428,26 @@ int fwi_fd_finalize_gradient(fwi_fd2d* p, float* grad_dev, void* stream) {
 }
 
 
+// Small persistent device scratch per GPU for the plan-less reductions below.  (cudaMallocAsync / cudaFreeAsync around a
+// synchronising call hands the block back to the driver every time: measured 8 ms per call with 25 GB allocated, which
+// was 40 % of a config-3 line search.)  One caller per device at a time: both users synchronise before returning.
+static void* device_scratch() {
+    static void* scratch[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!scratch[dev] && cudaMalloc(&scratch[dev], 256) != cudaSuccess) { cudaGetLastError(); scratch[dev] = nullptr; }
+    return scratch[dev];
+}
+
 int fwi_fd_misfit(const float* syn_dev, const float* obs_dev, int64_t n, float* resid_dev, double* misfit_host, void* stream) {
     FWI_REQUIRE(syn_dev && obs_dev && resid_dev && misfit_host && n >= 0, "fwi_fd_misfit: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    double* dJ = nullptr;
-    FWI_CUDA(cudaMallocAsync(&dJ, sizeof(double), st));
+    double* dJ = (double*)device_scratch();
+    FWI_REQUIRE(dJ, "fwi_fd_misfit: no device scratch");
     FWI_CUDA(cudaMemsetAsync(dJ, 0, sizeof(double), st));
     if (n > 0) fd_residual_kernel<<<(unsigned)std::min<int64_t>(1024, (n + 255) / 256), 256, 0, st>>>(syn_dev, obs_dev, n, resid_dev, dJ);
     FWI_CUDA(cudaGetLastError());
     FWI_CUDA(cudaMemcpyAsync(misfit_host, dJ, sizeof(double), cudaMemcpyDeviceToHost, st));
-    FWI_CUDA(cudaFreeAsync(dJ, st));
     FWI_CUDA(cudaStreamSynchronize(st));
     return FWI_OK;
 }
@@ -1446,14 +1462,14 @@ int fwi_fd_model_update(float* v_dev, const float* grad_dev, int64_t n, float st
 int fwi_fd_absmax(const float* x_dev, int64_t n, float* out_host, void* stream) {
     FWI_REQUIRE(x_dev && out_host && n >= 1, "fwi_fd_absmax: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned int* d = nullptr;
-    FWI_CUDA(cudaMallocAsync(&d, sizeof(unsigned int), st));
+    unsigned int* d = (unsigned int*)device_scratch();
+    FWI_REQUIRE(d, "fwi_fd_absmax: no device scratch");
+    d += 16;                                             // its own slot (the misfit uses the first 8 bytes)
     FWI_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned int), st));
     fd_absmax_kernel<<<(unsigned)std::min<int64_t>(1024, (n + 255) / 256), 256, 0, st>>>(x_dev, n, d);
     FWI_CUDA(cudaGetLastError());
     unsigned int h = 0;
     FWI_CUDA(cudaMemcpyAsync(&h, d, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-    FWI_CUDA(cudaFreeAsync(d, st));
     FWI_CUDA(cudaStreamSynchronize(st));
     memcpy(out_host, &h, sizeof(float));
     return FWI_OK;
