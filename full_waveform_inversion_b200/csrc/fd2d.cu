@@ -318,7 +318,7 @@ struct GraphEntry {
 struct fwi_fd2d {
     int device = 0, nz = 0, ny = 1, nx = 0, px = 0, nabs = 0;   // ny == 1: 2-D plan; rows() = nz * ny
     float h = 0, dt = 0, alpha = 0;
-    int tiles_y = 1, zchunk = 0, nzch = 1;                      // 3-D tiling: 128 x 16 columns, z chunks
+    int tiles_y = 1, zchunk = 0, nzch = 1, by = 16;             // 3-D tiling: 128 x by columns (by = 16 or 14), z chunks
     float* gy = nullptr;
     CUtensorMap tm3[8], tm3_old[8], tm3_m;
     // slab decomposition over peer memory (3-D only)
@@ -381,26 +381,35 @@ static void drop_graphs(fwi_fd2d* p) {
 
 static int make_tmaps3(fwi_fd2d* p) {
     p->tiles_x = (p->nx + k3BX - 1) / k3BX;
-    p->tiles_y = (p->ny + k3BY - 1) / k3BY;
-    // z chunks: one CTA per SM is resident (170 KB of plane rings), every chunk re-reads 8 halo planes; pick the chunk
-    // count that minimises  waves x (planes per chunk + 8)
+    // Tile height and z chunks.  One CTA per SM is resident (170 KB of plane rings) and every chunk re-reads 8 halo planes;
+    // for a tile height BY and a chunk count the model cost is  waves x (planes per chunk + 8) x BY.  Single-GPU plans keep
+    // BY = 16 (0.96 of the HBM roofline at 512^3); peer-memory slabs, whose few chunks make the last wave's tail expensive,
+    // take the cheaper of 16 and 14 (512-wide planes: 4 x 37 = 148 tiles of 14 rows, one per SM).  FWI_FD3D_BY overrides.
     {
-        const int txy = p->tiles_x * p->tiles_y;
-        int best = 1;
-        double best_cost = 1e300;
         const int nzo = (p->z_own1 > 0 ? p->z_own1 : p->nz) - p->z_own0;
         // peer-memory slabs: with a lower neighbour the last chunk marches downwards, so that both boundaries are pushed
         // early - that needs at least two chunks; and a 4-plane boundary must not straddle two chunks
         const int min_ch = (p->peer_arena[1] && nzo >= 4 * kHalo) ? 2 : 1;
-        for (int nzch = min_ch; nzch <= std::max(min_ch, nzo / 8); ++nzch) {
-            const int zc = (nzo + nzch - 1) / nzch;
-            const int real = (nzo + zc - 1) / zc;
-            if (real < min_ch) continue;
-            if (p->peers() && nzo - (real - 1) * zc < kHalo) continue;
-            const double waves = std::ceil((double)txy * real / p->sm_count);
-            const double cost = waves * (zc + 2 * kHalo);
-            if (cost < best_cost - 1e-9) { best_cost = cost; best = nzch; }
+        int force_by = 0;
+        if (const char* e = getenv("FWI_FD3D_BY")) force_by = atoi(e);
+        int best_by = 16, best = 1;
+        double best_cost = 1e300;
+        for (int by : {16, 14}) {
+            if (force_by ? by != force_by : (by != 16 && !p->peers())) continue;
+            const int txy = p->tiles_x * ((p->ny + by - 1) / by);
+            for (int nzch = min_ch; nzch <= std::max(min_ch, nzo / 8); ++nzch) {
+                const int zc = (nzo + nzch - 1) / nzch;
+                const int real = (nzo + zc - 1) / zc;
+                if (real < min_ch) continue;
+                if (p->peers() && nzo - (real - 1) * zc < kHalo) continue;
+                const double waves = std::ceil((double)txy * real / p->sm_count);
+                const double cost = waves * (zc + 2 * kHalo) * by;
+                if (cost < best_cost - 1e-9) { best_cost = cost; best = nzch; best_by = by; }
+            }
         }
+        if (force_by == 14 || force_by == 16) best_by = force_by;
+        p->by = best_by;
+        p->tiles_y = (p->ny + p->by - 1) / p->by;
         p->zchunk = (nzo + best - 1) / best;
         p->nzch = (nzo + p->zchunk - 1) / p->zchunk;
         p->last_desc = (p->peer_arena[1] && p->nzch >= 2) ? 1 : 0;
@@ -408,11 +417,11 @@ static int make_tmaps3(fwi_fd2d* p) {
     for (int i = 0; i < 8; ++i) {
         const uint64_t dims[3] = {(uint64_t)p->nx, (uint64_t)p->ny, (uint64_t)p->nz};
         const uint64_t strides[2] = {(uint64_t)p->px * sizeof(float), (uint64_t)p->px * p->ny * sizeof(float)};
-        const uint32_t box[3] = {(uint32_t)k3SX, (uint32_t)k3SY, 1u};
+        const uint32_t box[3] = {(uint32_t)k3SX, (uint32_t)(p->by + 2 * kHalo), 1u};
         int rc = encode_tiled_f32(&p->tm3[i], p->fld[i], 3, dims, strides, box);
         if (rc) return rc;
         const uint64_t dims_p[3] = {(uint64_t)p->px, (uint64_t)p->ny, (uint64_t)p->nz};
-        const uint32_t box_o[3] = {(uint32_t)k3BX, (uint32_t)k3BY, 1u};
+        const uint32_t box_o[3] = {(uint32_t)k3BX, (uint32_t)p->by, 1u};
         rc = encode_tiled_f32(&p->tm3_old[i], p->fld[i], 3, dims_p, strides, box_o);
         if (rc) return rc;
         if (i == 0 && (rc = encode_tiled_f32(&p->tm3_m, p->m, 3, dims_p, strides, box_o))) return rc;
@@ -450,7 +459,7 @@ static int make_tmaps(fwi_fd2d* p) {
 
 // bin that owns grid point (z, x): the CTA tile (tiled variant) or the warp whose row-unit range holds it
 static int owner_bin(const fwi_fd2d* p, int z, int y, int x) {
-    if (p->ny > 1) return ((std::max(0, z - p->z_own0) / p->zchunk) * p->tiles_y + y / k3BY) * p->tiles_x + x / k3BX;
+    if (p->ny > 1) return ((std::max(0, z - p->z_own0) / p->zchunk) * p->tiles_y + y / p->by) * p->tiles_x + x / k3BX;
     return (z / p->bz) * p->tiles_x + x / kBX;
 }
 
@@ -610,13 +619,19 @@ static int launch_step3(fwi_fd2d* p, int mode, int cur, float* oldnew, const Poi
     a.flag_peer_up = p->peer_arena[0] ? (int*)((char*)p->peer_arena[0] + p->peer_flags_off[0]) + kSyncFlagDn : nullptr;   // I am its lower neighbour
     a.flag_peer_dn = p->peer_arena[1] ? (int*)((char*)p->peer_arena[1] + p->peer_flags_off[1]) + kSyncFlagUp : nullptr;   // I am its upper neighbour
     a.timeout_cycles = p->slab_timeout_cycles;
-    const dim3 grid(p->tiles_x, p->tiles_y, p->nzch), block((k3CW + k3Prod) * 32);
-    const size_t smem = ((size_t)k3NP * k3PlaneFloats + (size_t)k3NO * 2 * k3OmFloats) * sizeof(float);
+    const dim3 grid(p->tiles_x, p->tiles_y, p->nzch);
     // (programmatic dependent launch was measured on this kernel too: 2 % at 128^3, nothing from 256^3 up - not used)
-    if (mode == STEP_FWD) fd3d_step_kernel<STEP_FWD><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
-    else if (mode == STEP_FWD_SAVE) fd3d_step_kernel<STEP_FWD_SAVE><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
-    else if (mode == STEP_ADJ2) fd3d_step_kernel<STEP_ADJ2><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
-    else fd3d_step_kernel<STEP_ADJ><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);
+#define FD3_LAUNCH(BYV)                                                                                                         \
+    do {                                                                                                                        \
+        const dim3 block(T3<BYV>::Threads);                                                                                     \
+        const size_t smem = T3<BYV>::Smem;                                                                                      \
+        if (mode == STEP_FWD) fd3d_step_kernel<STEP_FWD, BYV><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);               \
+        else if (mode == STEP_FWD_SAVE) fd3d_step_kernel<STEP_FWD_SAVE, BYV><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a); \
+        else if (mode == STEP_ADJ2) fd3d_step_kernel<STEP_ADJ2, BYV><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);        \
+        else fd3d_step_kernel<STEP_ADJ, BYV><<<grid, block, smem, st>>>(p->tm3[cur], p->tm3_old[oi], p->tm3_m, a);                               \
+    } while (0)
+    if (p->by == 14) FD3_LAUNCH(14); else FD3_LAUNCH(16);
+#undef FD3_LAUNCH
     return FWI_OK;
 }
 
@@ -1004,11 +1019,13 @@ static int init_plan(fwi_fd2d* p, int device, int nz, int ny, int nx, float h, f
     int rc = make_tmaps(p);
     if (rc) return rc;
     if ((rc = tb2_attrs<32, 8>()) || (rc = tb2_attrs<24, 8>()) || (rc = tb2_attrs<16, 8>())) return rc;
-    const int smem3 = (k3NP * k3PlaneFloats + k3NO * 2 * k3OmFloats) * (int)sizeof(float);
-    FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-    FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-    FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-    FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_ADJ2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+#define FD3_ATTR(BYV)                                                                                                                        \
+    FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_FWD, BYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3<BYV>::Smem));        \
+    FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_FWD_SAVE, BYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3<BYV>::Smem));   \
+    FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_ADJ, BYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3<BYV>::Smem));        \
+    FWI_CUDA(cudaFuncSetAttribute(fd3d_step_kernel<STEP_ADJ2, BYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3<BYV>::Smem))
+    FD3_ATTR(16); FD3_ATTR(14);
+#undef FD3_ATTR
     return FWI_OK;
 }
 

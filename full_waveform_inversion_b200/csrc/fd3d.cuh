@@ -34,12 +34,23 @@ namespace fwi {
 #ifndef FD3_SPLIT
 #define FD3_SPLIT 1
 #endif
-constexpr int k3BX = 128, k3BY = 16, k3NP = FD3_NP;                  // tile, ring depth
-constexpr int k3RPW = FD3_RPW, k3CW = k3BY / k3RPW;                  // y rows per consumer warp, consumer warps
-constexpr int k3SX = k3BX + 2 * kHalo, k3SY = k3BY + 2 * kHalo;     // 136 x 24
-constexpr int k3PlaneFloats = k3SX * k3SY;                          // 3264 floats = 13056 B (102 * 128)
-constexpr int k3NO = FD3_NO, k3OmLead = FD3_OMLEAD, k3Prod = 1 + FD3_SPLIT;                               // u_{n-1}/m plane ring depth; issued 3 planes before use
-constexpr int k3OmFloats = k3BX * k3BY;                             // 2048 floats = 8 KB per array per plane
+constexpr int k3BX = 128, k3NP = FD3_NP;                            // tile width, u_n ring depth
+constexpr int k3RPW = FD3_RPW;                                      // y rows per consumer warp
+constexpr int k3SX = k3BX + 2 * kHalo;                              // 136
+constexpr int k3NO = FD3_NO, k3OmLead = FD3_OMLEAD, k3Prod = 1 + FD3_SPLIT;   // u_{n-1}/m plane ring depth; issued 3 planes before use
+// The tile height BY is a template parameter: 16 rows (8 consumer warps) or 14 rows (7 consumer warps).  512-wide planes
+// give 4 x 32 = 128 tiles of 16 rows but 4 x 37 = 148 tiles of 14 rows - exactly one per SM, which removes the 25 % tail of
+// a second wave that only 108 CTAs fill (measured on 4-GPU slabs: 0.78 -> see DESIGN.md); fwi_fd2d picks per plan.
+template <int BY> struct T3 {
+    static constexpr int CW = BY / k3RPW;                           // consumer warps
+    static constexpr int SY = BY + 2 * kHalo;
+    static constexpr int PlaneFloats = k3SX * SY;                   // BY = 16: 3264 floats = 13056 B; BY = 14: 2992 floats = 11968 B
+    static constexpr int PlaneStride = (PlaneFloats + 31) / 32 * 32; // ring slots start on 128-byte lines (TMA destination alignment)
+    static constexpr int OmFloats = k3BX * BY;
+    static constexpr int Threads = (CW + k3Prod) * 32;
+    static constexpr size_t Smem = ((size_t)k3NP * PlaneStride + (size_t)k3NO * 2 * OmFloats) * sizeof(float);
+    static_assert(BY % k3RPW == 0 && (OmFloats * 4) % 128 == 0, "u_{n-1} / m planes must stay 128-byte multiples");
+};
 
 struct Step3DArgs {
     float* oldnew;
@@ -114,12 +125,13 @@ __global__ void fd3d_slab_sync_kernel(int* sync, int has_up, int has_dn, long lo
     }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(const __grid_constant__ CUtensorMap tm_cur,
+template <int MODE, int BY>
+__global__ void __launch_bounds__(T3<BY>::Threads, 1) fd3d_step_kernel(const __grid_constant__ CUtensorMap tm_cur,
                                                                        const __grid_constant__ CUtensorMap tm_old,
                                                                        const __grid_constant__ CUtensorMap tm_m, Step3DArgs a) {
+    constexpr int k3BY = BY, k3CW = T3<BY>::CW, k3PlaneFloats = T3<BY>::PlaneFloats, k3PlaneStride = T3<BY>::PlaneStride, k3OmFloats = T3<BY>::OmFloats;
     extern __shared__ __align__(128) float ring[];                   // [NP][SY][SX] u_n planes, then [NO][2][BY][BX] u_{n-1} / m planes
-    float* om_ring = ring + (size_t)k3NP * k3PlaneFloats;
+    float* om_ring = ring + (size_t)k3NP * k3PlaneStride;
     __shared__ __align__(8) uint64_t full_bar[k3NP], empty_bar[k3NP], om_full[k3NO], om_empty[k3NO];
     __shared__ int slab_state[4];                  // [0] step id of this launch, [1] abort, [2]/[3] consumer warps done with the upper / lower boundary
 
@@ -187,7 +199,7 @@ __global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(cons
                     const int slot = t % k3NP;
                     if (t >= k3NP) mbar_wait(&empty_bar[slot], ((t / k3NP) - 1) & 1);
                     mbar_expect_tx(&full_bar[slot], k3PlaneFloats * (uint32_t)sizeof(float));
-                    tma_load_3d(ring + (size_t)slot * k3PlaneFloats, &tm_cur, x0 - kHalo, y0 - kHalo, zbeg + zstep * (t - kHalo), &full_bar[slot]);
+                    tma_load_3d(ring + (size_t)slot * k3PlaneStride, &tm_cur, x0 - kHalo, y0 - kHalo, zbeg + zstep * (t - kHalo), &full_bar[slot]);
                 }
                 const int j = t - k3OmLead;
                 if (do_om && j >= 0 && j < nout) {
@@ -213,7 +225,7 @@ __global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(cons
 
         float4 win[k3RPW][9];
         auto own = [&](int p, int r) {                 // this lane's element of row r in ring plane p
-            return ld4(ring + (size_t)(p % k3NP) * k3PlaneFloats + (yl + r + kHalo) * k3SX + kHalo + 4 * lane);
+            return ld4(ring + (size_t)(p % k3NP) * k3PlaneStride + (yl + r + kHalo) * k3SX + kHalo + 4 * lane);
         };
         // prime with planes 0..7 (the four behind the first output plane and the first four); planes 0..3 are never
         // centre planes -> release them
@@ -262,7 +274,7 @@ __global__ void __launch_bounds__((k3CW + k3Prod) * 32, 1) fd3d_step_kernel(cons
             }
             // slab mode: the 4 owned planes next to a neighbour are also stored straight into its ghost planes (NVLink)
             const bool bu = a.peer_up && z < a.z_own0 + kHalo, bd = a.peer_dn && z >= a.z_own1 - kHalo;
-            const float* mid = ring + (size_t)(pmid % k3NP) * k3PlaneFloats;
+            const float* mid = ring + (size_t)(pmid % k3NP) * k3PlaneStride;
             float4 yc[8 + k3RPW];                        // rows yl-4 .. yl+3+RPW of the centre plane, this lane's float4
 #pragma unroll
             for (int k = 0; k < 8 + k3RPW; ++k) yc[k] = ld4(mid + (yl + k) * k3SX + kHalo + 4 * lane);

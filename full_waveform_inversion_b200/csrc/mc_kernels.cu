@@ -1264,21 +1264,38 @@ int fwi_mc_transform_draws(int type, const float* draws, int64_t ldn, int64_t N,
     return FWI_OK;
 }
 
+// Persistent per-device partials buffer for fwi_mc_reduce (a stream-ordered allocation around a synchronising call is
+// handed back to the driver every time, which costs milliseconds once tens of GB are allocated).  One caller per device
+// at a time: the call synchronises before it returns.
+static void* reduce_scratch(size_t bytes) {
+    static void* buf[64] = {};
+    static size_t cap[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (cap[dev] < bytes) {
+        if (buf[dev]) cudaFree(buf[dev]);
+        buf[dev] = nullptr; cap[dev] = 0;
+        if (cudaMalloc(&buf[dev], bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        cap[dev] = bytes;
+    }
+    return buf[dev];
+}
+
 int fwi_mc_reduce(const float* L, int64_t N, double* sum_host, int64_t* argmax_host, float* max_host, void* stream) {
     FWI_REQUIRE(L && N >= 1, "fwi_mc_reduce: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const int blocks = (int)std::min<int64_t>(1024, ceil_div(N, 1024));
-    double* psum; float* pmax; long long* parg;
-    FWI_CUDA(cudaMallocAsync(&psum, blocks * sizeof(double), st));
-    FWI_CUDA(cudaMallocAsync(&pmax, blocks * sizeof(float), st));
-    FWI_CUDA(cudaMallocAsync(&parg, blocks * sizeof(long long), st));
+    char* scratch = (char*)reduce_scratch(1024 * (sizeof(double) + sizeof(long long) + sizeof(float)));
+    FWI_REQUIRE(scratch, "fwi_mc_reduce: no device scratch");
+    double* psum = (double*)scratch;
+    long long* parg = (long long*)(scratch + 1024 * sizeof(double));
+    float* pmax = (float*)(scratch + 1024 * (sizeof(double) + sizeof(long long)));
     mc_reduce_kernel<<<blocks, 256, 0, st>>>(L, N, psum, pmax, parg);
     FWI_CUDA(cudaGetLastError());
     std::vector<double> hs(blocks); std::vector<float> hm(blocks); std::vector<long long> ha(blocks);
     FWI_CUDA(cudaMemcpyAsync(hs.data(), psum, blocks * sizeof(double), cudaMemcpyDeviceToHost, st));
     FWI_CUDA(cudaMemcpyAsync(hm.data(), pmax, blocks * sizeof(float), cudaMemcpyDeviceToHost, st));
     FWI_CUDA(cudaMemcpyAsync(ha.data(), parg, blocks * sizeof(long long), cudaMemcpyDeviceToHost, st));
-    FWI_CUDA(cudaFreeAsync(psum, st)); FWI_CUDA(cudaFreeAsync(pmax, st)); FWI_CUDA(cudaFreeAsync(parg, st));
     FWI_CUDA(cudaStreamSynchronize(st));
     double s = 0.0; float mx = -INFINITY; long long am = -1;
     for (int b = 0; b < blocks; ++b) {

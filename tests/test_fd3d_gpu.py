@@ -296,3 +296,27 @@ def test_peer_memory_slab_timeout_is_reported_not_hung(ac):
     assert e.value == 0
     for s in slabs:
         s["p"].close()
+
+
+@pytest.mark.parametrize("by", ["14", "16"])
+def test_tile_height_variants_agree_with_the_oracle(ac, monkeypatch, by):
+    """The 3-D kernel's tile height (16 rows / 8 consumer warps, or 14 rows / 7 warps - chosen per plan, FWI_FD3D_BY forces it):
+    same traces and gradient, against the oracle and bit-identical to each other."""
+    shape, nt = (30, 45, 150), 60
+    v, h, dt, src, rec, wav = _case(shape, nt, seed=8)
+    obs = fo.Problem(v * 1.03, h, dt, src, rec, nabs=8).forward(wav)
+    J_want, g_want, tr_want = fo.Problem(v, h, dt, src, rec, nabs=8).misfit_and_gradient(wav, obs)
+    monkeypatch.setenv("FWI_FD3D_BY", by)
+    prop = ac.Propagator(shape, h, dt, nabs=8)
+    prop.set_model(v)
+    prop.set_geometry(src, rec)
+    J, g, tr = prop.gradient(wav, obs, want_traces=True)
+    prop.close()
+    assert rel_l2(tr.cpu().numpy(), tr_want) <= 1e-5 and rel_l2(g.cpu().numpy(), g_want) <= 1e-4 and abs(J - J_want) <= 1e-4 * J_want
+    monkeypatch.setenv("FWI_FD3D_BY", "16")
+    ref = ac.Propagator(shape, h, dt, nabs=8)
+    ref.set_model(v)
+    ref.set_geometry(src, rec)
+    J2, g2, tr2 = ref.gradient(wav, obs, want_traces=True)
+    ref.close()
+    assert np.array_equal(tr.cpu().numpy(), tr2.cpu().numpy()) and np.array_equal(g.cpu().numpy(), g2.cpu().numpy())
