@@ -205,19 +205,20 @@ def track_a_numbers(device, dist=None, cpu=True):
     dev = torch.device("cuda", device)
     # ---- N GPUs: contiguous sample ranges per rank (FWI:833-834 order), one all-reduce of sum L (FWI:847)
     if dist:
-        N = 16_000_000
+        N = 8_000_000
         tot = torch.zeros(1, dtype=torch.float64, device=dev)
 
         def shard(r):
-            _, _, _, (s, _, _) = prob.sample_eval_dev(6, 1 + r, rank * N, N, amp, 0, 0)
-            tot[0] = s
-            dist.all_reduce(tot)
+            _, _, L, _ = prob.sample_eval_dev(6, 1 + r, rank * N, N, amp, 0, 0, reduce=False)
+            tot.copy_(L.sum(dtype=torch.float64))          # sum L of this rank's shard, on the device
+            dist.all_reduce(tot)                            # p_data over all ranks (FWI:847), stream-ordered: no host sync
         shard(0)
         dist.barrier()
-        dt_ = _ev_time(torch, dev, shard, 3)
+        dt_ = _ev_time(torch, dev, shard, 4)
         t = torch.tensor([dt_], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out["multi_gpu"] = {"samples_per_s": world * N / float(t[0]), "samples_per_rank": N, "n_gpus": world, "scaling": "weak",
+                            "ms_per_batch": float(t[0]) * 1e3,
                             "collective": "one NCCL all-reduce of sum L (float64 scalar) per batch"}
         prob.close()
         return out
