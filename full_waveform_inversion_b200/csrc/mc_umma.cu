@@ -1,0 +1,371 @@
+// Track A on the 5th-generation tensor cores: the [N x C] . [C x K.T] contraction of the Monte-Carlo likelihood path
+// (forward_model FWI:253-264 + variance_reduction FWI:512-520 per trace, FWI:664-668) as tcgen05.mma kind::tf32 with an
+// error-compensated 3 x TF32 split, accumulators in TMEM, the misfit folded in the TMEM epilogue.
+//
+// Formulation.  For a trace k the residual of every sample n at every time t is ONE matrix product:
+//     r[n, t] = sum_c M[n, c] G[k, c, t] - d[k, t]  =  A''[n, :] . B''[k][t, :]
+// with 32-wide rows (four tcgen05 K-steps of 8):
+//     A''[n] = [ M_hi (9) | M_hi (9) | M_lo (9) | -1 | -1 | 0 0 0 ]        hi = tf32(x), lo = tf32(x - hi)
+//     B''[t] = [ G_hi (9) | G_lo (9) | G_hi (9) | d_hi | d_lo | 0 0 0 ]
+// i.e. hi.hi + hi.lo + lo.hi (the lo.lo term is below fp32 rounding), accumulated in fp32 by the tensor core.  The
+// epilogue reads the 128 x 256 accumulator tile from TMEM (one sample per thread, tcgen05.ld 32x32b.x32) and folds
+// sum_t r^2 per (sample, trace); VR_k = max(0, 1 - SSE_k / sum d_k^2) (FWI:512-520), summed over the traces of the CTA.
+//
+// Work split.  B'' of a few traces (6 tiles of 256 x 32 fp32 = 192 KB) stays RESIDENT in shared memory; a CTA walks over
+// 128-sample groups, TMA-loading only the 16 KB A'' tile per group (2 stages).  Trace groups are separate CTAs that write
+// partial sums part[g][n]; a small kernel adds them, divides by K and applies L = exp(-(1 - s)/2) (FWI:774).
+// Per group and tile: 4 MMAs (128 x 256 x 8) into one of two TMEM accumulators (2 x 256 columns), committed to an
+// mbarrier the four epilogue warps wait on; they hand the accumulator back through a second mbarrier.
+//
+// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp index), warp 4 TMA producer, warp 5 MMA issuer.
+#include "fd_common.cuh"
+#include <vector>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+
+namespace fwi {
+
+constexpr int kUK = 32;                 // padded K (floats per operand row = one 128-byte swizzle row)
+constexpr int kUM = 128;                // samples per MMA tile (TMEM lanes)
+constexpr int kUN = 256;                // time samples per MMA tile (TMEM columns per accumulator)
+constexpr int kUTilesMax = 6;           // resident B'' tiles per CTA (6 x 32 KB)
+constexpr int kUStagesA = 2;
+constexpr uint32_t kUIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kUN >> 3) << 17) | ((kUM >> 4) << 24);   // F32 acc, TF32 x TF32, K-major both
+
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+    // K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (1), descriptor version 1
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__host__ __device__ inline float tf32_round(float x) {          // round to nearest-even onto the 10-bit tf32 mantissa
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return x;
+    u += 0x00000FFFu + ((u >> 13) & 1u);
+    u &= 0xFFFFE000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
+struct UmmaEvalArgs {
+    int64_t N;                  // samples
+    int n_groups;               // 128-sample groups = ceil(N / 128)
+    int tiles_per_trace;        // ceil(T / 256)
+    int traces_per_cta;         // resident traces per CTA
+    int K;                      // traces
+    int T;
+    const float* inv_sum_d2;    // [K] 1 / sum_t d_k^2
+    float* part;                // [n_trace_groups][N] partial sums of per-trace VR
+};
+
+// grid = (ctas_per_trace_group, n_trace_groups); block = 192
+__global__ void __launch_bounds__(192, 1) mc_umma_vr_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                                                              UmmaEvalArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* b_smem = reinterpret_cast<float*>(smem);                                    // [tiles][256][32] swizzled
+    float* a_smem = reinterpret_cast<float*>(smem + (size_t)kUTilesMax * kUN * kUK * 4); // [stages][128][32] swizzled
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kUTilesMax * kUN * kUK * 4 + (size_t)kUStagesA * kUM * kUK * 4);
+    uint64_t* b_full = bars;                       // 1
+    uint64_t* a_full = bars + 1;                   // [stages]
+    uint64_t* a_empty = bars + 1 + kUStagesA;      // [stages]
+    uint64_t* t_full = bars + 1 + 2 * kUStagesA;   // [2]
+    uint64_t* t_empty = bars + 3 + 2 * kUStagesA;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * kUStagesA);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tg = blockIdx.y;                                       // trace group
+    const int k0 = tg * a.traces_per_cta, k1 = min(a.K, k0 + a.traces_per_cta);
+    const int ntiles = (k1 - k0) * a.tiles_per_trace;                // resident tiles of this CTA
+
+    if (threadIdx.x == 0) {
+        mbar_init(b_full, 1);
+        for (int s = 0; s < kUStagesA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ------------------------------------------------ TMA producer: resident B'' tiles once, then the A'' tile of every group
+        if (lane == 0) {
+            mbar_expect_tx(b_full, (uint32_t)ntiles * kUN * kUK * 4);
+            for (int j = 0; j < ntiles; ++j) {
+                const int k = k0 + j / a.tiles_per_trace, tt = j % a.tiles_per_trace;
+                tma_load_2d(b_smem + (size_t)j * kUN * kUK, &tm_b, 0, k * a.tiles_per_trace * kUN + tt * kUN, b_full);
+            }
+            int it = 0;
+            for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x, ++it) {
+                const int s = it % kUStagesA;
+                if (it >= kUStagesA) mbar_wait(&a_empty[s], ((it / kUStagesA) - 1) & 1);
+                mbar_expect_tx(&a_full[s], kUM * kUK * 4);
+                tma_load_2d(a_smem + (size_t)s * kUM * kUK, &tm_a, 0, g * kUM, &a_full[s]);
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------ MMA issuer (one elected lane)
+        if (lane == 0) {
+            mbar_wait(b_full, 0);
+            int it = 0, acc_it = 0;
+            for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x, ++it) {
+                const int s = it % kUStagesA;
+                mbar_wait(&a_full[s], (it / kUStagesA) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(a_smem + (size_t)s * kUM * kUK);
+                for (int j = 0; j < ntiles; ++j, ++acc_it) {
+                    const int buf = acc_it & 1;
+                    if (acc_it >= 2) { mbar_wait(&t_empty[buf], ((acc_it >> 1) - 1) & 1); tc_fence_after(); }
+                    const uint32_t b_addr = smem_u32(b_smem + (size_t)j * kUN * kUK);
+#pragma unroll
+                    for (int ks = 0; ks < kUK / 8; ++ks)
+                        umma_tf32(tmem_base + buf * kUN, umma_smem_desc(a_addr + ks * 32), umma_smem_desc(b_addr + ks * 32), kUIdesc, ks > 0);
+                    umma_commit(&t_full[buf]);                      // accumulator ready for the epilogue
+                }
+                umma_commit(&a_empty[s]);                           // all MMAs reading this A'' stage have completed
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue warps 0..3: one sample per thread, TMEM lane = 32 * warp + lane
+        int acc_it = 0;
+        for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
+            const int64_t n = (int64_t)g * kUM + warp * 32 + lane;
+            float vr_sum = 0.f;
+            for (int k = k0; k < k1; ++k) {
+                float sse = 0.f;
+                for (int tt = 0; tt < a.tiles_per_trace; ++tt, ++acc_it) {
+                    const int buf = acc_it & 1;
+                    mbar_wait(&t_full[buf], (acc_it >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + buf * kUN + ((uint32_t)(warp * 32) << 16);
+                    const int ncol = min(kUN, a.T - tt * kUN);
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    for (int c0 = 0; c0 < ncol; c0 += 32) {
+                        float v[32];
+                        tmem_ld32(taddr + c0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
+                            s2 = fmaf(v[i + 2], v[i + 2], s2); s3 = fmaf(v[i + 3], v[i + 3], s3);
+                        }
+                    }
+                    sse += (s0 + s1) + (s2 + s3);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&t_empty[buf]);       // accumulator drained by this warp
+                }
+                vr_sum += fmaxf(0.f, 1.0f - sse * a.inv_sum_d2[k]);    // FWI:512-520
+            }
+            if (n < a.N) a.part[(size_t)tg * a.N + n] = vr_sum;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+// A''[n][32] from the sampler's (rows, N) layout
+__global__ void mc_umma_pack_kernel(const float* __restrict__ M, int64_t ldm, int C, int64_t N, int64_t Npad, float* __restrict__ A) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= Npad) return;
+    float row[kUK];
+#pragma unroll
+    for (int i = 0; i < kUK; ++i) row[i] = 0.f;
+    if (n < N) {
+        for (int c = 0; c < C; ++c) {
+            const float x = M[(size_t)c * ldm + n];
+            const float hi = tf32_round(x), lo = tf32_round(x - hi);
+            row[c] = hi; row[C + c] = hi; row[2 * C + c] = lo;
+        }
+        row[3 * C] = -1.f; row[3 * C + 1] = -1.f;
+    }
+    float4* dst = reinterpret_cast<float4*>(A + (size_t)n * kUK);
+#pragma unroll
+    for (int i = 0; i < kUK / 4; ++i) dst[i] = make_float4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
+}
+
+__global__ void mc_umma_finish_kernel(const float* __restrict__ part, int ngroups, int64_t N, float inv_K, float* __restrict__ sim,
+                                      float* __restrict__ like) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int g = 0; g < ngroups; ++g) s += part[(size_t)g * N + n];
+    s *= inv_K;                                                    // np.average over the traces (FWI:682)
+    sim[n] = s;
+    if (like) like[n] = expf(-(1.0f - s) * 0.5f);                  // FWI:774
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int encode_rows32_sw128(CUtensorMap* out, void* base, uint64_t rows, uint32_t box_rows) {
+    static EncodeTiledFn2 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        FWI_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available from the driver"); return FWI_ECUDA; }
+        fn = (EncodeTiledFn2)p;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)kUK, rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)kUK * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kUK, box_rows}, es[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (swizzle 128B) failed with CUresult %d", (int)r); return FWI_ECUDA; }
+    return FWI_OK;
+}
+
+}  // namespace fwi
+
+using namespace fwi;
+
+// Device-resident state of the tensor-core path for one (G, d): B'' and 1 / sum d^2.
+struct fwi_umma {
+    int device = 0, K = 0, C = 0, T = 0, tiles_per_trace = 0, traces_per_cta = 0, n_tgroups = 0;
+    float* B = nullptr;          // [K][tiles_per_trace * 256][32]
+    float* inv_d2 = nullptr;     // [K]
+    float* A = nullptr; size_t A_rows = 0;
+    float* part = nullptr; size_t part_cap = 0;
+    CUtensorMap tm_b;
+};
+
+extern "C" {
+
+// G (K, C, T) and d (K, T) float64 host arrays (FWI:85 layout).  C in {3, 6, 9}; T a multiple of 16 with ceil(T/256) <= 6.
+int fwi_umma_create(int device, const double* G, const double* d, int K, int C, int T, fwi_umma** out) {
+    FWI_REQUIRE(out && G && d && K >= 1 && T >= 16, "fwi_umma_create: bad arguments");
+    FWI_REQUIRE(3 * C + 2 <= kUK, "fwi_umma_create: C = %d does not fit the 32-wide operand rows", C);
+    const int tpt = (T + kUN - 1) / kUN;
+    FWI_REQUIRE(tpt <= kUTilesMax && T % 8 == 0, "fwi_umma_create: T = %d not supported by the tensor-core path (multiple of 8, at most %d)", T, kUTilesMax * kUN);
+    DeviceGuard g(device);
+    auto* u = new fwi_umma();
+    u->device = device; u->K = K; u->C = C; u->T = T; u->tiles_per_trace = tpt;
+    u->traces_per_cta = std::max(1, kUTilesMax / tpt);
+    u->n_tgroups = (K + u->traces_per_cta - 1) / u->traces_per_cta;
+    const size_t rows = (size_t)K * tpt * kUN;
+    std::vector<float> B(rows * kUK, 0.f), inv(K);
+    for (int k = 0; k < K; ++k) {
+        double sd2 = 0.0;
+        for (int t = 0; t < T; ++t) {
+            float* row = &B[((size_t)k * tpt * kUN + t) * kUK];
+            for (int c = 0; c < C; ++c) {
+                const float x = (float)G[((size_t)k * C + c) * T + t];
+                const float hi = tf32_round(x), lo = tf32_round(x - hi);
+                row[c] = hi; row[C + c] = lo; row[2 * C + c] = hi;
+            }
+            const float dv = (float)d[(size_t)k * T + t];
+            const float dhi = tf32_round(dv), dlo = tf32_round(dv - dhi);
+            row[3 * C] = dhi; row[3 * C + 1] = dlo;
+            sd2 += d[(size_t)k * T + t] * d[(size_t)k * T + t];
+        }
+        inv[k] = (float)(1.0 / sd2);
+    }
+    FWI_CUDA(cudaMalloc(&u->B, B.size() * sizeof(float)));
+    FWI_CUDA(cudaMalloc(&u->inv_d2, K * sizeof(float)));
+    FWI_CUDA(cudaMemcpy(u->B, B.data(), B.size() * sizeof(float), cudaMemcpyHostToDevice));
+    FWI_CUDA(cudaMemcpy(u->inv_d2, inv.data(), K * sizeof(float), cudaMemcpyHostToDevice));
+    int rc = encode_rows32_sw128(&u->tm_b, u->B, rows, kUN);
+    if (rc) return rc;
+    const int smem = kUTilesMax * kUN * kUK * 4 + kUStagesA * kUM * kUK * 4 + 256;
+    FWI_CUDA(cudaFuncSetAttribute(mc_umma_vr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    *out = u;
+    return FWI_OK;
+}
+
+int fwi_umma_destroy(fwi_umma* u) {
+    if (!u) return FWI_OK;
+    DeviceGuard g(u->device);
+    cudaFree(u->B); cudaFree(u->inv_d2);
+    if (u->A) cudaFree(u->A);
+    if (u->part) cudaFree(u->part);
+    delete u;
+    return FWI_OK;
+}
+
+// Per-trace un-normalised VR similarity (the reference's default mode, FWI:53-56) of N source vectors given in the
+// sampler's layout M_dev[c * ldm + n]; sim_dev (N) and like_dev (N, nullable) as fwi_mc_eval.
+int fwi_umma_eval_vr(fwi_umma* u, const float* M_dev, int64_t ldm, int64_t N, float* sim_dev, float* like_dev, void* stream) {
+    FWI_REQUIRE(u && M_dev && sim_dev && N >= 0 && ldm >= N, "fwi_umma_eval_vr: bad arguments");
+    if (N == 0) return FWI_OK;
+    DeviceGuard g(u->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ngroups = (N + kUM - 1) / kUM, Npad = ngroups * kUM;
+    if (u->A_rows < (size_t)Npad) {
+        if (u->A) cudaFree(u->A);
+        u->A = nullptr; u->A_rows = 0;
+        FWI_CUDA(cudaMalloc(&u->A, (size_t)Npad * kUK * sizeof(float)));
+        u->A_rows = (size_t)Npad;
+    }
+    if (u->part_cap < (size_t)u->n_tgroups * N) {
+        if (u->part) cudaFree(u->part);
+        u->part = nullptr; u->part_cap = 0;
+        FWI_CUDA(cudaMalloc(&u->part, (size_t)u->n_tgroups * N * sizeof(float)));
+        u->part_cap = (size_t)u->n_tgroups * N;
+    }
+    CUtensorMap tm_a;
+    int rc = encode_rows32_sw128(&tm_a, u->A, (uint64_t)Npad, kUM);
+    if (rc) return rc;
+    mc_umma_pack_kernel<<<(unsigned)((Npad + 127) / 128), 128, 0, st>>>(M_dev, ldm, u->C, N, Npad, u->A);
+    FWI_CUDA(cudaGetLastError());
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, u->device);
+    const int per_group = (int)std::min<int64_t>(ngroups, std::max(1, sms / u->n_tgroups));
+    UmmaEvalArgs a{};
+    a.N = N; a.n_groups = (int)ngroups; a.tiles_per_trace = u->tiles_per_trace; a.traces_per_cta = u->traces_per_cta;
+    a.K = u->K; a.T = u->T; a.inv_sum_d2 = u->inv_d2; a.part = u->part;
+    const int smem = kUTilesMax * kUN * kUK * 4 + kUStagesA * kUM * kUK * 4 + 256;
+    mc_umma_vr_kernel<<<dim3(per_group, u->n_tgroups), 192, smem, st>>>(tm_a, u->tm_b, a);
+    FWI_CUDA(cudaGetLastError());
+    mc_umma_finish_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(u->part, u->n_tgroups, N, 1.0f / u->K, sim_dev, like_dev);
+    FWI_CUDA(cudaGetLastError());
+    return FWI_OK;
+}
+
+}  // extern "C"
