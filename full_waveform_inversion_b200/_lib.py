@@ -49,9 +49,6 @@ _SIGS = {
     "fwi_mc_posterior_hist": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "fwi_mc_lstsq": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "fwi_diag_fp32_peak": (c_int, [c_int, POINTER(c_double)]),
-    "fwi_umma_create": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]),
-    "fwi_umma_destroy": (c_int, [c_void_p]),
-    "fwi_umma_eval_vr": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "fwi_mc_eval_host": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 

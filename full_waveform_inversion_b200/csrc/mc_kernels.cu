@@ -10,6 +10,7 @@
 // share one sample group and split the traces.
 // The path is FP32-FMA bound (G is ~0.4 MB and L2/L1 resident; ~40-80 B of HBM traffic per sample).
 #include "common.cuh"
+#include "mc_common.cuh"
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -26,22 +27,6 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-struct TraceConst {
-    double mean_d;   // mean of the trace's data (the centring constant used for d')
-    double ssd;      // sum (d - mean_d)^2
-    double sumd2;    // sum d^2
-    double maxd;     // max |d| of the ORIGINAL trace (normalisation, FWI:598)
-    double sigma;    // mean |d[-60:-10]| (FWI:580), NaN when T < 60
-    double d_first, d_last;
-};
-
-struct FlatConst {   // constants of the flattened (K*Tv) data array; index = normalised?
-    double n;
-    double D1[2], D2[2];   // sum d, sum d^2
-    double sigma[2];       // gaussian noise level of the flattened array
-};
-
-enum { MODE_SSE = 0, MODE_MOM = 1, MODE_MOM_MAX = 2 };
 #ifndef MC_MIN_BLOCKS
 #define MC_MIN_BLOCKS 3
 #endif
@@ -901,6 +886,7 @@ struct fwi_mc_ctx {
     double* dstage = nullptr; int64_t dstage_bytes = 0;
     int sm_count = 148;
     bool uploaded = false;
+    UmmaPath* umma = nullptr;     // tensor-core evaluation path (mc_umma.cu), built at upload when the shapes allow it
 };
 
 static void free_rowset(RowSet& r) {
@@ -1109,6 +1095,7 @@ int fwi_mc_create(int device, int K, int C, int T, int n_media, fwi_mc_ctx** out
 int fwi_mc_destroy(fwi_mc_ctx* c) {
     if (!c) return FWI_OK;
     DeviceGuard g(c->device);
+    umma_free(c->umma); c->umma = nullptr;
     free_rowset(c->base); free_rowset(c->hr); free_rowset(c->hrflat);
     if (c->phase_dev) cudaFree(c->phase_dev);
     if (c->stage_M) cudaFree(c->stage_M);
@@ -1139,8 +1126,13 @@ int fwi_mc_upload(fwi_mc_ctx* c, const double* G, const double* d, const int* ph
         for (int t = 0; t < c->T; ++t) mx = std::max(mx, std::fabs(d[(size_t)k * c->T + t]));
         FWI_REQUIRE(std::isfinite(mx), "fwi_mc_upload: non-finite value in data trace %d", k);
     }
+    umma_free(c->umma); c->umma = nullptr;
     int rc = build_rowset(c, c->base, 0);
     if (rc) return rc;
+    if (c->NM == 1) {       // operands of the tensor-core path (one medium; two-media batches stay on the CUDA-core kernels)
+        rc = umma_build(&c->umma, c->device, c->G.data(), c->d.data(), c->K, c->C, c->T, c->base.tc, c->base.fc);
+        if (rc) return rc;
+    }
     c->uploaded = true;
     return FWI_OK;
 }
@@ -1211,6 +1203,17 @@ int fwi_mc_eval(fwi_mc_ctx* c, const float* M, int64_t ldm, const float* frac, i
     p.phase = c->phase_dev; p.M = M; p.ldm = ldm; p.frac = frac; p.nfrac = nfrac; p.N = N; p.K = c->K; p.Tv = rs->Tv;
     p.metric = metric; p.flags = flags; p.boundary_fix = boundary_fix; p.sim = sim; p.like = like;
 
+    // Tensor-core path (tcgen05, 3 x TF32 split, TMEM epilogue; mc_umma.cu): every metric except the 4x-interpolated
+    // CC-shift, one medium.  Default for batches of 256 samples and more; FWI_FLAG_TENSOR requires it, FWI_FLAG_NO_TENSOR /
+    // FWI_MC_TENSOR=0 keep the CUDA-core kernels.
+    {
+        const char* e = getenv("FWI_MC_TENSOR");
+        const bool env_off = e && e[0] == '0';
+        const bool can = c->umma && c->NM == 1 && nfrac == 0 && umma_supports(c->umma, metric, flags);
+        FWI_REQUIRE(!(flags & FWI_FLAG_TENSOR) || can, "fwi_mc_eval: FWI_FLAG_TENSOR but the tensor-core path does not cover this case (CC-shift, two media, Gram mode, T > 1536 or C > 9)");
+        if (can && !(flags & FWI_FLAG_NO_TENSOR) && ((flags & FWI_FLAG_TENSOR) || (!env_off && N >= 256)))
+            return umma_eval(c->umma, M, ldm, N, metric, flags, sim, like, (cudaStream_t)stream);
+    }
     if (flags & FWI_FLAG_GRAM) {
         FWI_REQUIRE(!norm, "fwi_mc_eval: the Gram mode cannot normalise traces (it never forms them); drop FWI_FLAG_GRAM or FWI_FLAG_NORMALISED");
         FWI_REQUIRE(c->NM == 1 && rs->gram, "fwi_mc_eval: the Gram mode supports single-medium Green's functions only");

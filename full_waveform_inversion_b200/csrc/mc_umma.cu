@@ -8,8 +8,14 @@
 //     A''[n] = [ M_hi (9) | M_hi (9) | M_lo (9) | -1 | -1 | 0 0 0 ]        hi = tf32(x), lo = tf32(x - hi)
 //     B''[t] = [ G_hi (9) | G_lo (9) | G_hi (9) | d_hi | d_lo | 0 0 0 ]
 // i.e. hi.hi + hi.lo + lo.hi (the lo.lo term is below fp32 rounding), accumulated in fp32 by the tensor core.  The
-// epilogue reads the 128 x 256 accumulator tile from TMEM (one sample per thread, tcgen05.ld 32x32b.x32) and folds
-// sum_t r^2 per (sample, trace); VR_k = max(0, 1 - SSE_k / sum d_k^2) (FWI:512-520), summed over the traces of the CTA.
+// epilogue reads the 128 x 256 accumulator tile from TMEM (one sample per thread, tcgen05.ld 32x32b.x32, double
+// buffered) and folds the statistics of the (sample, trace) pair:
+//   MODE_SSE      (un-normalised VR / gau, FWI:512-520, 578-582): sum_t r^2;
+//   MODE_MOM      (CC == PCC, FWI:534-546, 568-576): B'' holds the CENTRED rows G' = G - mean_t G and the -1 columns of
+//                 A'' are 0, so the accumulator is the centred synthetic s' and the fold is sum_t s'^2; the cross moment
+//                 sum_t d' s' = M . (G' d') and the mean M . gbar are 9-term dot products with float64 constants;
+//   MODE_MOM_MAX  (normalised modes, FWI:597-599): additionally max / min of s' (max |s| = max(|max + mu|, |min + mu|)).
+// The per-trace combination (float64, same expressions as mc_eval_kernel) runs in the same thread.
 //
 // Work split.  B'' of a few traces (6 tiles of 256 x 32 fp32 = 192 KB) stays RESIDENT in shared memory; a CTA walks over
 // 128-sample groups, TMA-loading only the 16 KB A'' tile per group (2 stages).  Trace groups are separate CTAs that write
@@ -19,6 +25,7 @@
 //
 // Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp index), warp 4 TMA producer, warp 5 MMA issuer.
 #include "fd_common.cuh"
+#include "mc_common.cuh"
 #include <vector>
 #include <cstring>
 #include <cmath>
@@ -31,7 +38,6 @@ constexpr int kUM = 128;                // samples per MMA tile (TMEM lanes)
 constexpr int kUN = 256;                // time samples per MMA tile (TMEM columns per accumulator)
 constexpr int kUTilesMax = 6;           // resident B'' tiles per CTA (6 x 32 KB)
 constexpr int kUStagesA = 2;
-constexpr uint32_t kUIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kUN >> 3) << 17) | ((kUM >> 4) << 24);   // F32 acc, TF32 x TF32, K-major both
 
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
     // K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (1), descriptor version 1
@@ -77,6 +83,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same wait, tied to the registers of the load it completes (keeps the compiler from using them earlier)
+__device__ __forceinline__ void tmem_ld_wait_dep(float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                   "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
 
 __host__ __device__ inline float tf32_round(float x) {          // round to nearest-even onto the 10-bit tf32 mantissa
     uint32_t u;
@@ -94,15 +110,21 @@ struct UmmaEvalArgs {
     int n_groups;               // 128-sample groups = ceil(N / 128)
     int tiles_per_trace;        // ceil(T / 256)
     int traces_per_cta;         // resident traces per CTA
-    int K;                      // traces
-    int T;
-    const float* inv_sum_d2;    // [K] 1 / sum_t d_k^2
-    float* part;                // [n_trace_groups][N] partial sums of per-trace VR
+    int K, C, T;
+    int metric, flags;
+    uint32_t idesc_full, idesc_last;      // instruction descriptors of a full tile / of the last tile of a trace
+    const TraceConst* tc;       // [K]
+    const double* gbar;         // [K][C] mean_t G
+    const double* gdc;          // [K][C] sum_t (d - mean d) G
+    const float* M;             // the samples, (rows, N)
+    int64_t ldm;
+    double* part;               // [n_trace_groups][3][N] partial sums of the per-trace combination
 };
 
 // grid = (ctas_per_trace_group, n_trace_groups); block = 192
-__global__ void __launch_bounds__(192, 1) mc_umma_vr_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                                                              UmmaEvalArgs a) {
+template <int MODE>
+__global__ void __launch_bounds__(192, 1) mc_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                                                           UmmaEvalArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* b_smem = reinterpret_cast<float*>(smem);                                    // [tiles][256][32] swizzled
     float* a_smem = reinterpret_cast<float*>(smem + (size_t)kUTilesMax * kUN * kUK * 4); // [stages][128][32] swizzled
@@ -138,7 +160,7 @@ __global__ void __launch_bounds__(192, 1) mc_umma_vr_kernel(const __grid_constan
             mbar_expect_tx(b_full, (uint32_t)ntiles * kUN * kUK * 4);
             for (int j = 0; j < ntiles; ++j) {
                 const int k = k0 + j / a.tiles_per_trace, tt = j % a.tiles_per_trace;
-                tma_load_2d(b_smem + (size_t)j * kUN * kUK, &tm_b, 0, k * a.tiles_per_trace * kUN + tt * kUN, b_full);
+                tma_load_2d(b_smem + (size_t)j * kUN * kUK, &tm_b, 0, (k * a.tiles_per_trace + tt) * kUN, b_full);
             }
             int it = 0;
             for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x, ++it) {
@@ -162,9 +184,10 @@ __global__ void __launch_bounds__(192, 1) mc_umma_vr_kernel(const __grid_constan
                     const int buf = acc_it & 1;
                     if (acc_it >= 2) { mbar_wait(&t_empty[buf], ((acc_it >> 1) - 1) & 1); tc_fence_after(); }
                     const uint32_t b_addr = smem_u32(b_smem + (size_t)j * kUN * kUK);
+                    const uint32_t idesc = (j % a.tiles_per_trace == a.tiles_per_trace - 1) ? a.idesc_last : a.idesc_full;
 #pragma unroll
                     for (int ks = 0; ks < kUK / 8; ++ks)
-                        umma_tf32(tmem_base + buf * kUN, umma_smem_desc(a_addr + ks * 32), umma_smem_desc(b_addr + ks * 32), kUIdesc, ks > 0);
+                        umma_tf32(tmem_base + buf * kUN, umma_smem_desc(a_addr + ks * 32), umma_smem_desc(b_addr + ks * 32), idesc, ks > 0);
                     umma_commit(&t_full[buf]);                      // accumulator ready for the epilogue
                 }
                 umma_commit(&a_empty[s]);                           // all MMAs reading this A'' stage have completed
@@ -172,37 +195,100 @@ __global__ void __launch_bounds__(192, 1) mc_umma_vr_kernel(const __grid_constan
         }
     } else {
         // ------------------------------------------------ epilogue warps 0..3: one sample per thread, TMEM lane = 32 * warp + lane
+        const bool simul = a.flags & FWI_FLAG_SIMULTANEOUS;
+        const bool vr_like = a.metric == FWI_METRIC_VR || a.metric == FWI_METRIC_GAU;
+        const double Tn = (double)a.T;
         int acc_it = 0;
         for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
             const int64_t n = (int64_t)g * kUM + warp * 32 + lane;
-            float vr_sum = 0.f;
+            const bool live = n < a.N;
+            double coef[9];
+            if (MODE != MODE_SSE) {
+#pragma unroll
+                for (int c = 0; c < 9; ++c) coef[c] = (live && c < a.C) ? (double)a.M[(size_t)c * a.ldm + n] : 0.0;
+            }
+            double q0 = 0.0, q1 = 0.0, q2 = 0.0;
             for (int k = k0; k < k1; ++k) {
-                float sse = 0.f;
+                float s0 = 0.f, s1 = 0.f, s2a = 0.f, s3 = 0.f, vmax = -3.0e38f, vmin = 3.0e38f;
                 for (int tt = 0; tt < a.tiles_per_trace; ++tt, ++acc_it) {
                     const int buf = acc_it & 1;
                     mbar_wait(&t_full[buf], (acc_it >> 1) & 1);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + buf * kUN + ((uint32_t)(warp * 32) << 16);
-                    const int ncol = min(kUN, a.T - tt * kUN);
-                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                    for (int c0 = 0; c0 < ncol; c0 += 32) {
-                        float v[32];
-                        tmem_ld32(taddr + c0, v);
-                        tmem_ld_wait();
+                    const int ncol = min(kUN, a.T - tt * kUN);       // (columns past T hold 0: B'' is zero-padded)
+                    float va[32], vb[32];
+                    auto fold = [&](const float* v, int valid) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
-                            s2 = fmaf(v[i + 2], v[i + 2], s2); s3 = fmaf(v[i + 3], v[i + 3], s3);
+                            s2a = fmaf(v[i + 2], v[i + 2], s2a); s3 = fmaf(v[i + 3], v[i + 3], s3);
+                        }
+                        if (MODE == MODE_MOM_MAX) {
+                            if (valid >= 32) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) { vmax = fmaxf(vmax, v[i]); vmin = fminf(vmin, v[i]); }
+                            } else {
+                                for (int i = 0; i < valid; ++i) { vmax = fmaxf(vmax, v[i]); vmin = fminf(vmin, v[i]); }
+                            }
+                        }
+                    };
+                    tmem_ld32(taddr, va);
+                    for (int c0 = 0; c0 < ncol; c0 += 64) {
+                        tmem_ld_wait_dep(va);
+                        if (c0 + 32 < ncol) tmem_ld32(taddr + c0 + 32, vb);
+                        fold(va, ncol - c0);
+                        if (c0 + 32 < ncol) {
+                            tmem_ld_wait_dep(vb);
+                            if (c0 + 64 < ncol) tmem_ld32(taddr + c0 + 64, va);
+                            fold(vb, ncol - c0 - 32);
                         }
                     }
-                    sse += (s0 + s1) + (s2 + s3);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&t_empty[buf]);       // accumulator drained by this warp
                 }
-                vr_sum += fmaxf(0.f, 1.0f - sse * a.inv_sum_d2[k]);    // FWI:512-520
+                // ---- combine trace k (float64; the expressions of mc_eval_kernel's fold)
+                const TraceConst tc = a.tc[k];
+                const double s2 = (double)((s0 + s1) + (s2a + s3));
+                if (MODE == MODE_SSE) {
+                    const double sse = s2, dd = tc.sumd2;
+                    q1 += sse; q2 += dd;
+                    if (a.metric == FWI_METRIC_VR) q0 += fmax(0.0, 1.0 - sse / dd);            // FWI:515-519
+                    else q0 += exp(-sse / (2.0 * tc.sigma * tc.sigma));                         // FWI:581
+                } else {
+                    double mud = 0.0, sd = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {
+                        if (c < a.C) { mud = fma(coef[c], a.gbar[k * a.C + c], mud); sd = fma(coef[c], a.gdc[k * a.C + c], sd); }
+                    }
+                    double aa = 1.0, bb = 1.0;
+                    if (MODE == MODE_MOM_MAX) {
+                        aa = 1.0 / fmax(fabs((double)vmax + mud), fabs((double)vmin + mud));      // FWI:598-599
+                        bb = 1.0 / tc.maxd;
+                    }
+                    if (vr_like) {
+                        const double Sss = (s2 + Tn * mud * mud) * aa * aa;
+                        const double Sds = (sd + Tn * tc.mean_d * mud) * aa * bb;
+                        const double dd = tc.sumd2 * bb * bb;
+                        const double sse = dd - 2.0 * Sds + Sss;
+                        const double sig = tc.sigma * bb;
+                        q1 += sse; q2 += dd;
+                        if (a.metric == FWI_METRIC_VR) q0 += fmax(0.0, 1.0 - sse / dd);
+                        else q0 += exp(-sse / (2.0 * sig * sig));
+                    } else if (!simul) {
+                        const double pcc = sd / sqrt(s2 * tc.ssd);                              // FWI:572-573
+                        q0 += (pcc < 0.0) ? 0.0 : pcc;                                          // FWI:574-575
+                    } else {
+                        q0 += aa * Tn * mud;
+                        q1 += aa * aa * (s2 + Tn * mud * mud);
+                        q2 += aa * bb * (sd + Tn * tc.mean_d * mud);
+                    }
+                }
             }
-            if (n < a.N) a.part[(size_t)tg * a.N + n] = vr_sum;
+            if (live) {
+                double* o = a.part + (size_t)tg * 3 * a.N + n;
+                o[0] = q0; o[a.N] = q1; o[2 * a.N] = q2;
+            }
         }
     }
     tc_fence_before();
@@ -210,35 +296,61 @@ __global__ void __launch_bounds__(192, 1) mc_umma_vr_kernel(const __grid_constan
     if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
-// A''[n][32] from the sampler's (rows, N) layout
-__global__ void mc_umma_pack_kernel(const float* __restrict__ M, int64_t ldm, int C, int64_t N, int64_t Npad, float* __restrict__ A) {
+// A''[n][32] from the sampler's (rows, N) layout; `with_d`: the two -1 columns that subtract d (MODE_SSE)
+__global__ void mc_umma_pack_kernel(const float* __restrict__ M, int64_t ldm, int C, int64_t N, int64_t Npad, int with_d, float* __restrict__ A) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= Npad) return;
     float row[kUK];
 #pragma unroll
     for (int i = 0; i < kUK; ++i) row[i] = 0.f;
     if (n < N) {
-        for (int c = 0; c < C; ++c) {
-            const float x = M[(size_t)c * ldm + n];
-            const float hi = tf32_round(x), lo = tf32_round(x - hi);
-            row[c] = hi; row[C + c] = hi; row[2 * C + c] = lo;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            if (c < C) {
+                const float x = M[(size_t)c * ldm + n];
+                const float hi = tf32_round(x), lo = tf32_round(x - hi);
+                row[c] = hi; row[C + c] = hi; row[2 * C + c] = lo;
+            }
         }
-        row[3 * C] = -1.f; row[3 * C + 1] = -1.f;
+        if (with_d) { row[3 * C] = -1.f; row[3 * C + 1] = -1.f; }
     }
     float4* dst = reinterpret_cast<float4*>(A + (size_t)n * kUK);
 #pragma unroll
     for (int i = 0; i < kUK / 4; ++i) dst[i] = make_float4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
 }
 
-__global__ void mc_umma_finish_kernel(const float* __restrict__ part, int ngroups, int64_t N, float inv_K, float* __restrict__ sim,
-                                      float* __restrict__ like) {
+// adds the trace groups' partial sums and applies the final expressions of mc_eval_kernel (FWI:601-632, 682, 774)
+__global__ void mc_umma_finish_kernel(const double* __restrict__ part, int ngroups, int64_t N, int K, int metric, int flags, FlatConst fc,
+                                      float* __restrict__ sim, float* __restrict__ like) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
-    float s = 0.f;
-    for (int g = 0; g < ngroups; ++g) s += part[(size_t)g * N + n];
-    s *= inv_K;                                                    // np.average over the traces (FWI:682)
-    sim[n] = s;
-    if (like) like[n] = expf(-(1.0f - s) * 0.5f);                  // FWI:774
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+    for (int g = 0; g < ngroups; ++g) {
+        const double* o = part + (size_t)g * 3 * N + n;
+        q0 += o[0]; q1 += o[N]; q2 += o[2 * N];
+    }
+    const bool norm = flags & FWI_FLAG_NORMALISED, simul = flags & FWI_FLAG_SIMULTANEOUS;
+    const bool vr_like = metric == FWI_METRIC_VR || metric == FWI_METRIC_GAU;
+    double result;
+    if (vr_like) {
+        if (simul) {
+            if (metric == FWI_METRIC_VR) result = fmax(0.0, 1.0 - q1 / q2);
+            else { const double sg = fc.sigma[norm ? 1 : 0]; result = exp(-q1 / (2.0 * sg * sg)); }
+        } else {
+            result = q0 / K;                                                               // FWI:682
+            if (metric == FWI_METRIC_GAU && (flags & FWI_FLAG_STRICT_REF)) result = 0.0;   // quirk q1
+        }
+    } else if (!simul) {
+        result = q0 / K;
+    } else {
+        const int ni = norm ? 1 : 0;
+        const double nn = fc.n, D1 = fc.D1[ni], D2 = fc.D2[ni];
+        const double cov = q2 - q0 * D1 / nn, vs = q1 - q0 * q0 / nn, vd = D2 - D1 * D1 / nn;
+        const double pcc = cov / sqrt(vs * vd);
+        result = (pcc < 0.0) ? 0.0 : pcc;
+    }
+    sim[n] = (float)result;
+    if (like) like[n] = (float)exp(-(1.0 - result) * 0.5);                                 // FWI:774
 }
 
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -262,80 +374,109 @@ static int encode_rows32_sw128(CUtensorMap* out, void* base, uint64_t rows, uint
     return FWI_OK;
 }
 
-}  // namespace fwi
-
-using namespace fwi;
-
-// Device-resident state of the tensor-core path for one (G, d): B'' and 1 / sum d^2.
-struct fwi_umma {
-    int device = 0, K = 0, C = 0, T = 0, tiles_per_trace = 0, traces_per_cta = 0, n_tgroups = 0;
-    float* B = nullptr;          // [K][tiles_per_trace * 256][32]
-    float* inv_d2 = nullptr;     // [K]
+// Device-resident state of the tensor-core path for one (G, d).
+struct UmmaPath {
+    int device = 0, K = 0, C = 0, T = 0, tiles_per_trace = 0, traces_per_cta = 0, n_tgroups = 0, sms = 148;
+    float* B_raw = nullptr;      // [K][tiles_per_trace * 256][32]: G and d (MODE_SSE)
+    float* B_cen = nullptr;      // same with centred G and no d (moment modes)
+    double* gbar = nullptr;      // [K][C]
+    double* gdc = nullptr;       // [K][C]
+    const TraceConst* tc = nullptr;   // owned by the Monte-Carlo context
+    FlatConst fc{};
     float* A = nullptr; size_t A_rows = 0;
-    float* part = nullptr; size_t part_cap = 0;
-    CUtensorMap tm_b;
+    double* part = nullptr; size_t part_cap = 0;
+    CUtensorMap tm_raw, tm_cen;
 };
 
-extern "C" {
+constexpr int kUSmem = kUTilesMax * kUN * kUK * 4 + kUStagesA * kUM * kUK * 4 + 256;
 
-// G (K, C, T) and d (K, T) float64 host arrays (FWI:85 layout).  C in {3, 6, 9}; T a multiple of 16 with ceil(T/256) <= 6.
-int fwi_umma_create(int device, const double* G, const double* d, int K, int C, int T, fwi_umma** out) {
-    FWI_REQUIRE(out && G && d && K >= 1 && T >= 16, "fwi_umma_create: bad arguments");
-    FWI_REQUIRE(3 * C + 2 <= kUK, "fwi_umma_create: C = %d does not fit the 32-wide operand rows", C);
+int umma_build(UmmaPath** out, int device, const double* G, const double* d, int K, int C, int T, const TraceConst* tc_dev,
+               const FlatConst& fc) {
+    *out = nullptr;
     const int tpt = (T + kUN - 1) / kUN;
-    FWI_REQUIRE(tpt <= kUTilesMax && T % 8 == 0, "fwi_umma_create: T = %d not supported by the tensor-core path (multiple of 8, at most %d)", T, kUTilesMax * kUN);
-    DeviceGuard g(device);
-    auto* u = new fwi_umma();
-    u->device = device; u->K = K; u->C = C; u->T = T; u->tiles_per_trace = tpt;
+    if (3 * C + 2 > kUK || C > 9 || tpt > kUTilesMax || K < 1 || T < 1) return FWI_OK;      // shape not covered: CUDA-core kernels only
+    auto* u = new UmmaPath();
+    u->device = device; u->K = K; u->C = C; u->T = T; u->tiles_per_trace = tpt; u->tc = tc_dev; u->fc = fc;
     u->traces_per_cta = std::max(1, kUTilesMax / tpt);
     u->n_tgroups = (K + u->traces_per_cta - 1) / u->traces_per_cta;
+    cudaDeviceGetAttribute(&u->sms, cudaDevAttrMultiProcessorCount, device);
     const size_t rows = (size_t)K * tpt * kUN;
-    std::vector<float> B(rows * kUK, 0.f), inv(K);
+    std::vector<float> Br(rows * kUK, 0.f), Bc(rows * kUK, 0.f);
+    std::vector<double> gbar((size_t)K * C), gdc((size_t)K * C);
     for (int k = 0; k < K; ++k) {
-        double sd2 = 0.0;
+        double md = 0.0;
+        for (int t = 0; t < T; ++t) md += d[(size_t)k * T + t];
+        md /= T;
+        for (int c = 0; c < C; ++c) {
+            const double* g = G + ((size_t)k * C + c) * T;
+            double gs = 0.0, gd = 0.0;
+            for (int t = 0; t < T; ++t) { gs += g[t]; gd += (d[(size_t)k * T + t] - md) * g[t]; }
+            gbar[(size_t)k * C + c] = gs / T;
+            gdc[(size_t)k * C + c] = gd;
+        }
         for (int t = 0; t < T; ++t) {
-            float* row = &B[((size_t)k * tpt * kUN + t) * kUK];
+            float* rr = &Br[((size_t)k * tpt * kUN + t) * kUK];
+            float* rc = &Bc[((size_t)k * tpt * kUN + t) * kUK];
             for (int c = 0; c < C; ++c) {
-                const float x = (float)G[((size_t)k * C + c) * T + t];
-                const float hi = tf32_round(x), lo = tf32_round(x - hi);
-                row[c] = hi; row[C + c] = lo; row[2 * C + c] = hi;
+                const double gv = G[((size_t)k * C + c) * T + t];
+                float x = (float)gv, hi = tf32_round(x), lo = tf32_round(x - hi);
+                rr[c] = hi; rr[C + c] = lo; rr[2 * C + c] = hi;
+                x = (float)(gv - gbar[(size_t)k * C + c]); hi = tf32_round(x); lo = tf32_round(x - hi);
+                rc[c] = hi; rc[C + c] = lo; rc[2 * C + c] = hi;
             }
             const float dv = (float)d[(size_t)k * T + t];
             const float dhi = tf32_round(dv), dlo = tf32_round(dv - dhi);
-            row[3 * C] = dhi; row[3 * C + 1] = dlo;
-            sd2 += d[(size_t)k * T + t] * d[(size_t)k * T + t];
+            rr[3 * C] = dhi; rr[3 * C + 1] = dlo;
         }
-        inv[k] = (float)(1.0 / sd2);
     }
-    FWI_CUDA(cudaMalloc(&u->B, B.size() * sizeof(float)));
-    FWI_CUDA(cudaMalloc(&u->inv_d2, K * sizeof(float)));
-    FWI_CUDA(cudaMemcpy(u->B, B.data(), B.size() * sizeof(float), cudaMemcpyHostToDevice));
-    FWI_CUDA(cudaMemcpy(u->inv_d2, inv.data(), K * sizeof(float), cudaMemcpyHostToDevice));
-    int rc = encode_rows32_sw128(&u->tm_b, u->B, rows, kUN);
-    if (rc) return rc;
-    const int smem = kUTilesMax * kUN * kUK * 4 + kUStagesA * kUM * kUK * 4 + 256;
-    FWI_CUDA(cudaFuncSetAttribute(mc_umma_vr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DeviceGuard g(device);
+    auto fail = [&](int rc) { umma_free(u); return rc; };
+    if (cudaMalloc(&u->B_raw, Br.size() * sizeof(float)) != cudaSuccess || cudaMalloc(&u->B_cen, Bc.size() * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&u->gbar, gbar.size() * sizeof(double)) != cudaSuccess || cudaMalloc(&u->gdc, gdc.size() * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError(); set_error("umma_build: out of device memory"); return fail(FWI_ENOMEM);
+    }
+    cudaMemcpy(u->B_raw, Br.data(), Br.size() * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(u->B_cen, Bc.data(), Bc.size() * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(u->gbar, gbar.data(), gbar.size() * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(u->gdc, gdc.data(), gdc.size() * sizeof(double), cudaMemcpyHostToDevice);
+    int rc = encode_rows32_sw128(&u->tm_raw, u->B_raw, rows, kUN);
+    if (!rc) rc = encode_rows32_sw128(&u->tm_cen, u->B_cen, rows, kUN);
+    if (rc) return fail(rc);
+    if (cudaFuncSetAttribute(mc_umma_kernel<MODE_SSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(mc_umma_kernel<MODE_MOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(mc_umma_kernel<MODE_MOM_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmem) != cudaSuccess) {
+        cudaGetLastError(); return fail(FWI_OK);          // no tensor-core path on this device: CUDA-core kernels only
+    }
     *out = u;
     return FWI_OK;
 }
 
-int fwi_umma_destroy(fwi_umma* u) {
-    if (!u) return FWI_OK;
+void umma_free(UmmaPath* u) {
+    if (!u) return;
     DeviceGuard g(u->device);
-    cudaFree(u->B); cudaFree(u->inv_d2);
+    if (u->B_raw) cudaFree(u->B_raw);
+    if (u->B_cen) cudaFree(u->B_cen);
+    if (u->gbar) cudaFree(u->gbar);
+    if (u->gdc) cudaFree(u->gdc);
     if (u->A) cudaFree(u->A);
     if (u->part) cudaFree(u->part);
     delete u;
-    return FWI_OK;
 }
 
-// Per-trace un-normalised VR similarity (the reference's default mode, FWI:53-56) of N source vectors given in the
-// sampler's layout M_dev[c * ldm + n]; sim_dev (N) and like_dev (N, nullable) as fwi_mc_eval.
-int fwi_umma_eval_vr(fwi_umma* u, const float* M_dev, int64_t ldm, int64_t N, float* sim_dev, float* like_dev, void* stream) {
-    FWI_REQUIRE(u && M_dev && sim_dev && N >= 0 && ldm >= N, "fwi_umma_eval_vr: bad arguments");
+bool umma_supports(const UmmaPath* u, int metric, int flags) {
+    if (!u) return false;
+    if (metric == FWI_METRIC_CC_SHIFT || (flags & FWI_FLAG_GRAM)) return false;      // 4x interpolated rows / the Gram algorithm stay on the CUDA cores
+    if (metric == FWI_METRIC_GAU && u->T < 60) return false;
+    return true;
+}
+
+int umma_eval(UmmaPath* u, const float* M_dev, int64_t ldm, int64_t N, int metric, int flags, float* sim_dev, float* like_dev, cudaStream_t st) {
     if (N == 0) return FWI_OK;
     DeviceGuard g(u->device);
-    cudaStream_t st = (cudaStream_t)stream;
+    const bool norm = flags & FWI_FLAG_NORMALISED, simul = flags & FWI_FLAG_SIMULTANEOUS;
+    int mode;
+    if (metric == FWI_METRIC_VR || metric == FWI_METRIC_GAU) mode = norm ? MODE_MOM_MAX : MODE_SSE;
+    else mode = (simul && norm) ? MODE_MOM_MAX : MODE_MOM;
     const int64_t ngroups = (N + kUM - 1) / kUM, Npad = ngroups * kUM;
     if (u->A_rows < (size_t)Npad) {
         if (u->A) cudaFree(u->A);
@@ -343,29 +484,33 @@ int fwi_umma_eval_vr(fwi_umma* u, const float* M_dev, int64_t ldm, int64_t N, fl
         FWI_CUDA(cudaMalloc(&u->A, (size_t)Npad * kUK * sizeof(float)));
         u->A_rows = (size_t)Npad;
     }
-    if (u->part_cap < (size_t)u->n_tgroups * N) {
+    if (u->part_cap < (size_t)u->n_tgroups * 3 * N) {
         if (u->part) cudaFree(u->part);
         u->part = nullptr; u->part_cap = 0;
-        FWI_CUDA(cudaMalloc(&u->part, (size_t)u->n_tgroups * N * sizeof(float)));
-        u->part_cap = (size_t)u->n_tgroups * N;
+        FWI_CUDA(cudaMalloc(&u->part, (size_t)u->n_tgroups * 3 * N * sizeof(double)));
+        u->part_cap = (size_t)u->n_tgroups * 3 * N;
     }
     CUtensorMap tm_a;
     int rc = encode_rows32_sw128(&tm_a, u->A, (uint64_t)Npad, kUM);
     if (rc) return rc;
-    mc_umma_pack_kernel<<<(unsigned)((Npad + 127) / 128), 128, 0, st>>>(M_dev, ldm, u->C, N, Npad, u->A);
+    mc_umma_pack_kernel<<<(unsigned)((Npad + 127) / 128), 128, 0, st>>>(M_dev, ldm, u->C, N, Npad, mode == MODE_SSE ? 1 : 0, u->A);
     FWI_CUDA(cudaGetLastError());
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, u->device);
-    const int per_group = (int)std::min<int64_t>(ngroups, std::max(1, sms / u->n_tgroups));
+    const int per_group = (int)std::min<int64_t>(ngroups, std::max(1, u->sms / u->n_tgroups));
     UmmaEvalArgs a{};
     a.N = N; a.n_groups = (int)ngroups; a.tiles_per_trace = u->tiles_per_trace; a.traces_per_cta = u->traces_per_cta;
-    a.K = u->K; a.T = u->T; a.inv_sum_d2 = u->inv_d2; a.part = u->part;
-    const int smem = kUTilesMax * kUN * kUK * 4 + kUStagesA * kUM * kUK * 4 + 256;
-    mc_umma_vr_kernel<<<dim3(per_group, u->n_tgroups), 192, smem, st>>>(tm_a, u->tm_b, a);
+    a.K = u->K; a.C = u->C; a.T = u->T; a.metric = metric; a.flags = flags;
+    const int n_last = ((u->T - (u->tiles_per_trace - 1) * kUN) + 15) & ~15;                // MMA N of a trace's last tile (multiple of 16)
+    auto idesc = [](int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kUM >> 4) << 24); };
+    a.idesc_full = idesc(kUN); a.idesc_last = idesc(n_last);
+    a.tc = u->tc; a.gbar = u->gbar; a.gdc = u->gdc; a.M = M_dev; a.ldm = ldm; a.part = u->part;
+    const dim3 grid(per_group, u->n_tgroups);
+    if (mode == MODE_SSE) mc_umma_kernel<MODE_SSE><<<grid, 192, kUSmem, st>>>(tm_a, u->tm_raw, a);
+    else if (mode == MODE_MOM) mc_umma_kernel<MODE_MOM><<<grid, 192, kUSmem, st>>>(tm_a, u->tm_cen, a);
+    else mc_umma_kernel<MODE_MOM_MAX><<<grid, 192, kUSmem, st>>>(tm_a, u->tm_cen, a);
     FWI_CUDA(cudaGetLastError());
-    mc_umma_finish_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(u->part, u->n_tgroups, N, 1.0f / u->K, sim_dev, like_dev);
+    mc_umma_finish_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(u->part, u->n_tgroups, N, u->K, metric, flags, u->fc, sim_dev, like_dev);
     FWI_CUDA(cudaGetLastError());
     return FWI_OK;
 }
 
-}  // extern "C"
+}  // namespace fwi

@@ -30,7 +30,7 @@ INVERSION_TYPES = ("full_mt", "DC", "single_force", "DC_single_force_couple", "D
 METRICS = ("VR", "CC", "PCC", "CC-shift", "gau")                                  # FWI:56
 _COMBINED = INVERSION_TYPES[3:]                                                   # FWI:797
 _PHASES = ("P", "S", "surface")                                                   # FWI:719-721
-FLAG_NORMALISED, FLAG_SIMULTANEOUS, FLAG_STRICT_REF, FLAG_GRAM = 1, 2, 4, 8
+FLAG_NORMALISED, FLAG_SIMULTANEOUS, FLAG_STRICT_REF, FLAG_GRAM, FLAG_TENSOR, FLAG_NO_TENSOR = 1, 2, 4, 8, 16, 32
 
 
 def _metric_id(comparison_metric):
@@ -159,41 +159,6 @@ class SourceInversion:
                                                 compare_all_waveforms_simultaneously, strict_reference, gram),
                                          out.ctypes.data_as(c_void_p)))
         return out
-
-
-class TensorCoreVR:
-    """The default-mode likelihood (per-trace un-normalised VR, FWI:53-56) on the tcgen05 tensor cores: 3 x TF32 split of
-    the [N x C] . [C x K T] contraction, accumulators in TMEM, the misfit folded in the TMEM epilogue (csrc/mc_umma.cu)."""
-
-    def __init__(self, real_data_array, green_func_array, device=None):
-        lib = _lib.require_gpu()
-        d = np.ascontiguousarray(real_data_array, dtype=np.float64)
-        G = np.ascontiguousarray(green_func_array, dtype=np.float64)
-        if d.ndim != 2 or G.ndim != 3 or G.shape[0] != d.shape[0] or G.shape[2] != d.shape[1]:
-            raise ValueError("real_data_array must be (K,T) and green_func_array (K,C,T)")
-        self.K, self.C, self.T = G.shape
-        self.device = torch.cuda.current_device() if device is None else int(device)
-        self._h = c_void_p()
-        self._lib = lib
-        check(lib.fwi_umma_create(self.device, G.ctypes.data_as(c_void_p), d.ctypes.data_as(c_void_p), self.K, self.C, self.T,
-                                  ctypes.byref(self._h)))
-
-    def close(self):
-        if getattr(self, "_h", None) is not None and self._h:
-            self._lib.fwi_umma_destroy(self._h)
-            self._h = None
-
-    __del__ = close
-
-    def eval_dev(self, M_dev, want_likelihood=False):
-        """M_dev (C, N) fp32 device tensor (the sampler's layout) -> similarity (N,) [, likelihood (N,)]."""
-        N = M_dev.shape[1]
-        dev = torch.device("cuda", self.device)
-        sim = torch.empty(N, dtype=torch.float32, device=dev)
-        like = torch.empty(N, dtype=torch.float32, device=dev) if want_likelihood else None
-        with torch.cuda.device(self.device):
-            check(self._lib.fwi_umma_eval_vr(self._h, ptr(M_dev), M_dev.stride(0), N, ptr(sim), ptr(like), current_stream()))
-        return (sim, like) if want_likelihood else sim
 
 
 def _as_M_dev(M, C, device):

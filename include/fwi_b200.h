@@ -51,6 +51,8 @@ enum {
     FWI_FLAG_NORMALISED   = 1,  /* perform_normallised_waveform_inversion (FWI:53)      */
     FWI_FLAG_SIMULTANEOUS = 2,  /* compare_all_waveforms_simultaneously  (FWI:54)       */
     FWI_FLAG_STRICT_REF   = 4,  /* reproduce quirk q1: per-trace 'gau' returns 0 (FWI:659-661, 678-682) */
+    FWI_FLAG_TENSOR       = 16, /* require the tensor-core path (tcgen05 3 x TF32, TMEM epilogue): error if the case is not covered */
+    FWI_FLAG_NO_TENSOR    = 32, /* keep the CUDA-core fp32 kernels (the tensor-core path is the default for N >= 256) */
     FWI_FLAG_GRAM         = 8   /* Gram-matrix mode (a different algorithm): un-normalised metrics only,
                                    O(K C^2) per sample in float64, no synthetic traces formed; one medium only */
 };
@@ -149,15 +151,6 @@ int fwi_mc_prepare(const double* raw_dev, int K, int C, int T, int n_media, cons
  *   mode 2: lune delta-gamma bins (pi/120) of the 6-vector in rows row0..row0+5, counts -> hist[122*41] (PLOT:1011-1059) */
 int fwi_mc_posterior_hist(int mode, const float* MTs_dev, int64_t ldn, const float* MTp_dev, const int64_t* idx_dev, int64_t n,
                           int row0, double* hist_dev, void* stream);
-
-/* Tensor-core (tcgen05, 3 x TF32 split, TMEM epilogue) variant of the default-mode likelihood kernel: per-trace
- * un-normalised VR (FWI:53-56 defaults; forward_model FWI:253-264 + variance_reduction FWI:512-520 + np.average FWI:682) and
- * L = exp(-(1-s)/2) (FWI:774).  G (K, C, T) and d (K, T) are float64 host arrays in the reference's layout (FWI:85);
- * M_dev is the sampler's (rows, N) fp32 layout, element (c, n) at M_dev[c * ldm + n].  C in {3, 6, 9}, T <= 1536. */
-typedef struct fwi_umma fwi_umma;
-int fwi_umma_create(int device, const double* G_host, const double* d_host, int K, int C, int T, fwi_umma** out);
-int fwi_umma_destroy(fwi_umma* ctx);
-int fwi_umma_eval_vr(fwi_umma* ctx, const float* M_dev, int64_t ldm, int64_t N, float* sim_dev, float* like_dev, void* stream);
 
 /* ===================================================================== Track B (2-D acoustic)
  * No reference counterpart exists: the specification these entry points implement is
