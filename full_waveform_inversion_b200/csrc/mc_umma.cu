@@ -35,7 +35,9 @@ namespace fwi {
 
 constexpr int kUK = 32;                 // padded K (floats per operand row = one 128-byte swizzle row)
 constexpr int kUM = 128;                // samples per MMA tile (TMEM lanes)
-constexpr int kUN = 256;                // time samples per MMA tile (TMEM columns per accumulator)
+constexpr int kUN = 256;                // time samples per resident B'' tile (one TMA box)
+constexpr int kUNacc = 128;             // time samples per accumulator stage (MMA N; TMEM columns per stage)
+constexpr int kUAcc = 4;                // accumulator stages in TMEM (4 x 128 = all 512 columns): hides the MMA <-> epilogue handshake
 constexpr int kUTilesMax = 6;           // resident B'' tiles per CTA (6 x 32 KB)
 constexpr int kUStagesA = 2;
 
@@ -94,6 +96,17 @@ __device__ __forceinline__ void tmem_ld_wait_dep(float* v) {
                  :: "memory");
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {      // FMNMX3: one instruction for two comparisons
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 __host__ __device__ inline float tf32_round(float x) {          // round to nearest-even onto the 10-bit tf32 mantissa
     uint32_t u;
     memcpy(&u, &x, 4);
@@ -108,11 +121,13 @@ __host__ __device__ inline float tf32_round(float x) {          // round to near
 struct UmmaEvalArgs {
     int64_t N;                  // samples
     int n_groups;               // 128-sample groups = ceil(N / 128)
-    int tiles_per_trace;        // ceil(T / 256)
+    int tiles_per_trace;        // ceil(T / 256): resident B'' tiles (TMA boxes) per trace
+    int chunks_per_trace;       // ceil(T / 128): accumulator stages per trace
+    int n_last;                 // MMA N of a trace's last chunk (multiple of 16, <= 128)
     int traces_per_cta;         // resident traces per CTA
     int K, C, T;
     int metric, flags;
-    uint32_t idesc_full, idesc_last;      // instruction descriptors of a full tile / of the last tile of a trace
+    uint32_t idesc_full, idesc_last;      // instruction descriptors of a full chunk / of the last chunk of a trace
     const TraceConst* tc;       // [K]
     const double* gbar;         // [K][C] mean_t G
     const double* gdc;          // [K][C] sum_t (d - mean d) G
@@ -132,9 +147,9 @@ __global__ void __launch_bounds__(192, 1) mc_umma_kernel(const __grid_constant__
     uint64_t* b_full = bars;                       // 1
     uint64_t* a_full = bars + 1;                   // [stages]
     uint64_t* a_empty = bars + 1 + kUStagesA;      // [stages]
-    uint64_t* t_full = bars + 1 + 2 * kUStagesA;   // [2]
-    uint64_t* t_empty = bars + 3 + 2 * kUStagesA;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * kUStagesA);
+    uint64_t* t_full = bars + 1 + 2 * kUStagesA;             // [kUAcc]
+    uint64_t* t_empty = bars + 1 + 2 * kUStagesA + kUAcc;    // [kUAcc]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kUStagesA + 2 * kUAcc);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tg = blockIdx.y;                                       // trace group
@@ -144,7 +159,7 @@ __global__ void __launch_bounds__(192, 1) mc_umma_kernel(const __grid_constant__
     if (threadIdx.x == 0) {
         mbar_init(b_full, 1);
         for (int s = 0; s < kUStagesA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+        for (int s = 0; s < kUAcc; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -180,15 +195,18 @@ __global__ void __launch_bounds__(192, 1) mc_umma_kernel(const __grid_constant__
                 mbar_wait(&a_full[s], (it / kUStagesA) & 1);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(a_smem + (size_t)s * kUM * kUK);
-                for (int j = 0; j < ntiles; ++j, ++acc_it) {
-                    const int buf = acc_it & 1;
-                    if (acc_it >= 2) { mbar_wait(&t_empty[buf], ((acc_it >> 1) - 1) & 1); tc_fence_after(); }
-                    const uint32_t b_addr = smem_u32(b_smem + (size_t)j * kUN * kUK);
-                    const uint32_t idesc = (j % a.tiles_per_trace == a.tiles_per_trace - 1) ? a.idesc_last : a.idesc_full;
+                for (int kk = 0; kk < k1 - k0; ++kk) {
+                    for (int ci = 0; ci < a.chunks_per_trace; ++ci, ++acc_it) {
+                        const int st = acc_it % kUAcc;
+                        if (acc_it >= kUAcc) { mbar_wait(&t_empty[st], ((acc_it / kUAcc) - 1) & 1); tc_fence_after(); }
+                        // chunk ci of trace kk: rows [128 ci, 128 ci + 128) of the trace's resident B'' tiles
+                        const uint32_t b_addr = smem_u32(b_smem + ((size_t)(kk * a.tiles_per_trace + (ci >> 1)) * kUN + (size_t)(ci & 1) * kUNacc) * kUK);
+                        const uint32_t idesc = (ci == a.chunks_per_trace - 1) ? a.idesc_last : a.idesc_full;
 #pragma unroll
-                    for (int ks = 0; ks < kUK / 8; ++ks)
-                        umma_tf32(tmem_base + buf * kUN, umma_smem_desc(a_addr + ks * 32), umma_smem_desc(b_addr + ks * 32), idesc, ks > 0);
-                    umma_commit(&t_full[buf]);                      // accumulator ready for the epilogue
+                        for (int ks = 0; ks < kUK / 8; ++ks)
+                            umma_tf32(tmem_base + st * kUNacc, umma_smem_desc(a_addr + ks * 32), umma_smem_desc(b_addr + ks * 32), idesc, ks > 0);
+                        umma_commit(&t_full[st]);                   // accumulator stage ready for the epilogue
+                    }
                 }
                 umma_commit(&a_empty[s]);                           // all MMAs reading this A'' stage have completed
             }
@@ -210,25 +228,24 @@ __global__ void __launch_bounds__(192, 1) mc_umma_kernel(const __grid_constant__
             double q0 = 0.0, q1 = 0.0, q2 = 0.0;
             for (int k = k0; k < k1; ++k) {
                 float s0 = 0.f, s1 = 0.f, s2a = 0.f, s3 = 0.f, vmax = -3.0e38f, vmin = 3.0e38f;
-                for (int tt = 0; tt < a.tiles_per_trace; ++tt, ++acc_it) {
-                    const int buf = acc_it & 1;
-                    mbar_wait(&t_full[buf], (acc_it >> 1) & 1);
+                for (int ci = 0; ci < a.chunks_per_trace; ++ci, ++acc_it) {
+                    const int st = acc_it % kUAcc;
+                    mbar_wait(&t_full[st], (acc_it / kUAcc) & 1);
                     tc_fence_after();
-                    const uint32_t taddr = tmem_base + buf * kUN + ((uint32_t)(warp * 32) << 16);
-                    const int ncol = min(kUN, a.T - tt * kUN);       // (columns past T hold 0: B'' is zero-padded)
+                    const uint32_t taddr = tmem_base + st * kUNacc + ((uint32_t)(warp * 32) << 16);
+                    // columns the MMA of this chunk wrote (those past T hold 0: B'' is zero-padded); a multiple of 16
+                    const int ncol = (ci == a.chunks_per_trace - 1) ? a.n_last : kUNacc;
                     float va[32], vb[32];
-                    auto fold = [&](const float* v, int valid) {
+                    auto fold = [&](const float* v, int valid) {      // valid: 32, or 16 in a trace's last piece
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
-                            s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
-                            s2a = fmaf(v[i + 2], v[i + 2], s2a); s3 = fmaf(v[i + 3], v[i + 3], s3);
-                        }
-                        if (MODE == MODE_MOM_MAX) {
-                            if (valid >= 32) {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) { vmax = fmaxf(vmax, v[i]); vmin = fminf(vmin, v[i]); }
-                            } else {
-                                for (int i = 0; i < valid; ++i) { vmax = fmaxf(vmax, v[i]); vmin = fminf(vmin, v[i]); }
+                            if (i < 16 || valid > 16) {
+                                s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
+                                s2a = fmaf(v[i + 2], v[i + 2], s2a); s3 = fmaf(v[i + 3], v[i + 3], s3);
+                                if (MODE == MODE_MOM_MAX) {
+                                    vmax = fmax3(vmax, v[i], v[i + 1]); vmin = fmin3(vmin, v[i], v[i + 1]);
+                                    vmax = fmax3(vmax, v[i + 2], v[i + 3]); vmin = fmin3(vmin, v[i + 2], v[i + 3]);
+                                }
                             }
                         }
                     };
@@ -245,7 +262,7 @@ __global__ void __launch_bounds__(192, 1) mc_umma_kernel(const __grid_constant__
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&t_empty[buf]);       // accumulator drained by this warp
+                    if (lane == 0) mbar_arrive(&t_empty[st]);        // accumulator stage drained by this warp
                 }
                 // ---- combine trace k (float64; the expressions of mc_eval_kernel's fold)
                 const TraceConst tc = a.tc[k];
@@ -499,9 +516,10 @@ int umma_eval(UmmaPath* u, const float* M_dev, int64_t ldm, int64_t N, int metri
     UmmaEvalArgs a{};
     a.N = N; a.n_groups = (int)ngroups; a.tiles_per_trace = u->tiles_per_trace; a.traces_per_cta = u->traces_per_cta;
     a.K = u->K; a.C = u->C; a.T = u->T; a.metric = metric; a.flags = flags;
-    const int n_last = ((u->T - (u->tiles_per_trace - 1) * kUN) + 15) & ~15;                // MMA N of a trace's last tile (multiple of 16)
+    a.chunks_per_trace = (u->T + kUNacc - 1) / kUNacc;
+    a.n_last = ((u->T - (a.chunks_per_trace - 1) * kUNacc) + 15) & ~15;                     // MMA N of a trace's last chunk (multiple of 16)
     auto idesc = [](int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kUM >> 4) << 24); };
-    a.idesc_full = idesc(kUN); a.idesc_last = idesc(n_last);
+    a.idesc_full = idesc(kUNacc); a.idesc_last = idesc(a.n_last);
     a.tc = u->tc; a.gbar = u->gbar; a.gdc = u->gdc; a.M = M_dev; a.ldm = ldm; a.part = u->part;
     const dim3 grid(per_group, u->n_tgroups);
     if (mode == MODE_SSE) mc_umma_kernel<MODE_SSE><<<grid, 192, kUSmem, st>>>(tm_a, u->tm_raw, a);
