@@ -23,7 +23,7 @@
 // Per group and tile: 4 MMAs (128 x 256 x 8) into one of two TMEM accumulators (2 x 256 columns), committed to an
 // mbarrier the four epilogue warps wait on; they hand the accumulator back through a second mbarrier.
 //
-// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp index), warp 4 TMA producer, warp 5 MMA issuer.
+// Warp roles (320 threads): warps 0-7 epilogue (two pipelines x four TMEM lane quarters), warp 8 TMA producer, warp 9 MMA issuer.
 #include "fd_common.cuh"
 #include "mc_common.cuh"
 #include <vector>
@@ -36,10 +36,10 @@ namespace fwi {
 constexpr int kUK = 32;                 // padded K (floats per operand row = one 128-byte swizzle row)
 constexpr int kUM = 128;                // samples per MMA tile (TMEM lanes)
 constexpr int kUN = 256;                // time samples per resident B'' tile (one TMA box)
-constexpr int kUNacc = 128;             // time samples per accumulator stage (MMA N; TMEM columns per stage)
-constexpr int kUAcc = 4;                // accumulator stages in TMEM (4 x 128 = all 512 columns): hides the MMA <-> epilogue handshake
+constexpr int kUNacc = 256;             // time samples per accumulator (MMA N; TMEM columns per pipeline).  Measured (N = 4e6, VR): the
+                                        // MMA <-> epilogue handshake costs ~0.25 us per accumulator use whatever its size, so
+                                        // 2 x 256 columns beat 4 x 128 (9.4 vs 8.0 ms before the second pipeline)
 constexpr int kUTilesMax = 6;           // resident B'' tiles per CTA (6 x 32 KB)
-constexpr int kUStagesA = 2;
 
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
     // K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (1), descriptor version 1
@@ -96,6 +96,18 @@ __device__ __forceinline__ void tmem_ld_wait_dep(float* v) {
                  :: "memory");
 }
 
+// float64 reciprocal / reciprocal square root from the fp32 SFU seed + two Newton steps (FMA only): the fp64 divide and
+// sqrt sequences were the largest part of the per-trace combination
+__device__ __forceinline__ double rcp64(double x) {
+    double r = (double)__frcp_rn((float)x);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+__device__ __forceinline__ double rsqrt64(double x) {
+    double y = (double)rsqrtf((float)x);
+    y = y * fma(-0.5 * x, y * y, 1.5);
+    return y * fma(-0.5 * x, y * y, 1.5);
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {      // FMNMX3: one instruction for two comparisons
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -126,7 +138,7 @@ struct UmmaEvalArgs {
     int n_last;                 // MMA N of a trace's last chunk (multiple of 16, <= 128)
     int traces_per_cta;         // resident traces per CTA
     int K, C, T;
-    int metric, flags;
+    int metric, flags, debug;      // debug (FWI_UMMA_DEBUG): 1 = no MMAs issued, 2 = no TMEM loads / folds (timing experiments)
     uint32_t idesc_full, idesc_last;      // instruction descriptors of a full chunk / of the last chunk of a trace
     const TraceConst* tc;       // [K]
     const double* gbar;         // [K][C] mean_t G
@@ -136,40 +148,45 @@ struct UmmaEvalArgs {
     double* part;               // [n_trace_groups][3][N] partial sums of the per-trace combination
 };
 
-// grid = (ctas_per_trace_group, n_trace_groups); block = 192
+// grid = (ctas_per_trace_group, n_trace_groups); block = 320.
+// Two pipelines per CTA, each with its own sample group in flight, its own A'' stage, its own TMEM accumulator (256 columns)
+// and its own four epilogue warps; the MMA issuer alternates between them.  Measured on B200: the MMA <-> epilogue
+// handshake of one accumulator costs ~0.3 us per use and the epilogue's serial work (TMEM load latency, per-trace
+// combination) does not overlap with its own pipeline's MMAs, so two independent pipelines on the same resident B'' tiles
+// is what keeps the tensor core and the epilogue warps busy at the same time.
 template <int MODE>
-__global__ void __launch_bounds__(192, 1) mc_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+__global__ void __launch_bounds__(320, 1) mc_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                                                            UmmaEvalArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* b_smem = reinterpret_cast<float*>(smem);                                    // [tiles][256][32] swizzled
-    float* a_smem = reinterpret_cast<float*>(smem + (size_t)kUTilesMax * kUN * kUK * 4); // [stages][128][32] swizzled
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kUTilesMax * kUN * kUK * 4 + (size_t)kUStagesA * kUM * kUK * 4);
+    float* a_smem = reinterpret_cast<float*>(smem + (size_t)kUTilesMax * kUN * kUK * 4); // [pipeline][128][32] swizzled
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kUTilesMax * kUN * kUK * 4 + (size_t)2 * kUM * kUK * 4);
     uint64_t* b_full = bars;                       // 1
-    uint64_t* a_full = bars + 1;                   // [stages]
-    uint64_t* a_empty = bars + 1 + kUStagesA;      // [stages]
-    uint64_t* t_full = bars + 1 + 2 * kUStagesA;             // [kUAcc]
-    uint64_t* t_empty = bars + 1 + 2 * kUStagesA + kUAcc;    // [kUAcc]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kUStagesA + 2 * kUAcc);
+    uint64_t* a_full = bars + 1;                   // [2]
+    uint64_t* a_empty = bars + 3;                  // [2]
+    uint64_t* t_full = bars + 5;                   // [2]
+    uint64_t* t_empty = bars + 7;                  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tg = blockIdx.y;                                       // trace group
     const int k0 = tg * a.traces_per_cta, k1 = min(a.K, k0 + a.traces_per_cta);
     const int ntiles = (k1 - k0) * a.tiles_per_trace;                // resident tiles of this CTA
+    const int nchunks = (k1 - k0) * a.chunks_per_trace;              // accumulator uses per sample group
 
     if (threadIdx.x == 0) {
         mbar_init(b_full, 1);
-        for (int s = 0; s < kUStagesA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < kUAcc; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
         fence_mbar_init();
         fence_proxy_async();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    if (warp == 9) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ------------------------------------------------ TMA producer: resident B'' tiles once, then the A'' tile of every group
         if (lane == 0) {
             mbar_expect_tx(b_full, (uint32_t)ntiles * kUN * kUK * 4);
@@ -177,48 +194,57 @@ __global__ void __launch_bounds__(192, 1) mc_umma_kernel(const __grid_constant__
                 const int k = k0 + j / a.tiles_per_trace, tt = j % a.tiles_per_trace;
                 tma_load_2d(b_smem + (size_t)j * kUN * kUK, &tm_b, 0, (k * a.tiles_per_trace + tt) * kUN, b_full);
             }
-            int it = 0;
-            for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x, ++it) {
-                const int s = it % kUStagesA;
-                if (it >= kUStagesA) mbar_wait(&a_empty[s], ((it / kUStagesA) - 1) & 1);
-                mbar_expect_tx(&a_full[s], kUM * kUK * 4);
-                tma_load_2d(a_smem + (size_t)s * kUM * kUK, &tm_a, 0, g * kUM, &a_full[s]);
+            int i = 0;
+            for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x, ++i) {
+                const int p = i & 1, use = i >> 1;                     // pipeline, and how often its A'' stage has been used
+                if (use >= 1) mbar_wait(&a_empty[p], (use - 1) & 1);
+                mbar_expect_tx(&a_full[p], kUM * kUK * 4);
+                tma_load_2d(a_smem + (size_t)p * kUM * kUK, &tm_a, 0, g * kUM, &a_full[p]);
             }
         }
-    } else if (warp == 5) {
-        // ------------------------------------------------ MMA issuer (one elected lane)
+    } else if (warp == 9) {
+        // ------------------------------------------------ MMA issuer (one elected lane), alternating between the two pipelines
         if (lane == 0) {
             mbar_wait(b_full, 0);
-            int it = 0, acc_it = 0;
-            for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x, ++it) {
-                const int s = it % kUStagesA;
-                mbar_wait(&a_full[s], (it / kUStagesA) & 1);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(a_smem + (size_t)s * kUM * kUK);
-                for (int kk = 0; kk < k1 - k0; ++kk) {
-                    for (int ci = 0; ci < a.chunks_per_trace; ++ci, ++acc_it) {
-                        const int st = acc_it % kUAcc;
-                        if (acc_it >= kUAcc) { mbar_wait(&t_empty[st], ((acc_it / kUAcc) - 1) & 1); tc_fence_after(); }
-                        // chunk ci of trace kk: rows [128 ci, 128 ci + 128) of the trace's resident B'' tiles
-                        const uint32_t b_addr = smem_u32(b_smem + ((size_t)(kk * a.tiles_per_trace + (ci >> 1)) * kUN + (size_t)(ci & 1) * kUNacc) * kUK);
-                        const uint32_t idesc = (ci == a.chunks_per_trace - 1) ? a.idesc_last : a.idesc_full;
+            int grp[2] = {blockIdx.x, blockIdx.x + (int)gridDim.x};      // the group each pipeline works on
+            int use_a[2] = {0, 0}, use_t[2] = {0, 0}, chunk[2] = {0, 0};
+            bool busy = true;
+            while (busy) {
+                busy = false;
 #pragma unroll
-                        for (int ks = 0; ks < kUK / 8; ++ks)
-                            umma_tf32(tmem_base + st * kUNacc, umma_smem_desc(a_addr + ks * 32), umma_smem_desc(b_addr + ks * 32), idesc, ks > 0);
-                        umma_commit(&t_full[st]);                   // accumulator stage ready for the epilogue
+                for (int p = 0; p < 2; ++p) {
+                    if (grp[p] >= a.n_groups) continue;
+                    busy = true;
+                    if (chunk[p] == 0) { mbar_wait(&a_full[p], use_a[p] & 1); tc_fence_after(); }
+                    if (use_t[p] >= 1) { mbar_wait(&t_empty[p], (use_t[p] - 1) & 1); tc_fence_after(); }
+                    const int kk = chunk[p] / a.chunks_per_trace, ci = chunk[p] % a.chunks_per_trace;
+                    const uint32_t a_addr = smem_u32(a_smem + (size_t)p * kUM * kUK);
+                    const uint32_t b_addr = smem_u32(b_smem + ((size_t)(kk * a.tiles_per_trace) * kUN + (size_t)ci * kUNacc) * kUK);
+                    const uint32_t idesc = (ci == a.chunks_per_trace - 1) ? a.idesc_last : a.idesc_full;
+                    if (!(a.debug & 1))
+#pragma unroll
+                    for (int ks = 0; ks < kUK / 8; ++ks)
+                        umma_tf32(tmem_base + p * kUNacc, umma_smem_desc(a_addr + ks * 32), umma_smem_desc(b_addr + ks * 32), idesc, ks > 0);
+                    umma_commit(&t_full[p]);                        // accumulator ready for this pipeline's epilogue warps
+                    ++use_t[p];
+                    if (++chunk[p] == nchunks) {
+                        umma_commit(&a_empty[p]);                   // all MMAs reading this A'' tile have completed
+                        chunk[p] = 0; ++use_a[p];
+                        grp[p] += 2 * gridDim.x;
                     }
                 }
-                umma_commit(&a_empty[s]);                           // all MMAs reading this A'' stage have completed
             }
         }
     } else {
-        // ------------------------------------------------ epilogue warps 0..3: one sample per thread, TMEM lane = 32 * warp + lane
+        // ------------------------------------------------ epilogue warps: pipeline p = warp / 4, TMEM lane quarter = warp % 4,
+        //                                                  one sample per thread
+        const int p = warp >> 2, wq = warp & 3;
         const bool simul = a.flags & FWI_FLAG_SIMULTANEOUS;
         const bool vr_like = a.metric == FWI_METRIC_VR || a.metric == FWI_METRIC_GAU;
         const double Tn = (double)a.T;
-        int acc_it = 0;
-        for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
-            const int64_t n = (int64_t)g * kUM + warp * 32 + lane;
+        int use_t = 0;
+        for (int g = blockIdx.x + p * gridDim.x; g < a.n_groups; g += 2 * gridDim.x) {
+            const int64_t n = (int64_t)g * kUM + wq * 32 + lane;
             const bool live = n < a.N;
             double coef[9];
             if (MODE != MODE_SSE) {
@@ -228,41 +254,34 @@ __global__ void __launch_bounds__(192, 1) mc_umma_kernel(const __grid_constant__
             double q0 = 0.0, q1 = 0.0, q2 = 0.0;
             for (int k = k0; k < k1; ++k) {
                 float s0 = 0.f, s1 = 0.f, s2a = 0.f, s3 = 0.f, vmax = -3.0e38f, vmin = 3.0e38f;
-                for (int ci = 0; ci < a.chunks_per_trace; ++ci, ++acc_it) {
-                    const int st = acc_it % kUAcc;
-                    mbar_wait(&t_full[st], (acc_it / kUAcc) & 1);
+                for (int ci = 0; ci < a.chunks_per_trace; ++ci, ++use_t) {
+                    mbar_wait(&t_full[p], use_t & 1);
                     tc_fence_after();
-                    const uint32_t taddr = tmem_base + st * kUNacc + ((uint32_t)(warp * 32) << 16);
+                    const uint32_t taddr = tmem_base + p * kUNacc + ((uint32_t)(wq * 32) << 16);
                     // columns the MMA of this chunk wrote (those past T hold 0: B'' is zero-padded); a multiple of 16
                     const int ncol = (ci == a.chunks_per_trace - 1) ? a.n_last : kUNacc;
-                    float va[32], vb[32];
-                    auto fold = [&](const float* v, int valid) {      // valid: 32, or 16 in a trace's last piece
+                    if (!(a.debug & 2)) {
+                        for (int c0 = 0; c0 < ncol; c0 += 32) {
+                            float v[32];
+                            tmem_ld32(taddr + c0, v);
+                            tmem_ld_wait_dep(v);
+                            const bool half = ncol - c0 < 32;           // a trace's last piece may hold 16 columns
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            if (i < 16 || valid > 16) {
-                                s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
-                                s2a = fmaf(v[i + 2], v[i + 2], s2a); s3 = fmaf(v[i + 3], v[i + 3], s3);
-                                if (MODE == MODE_MOM_MAX) {
-                                    vmax = fmax3(vmax, v[i], v[i + 1]); vmin = fmin3(vmin, v[i], v[i + 1]);
-                                    vmax = fmax3(vmax, v[i + 2], v[i + 3]); vmin = fmin3(vmin, v[i + 2], v[i + 3]);
+                            for (int i = 0; i < 32; i += 4) {
+                                if (i < 16 || !half) {
+                                    s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
+                                    s2a = fmaf(v[i + 2], v[i + 2], s2a); s3 = fmaf(v[i + 3], v[i + 3], s3);
+                                    if (MODE == MODE_MOM_MAX) {
+                                        vmax = fmax3(vmax, v[i], v[i + 1]); vmin = fmin3(vmin, v[i], v[i + 1]);
+                                        vmax = fmax3(vmax, v[i + 2], v[i + 3]); vmin = fmin3(vmin, v[i + 2], v[i + 3]);
+                                    }
                                 }
                             }
-                        }
-                    };
-                    tmem_ld32(taddr, va);
-                    for (int c0 = 0; c0 < ncol; c0 += 64) {
-                        tmem_ld_wait_dep(va);
-                        if (c0 + 32 < ncol) tmem_ld32(taddr + c0 + 32, vb);
-                        fold(va, ncol - c0);
-                        if (c0 + 32 < ncol) {
-                            tmem_ld_wait_dep(vb);
-                            if (c0 + 64 < ncol) tmem_ld32(taddr + c0 + 64, va);
-                            fold(vb, ncol - c0 - 32);
                         }
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&t_empty[st]);        // accumulator stage drained by this warp
+                    if (lane == 0) mbar_arrive(&t_empty[p]);         // accumulator drained by this warp
                 }
                 // ---- combine trace k (float64; the expressions of mc_eval_kernel's fold)
                 const TraceConst tc = a.tc[k];
@@ -270,7 +289,7 @@ __global__ void __launch_bounds__(192, 1) mc_umma_kernel(const __grid_constant__
                 if (MODE == MODE_SSE) {
                     const double sse = s2, dd = tc.sumd2;
                     q1 += sse; q2 += dd;
-                    if (a.metric == FWI_METRIC_VR) q0 += fmax(0.0, 1.0 - sse / dd);            // FWI:515-519
+                    if (a.metric == FWI_METRIC_VR) q0 += fmax(0.0, fma(-sse, rcp64(dd), 1.0));     // FWI:515-519
                     else q0 += exp(-sse / (2.0 * tc.sigma * tc.sigma));                         // FWI:581
                 } else {
                     double mud = 0.0, sd = 0.0;
@@ -280,8 +299,8 @@ __global__ void __launch_bounds__(192, 1) mc_umma_kernel(const __grid_constant__
                     }
                     double aa = 1.0, bb = 1.0;
                     if (MODE == MODE_MOM_MAX) {
-                        aa = 1.0 / fmax(fabs((double)vmax + mud), fabs((double)vmin + mud));      // FWI:598-599
-                        bb = 1.0 / tc.maxd;
+                        aa = rcp64(fmax(fabs((double)vmax + mud), fabs((double)vmin + mud)));     // FWI:598-599
+                        bb = rcp64(tc.maxd);
                     }
                     if (vr_like) {
                         const double Sss = (s2 + Tn * mud * mud) * aa * aa;
@@ -290,10 +309,10 @@ __global__ void __launch_bounds__(192, 1) mc_umma_kernel(const __grid_constant__
                         const double sse = dd - 2.0 * Sds + Sss;
                         const double sig = tc.sigma * bb;
                         q1 += sse; q2 += dd;
-                        if (a.metric == FWI_METRIC_VR) q0 += fmax(0.0, 1.0 - sse / dd);
+                        if (a.metric == FWI_METRIC_VR) q0 += fmax(0.0, fma(-sse, rcp64(dd), 1.0));
                         else q0 += exp(-sse / (2.0 * sig * sig));
                     } else if (!simul) {
-                        const double pcc = sd / sqrt(s2 * tc.ssd);                              // FWI:572-573
+                        const double pcc = sd * rsqrt64(s2 * tc.ssd);                           // FWI:572-573
                         q0 += (pcc < 0.0) ? 0.0 : pcc;                                          // FWI:574-575
                     } else {
                         q0 += aa * Tn * mud;
@@ -310,7 +329,7 @@ __global__ void __launch_bounds__(192, 1) mc_umma_kernel(const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, 512);
+    if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
 
 // A''[n][32] from the sampler's (rows, N) layout; `with_d`: the two -1 columns that subtract d (MODE_SSE)
@@ -405,7 +424,7 @@ struct UmmaPath {
     CUtensorMap tm_raw, tm_cen;
 };
 
-constexpr int kUSmem = kUTilesMax * kUN * kUK * 4 + kUStagesA * kUM * kUK * 4 + 256;
+constexpr int kUSmem = kUTilesMax * kUN * kUK * 4 + 2 * kUM * kUK * 4 + 256;
 
 int umma_build(UmmaPath** out, int device, const double* G, const double* d, int K, int C, int T, const TraceConst* tc_dev,
                const FlatConst& fc) {
@@ -516,15 +535,16 @@ int umma_eval(UmmaPath* u, const float* M_dev, int64_t ldm, int64_t N, int metri
     UmmaEvalArgs a{};
     a.N = N; a.n_groups = (int)ngroups; a.tiles_per_trace = u->tiles_per_trace; a.traces_per_cta = u->traces_per_cta;
     a.K = u->K; a.C = u->C; a.T = u->T; a.metric = metric; a.flags = flags;
+    { const char* e = getenv("FWI_UMMA_DEBUG"); a.debug = e ? atoi(e) : 0; }
     a.chunks_per_trace = (u->T + kUNacc - 1) / kUNacc;
     a.n_last = ((u->T - (a.chunks_per_trace - 1) * kUNacc) + 15) & ~15;                     // MMA N of a trace's last chunk (multiple of 16)
     auto idesc = [](int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kUM >> 4) << 24); };
     a.idesc_full = idesc(kUNacc); a.idesc_last = idesc(a.n_last);
     a.tc = u->tc; a.gbar = u->gbar; a.gdc = u->gdc; a.M = M_dev; a.ldm = ldm; a.part = u->part;
     const dim3 grid(per_group, u->n_tgroups);
-    if (mode == MODE_SSE) mc_umma_kernel<MODE_SSE><<<grid, 192, kUSmem, st>>>(tm_a, u->tm_raw, a);
-    else if (mode == MODE_MOM) mc_umma_kernel<MODE_MOM><<<grid, 192, kUSmem, st>>>(tm_a, u->tm_cen, a);
-    else mc_umma_kernel<MODE_MOM_MAX><<<grid, 192, kUSmem, st>>>(tm_a, u->tm_cen, a);
+    if (mode == MODE_SSE) mc_umma_kernel<MODE_SSE><<<grid, 320, kUSmem, st>>>(tm_a, u->tm_raw, a);
+    else if (mode == MODE_MOM) mc_umma_kernel<MODE_MOM><<<grid, 320, kUSmem, st>>>(tm_a, u->tm_cen, a);
+    else mc_umma_kernel<MODE_MOM_MAX><<<grid, 320, kUSmem, st>>>(tm_a, u->tm_cen, a);
     FWI_CUDA(cudaGetLastError());
     mc_umma_finish_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(u->part, u->n_tgroups, N, u->K, metric, flags, u->fc, sim_dev, like_dev);
     FWI_CUDA(cudaGetLastError());
