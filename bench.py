@@ -222,11 +222,25 @@ def track_a_numbers(device, dist=None, cpu=True):
                             "collective": "one NCCL all-reduce of sum L (float64 scalar) per batch"}
         prob.close()
         return out
+    NO_TENSOR = 32          # FWI_FLAG_NO_TENSOR: the CUDA-core fp32 kernels (the tensor-core path is the default for N >= 256)
     for N in (10_000, 4_000_000):
         for _ in range(3):
             prob.sample_eval_dev(6, 1, 0, N, amp, 0, 0)
         dt_ = _ev_time(torch, dev, lambda r: prob.sample_eval_dev(6, 1 + r, 0, N, amp, 0, 0, reduce=False), 5)
-        out["N=%d" % N] = {"samples_per_s": N / dt_, "ms": dt_ * 1e3, "fp32_tflops_direct": N * flops / dt_ / 1e12}
+        dt_c = _ev_time(torch, dev, lambda r: prob.sample_eval_dev(6, 1 + r, 0, N, amp, 0, NO_TENSOR, reduce=False), 5)
+        out["N=%d" % N] = {"samples_per_s": N / dt_, "ms": dt_ * 1e3, "path": "tcgen05 3xTF32 + TMEM epilogue (default)",
+                           "tf32_tflops_issued": N * 2 * 32 * K * T / dt_ / 1e12,
+                           "cuda_core_fp32": {"samples_per_s": N / dt_c, "ms": dt_c * 1e3, "fp32_tflops_direct": N * flops / dt_c / 1e12}}
+    # the other metric families on the tensor cores vs the CUDA cores (N = 4e6, device-resident, sampler included)
+    fam = {}
+    for name, metric, fl in (("VR_normalised_flattened", 0, 3), ("PCC_per_trace", 2, 0), ("PCC_normalised_flattened", 2, 3), ("gau_per_trace", 4, 0)):
+        N = 4_000_000
+        prob.sample_eval_dev(6, 1, 0, N, amp, metric, fl, reduce=False)
+        prob.sample_eval_dev(6, 1, 0, N, amp, metric, fl | NO_TENSOR, reduce=False)
+        t1 = _ev_time(torch, dev, lambda r: prob.sample_eval_dev(6, 1 + r, 0, N, amp, metric, fl, reduce=False), 3)
+        t2 = _ev_time(torch, dev, lambda r: prob.sample_eval_dev(6, 1 + r, 0, N, amp, metric, fl | NO_TENSOR, reduce=False), 3)
+        fam[name] = {"tensor_core_samples_per_s": N / t1, "cuda_core_samples_per_s": N / t2}
+    out["metric_families_N=4000000"] = fam
     # Gram-matrix mode: a different algorithm (2 K C^2 fp64 flop per sample, un-normalised metrics only) - own line
     N = 4_000_000
     prob.sample_eval_dev(6, 1, 0, N, amp, 0, 8, reduce=False)
@@ -251,10 +265,22 @@ def track_a_numbers(device, dist=None, cpu=True):
     from full_waveform_inversion_b200 import _lib
     peak = ctypes.c_double(0.0)
     _lib.check(_lib.require_gpu().fwi_diag_fp32_peak(device, ctypes.byref(peak)))
-    ach = out["N=4000000"]["fp32_tflops_direct"]
-    out["roofline"] = {"bound": "fp32 fma", "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value,
-                       "peak_source": "measured: register-only FMA kernel (fwi_diag_fp32_peak)",
-                       "algorithmic_flop_per_sample": flops}
+    ach = out["N=4000000"]["cuda_core_fp32"]["fp32_tflops_direct"]
+    out["roofline_cuda_core_fp32"] = {"bound": "fp32 fma", "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value,
+                                      "peak_source": "measured: register-only FMA kernel (fwi_diag_fp32_peak)",
+                                      "algorithmic_flop_per_sample": flops}
+    bf16 = None
+    try:
+        bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        pass
+    tf32_peak = (bf16 / 2.0) if bf16 else 1125.0
+    issued = out["N=4000000"]["tf32_tflops_issued"]
+    out["roofline"] = {"bound": "tensor", "achieved": issued, "peak": tf32_peak, "unit": "TFLOP/s", "frac": issued / tf32_peak,
+                       "peak_source": ("half of MEASURED_PEAKS.json bf16_tflops (TF32 runs at half the bf16 rate)" if bf16 else "nominal 1125 TFLOP/s dense TF32"),
+                       "issued_flop_per_sample": 2 * 32 * K * T,
+                       "note": "flops ISSUED to the tensor cores: the 3 x TF32 split pads the 10-term contraction to K = 32; in units of the "
+                               "direct algorithm ((2C+3) K T = %d flop per sample) the default path delivers %.1f TFLOP/s-equivalent" % (flops, out["N=4000000"]["samples_per_s"] * flops / 1e12)}
     # trace-length sweep of config 1 (T in {128, 512, 2048})
     gpu_T = {512: out["N=4000000"]["samples_per_s"]}
     for T2 in (128, 2048):
@@ -263,7 +289,10 @@ def track_a_numbers(device, dist=None, cpu=True):
         N2 = 4_000_000 if T2 == 128 else 1_000_000
         pr2.sample_eval_dev(6, 1, 0, N2, amp, 0, 0, reduce=False)
         dt_ = _ev_time(torch, dev, lambda r: pr2.sample_eval_dev(6, 1 + r, 0, N2, amp, 0, 0, reduce=False), 3)
-        out["T=%d_N=%d" % (T2, N2)] = {"samples_per_s": N2 / dt_, "fp32_tflops_direct": N2 * (2 * C + 3) * K * T2 / dt_ / 1e12}
+        if T2 <= 1536:
+            out["T=%d_N=%d" % (T2, N2)] = {"samples_per_s": N2 / dt_, "tf32_tflops_issued": N2 * 2 * 32 * K * T2 / dt_ / 1e12, "path": "tensor cores"}
+        else:       # B'' of one trace (T x 128 B) no longer fits in shared memory: the CUDA-core kernels take over
+            out["T=%d_N=%d" % (T2, N2)] = {"samples_per_s": N2 / dt_, "fp32_tflops_direct": N2 * (2 * C + 3) * K * T2 / dt_ / 1e12, "path": "CUDA cores (T > 1536)"}
         gpu_T[T2] = N2 / dt_
         pr2.close()
     prob.close()
