@@ -4,9 +4,10 @@ shared/global accesses).   python tools/sass_summary.py > profiles/r2_sass_summa
 import os, re, subprocess, sys, collections
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "full_waveform_inversion_b200", "libfwi_b200.so")
-HOT = ("fd2d_step_kernel", "fd2d_tb2_kernel", "fd3d_step_kernel", "mc_eval_kernel", "mc_sample_kernel", "fd3d_slab_sync")
+HOT = ("fd2d_step_kernel", "fd2d_tb2_kernel", "fd3d_step_kernel", "mc_umma_kernel", "mc_umma_pack", "mc_eval_kernel", "mc_sample_kernel", "fd3d_slab_sync")
 PAT = collections.OrderedDict([
-    ("UTMALDG", r"\bUTMALDG"), ("SYNCS(mbarrier)", r"\bSYNCS"), ("FFMA", r"\bFFMA"), ("FADD", r"\bFADD"), ("FMUL", r"\bFMUL"),
+    ("UTMALDG", r"\bUTMALDG"), ("UTCHMMA(tcgen05.mma)", r"\bUTCHMMA"), ("LDTM(tcgen05.ld)", r"\bLDTM"), ("UTCBAR(tcgen05.commit)", r"\bUTCBAR"),
+    ("UTCATOMSWS(tmem alloc)", r"\bUTCATOMSWS"), ("FMNMX3", r"\bFMNMX3"), ("SYNCS(mbarrier)", r"\bSYNCS"), ("FFMA", r"\bFFMA"), ("FADD", r"\bFADD"), ("FMUL", r"\bFMUL"),
     ("LDS.128", r"\bLDS\.(U\.)?128"), ("LDS", r"\bLDS"), ("LDG.128", r"\bLDG\.E\.(\w+\.)*128"), ("LDG", r"\bLDG"),
     ("STG.128", r"\bSTG\.E\.(\w+\.)*128"), ("STG", r"\bSTG"), ("ATOM/RED", r"\b(ATOMG|RED|ATOMS)\b"), ("BAR", r"\bBAR\."),
     ("ACQBULK", r"ACQBULK"), ("DFMA", r"\bDFMA"), ("MUFU", r"\bMUFU")])
