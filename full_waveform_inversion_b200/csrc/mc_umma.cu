@@ -35,12 +35,14 @@ namespace fwi {
 
 constexpr int kUK = 32;                 // padded K (floats per operand row = one 128-byte swizzle row)
 constexpr int kUM = 128;                // samples per MMA tile (TMEM lanes)
+#ifndef FWI_UMMA_PIPES
+#define FWI_UMMA_PIPES 2
+#endif
 constexpr int kUN = 256;                // time samples per resident B'' tile (one TMA box)
-constexpr int kUNacc = 256;             // time samples per accumulator (MMA N; TMEM columns per pipeline).  Measured (N = 4e6, VR): the
-                                        // MMA <-> epilogue handshake costs ~0.25 us per accumulator use whatever its size, so
-                                        // 2 x 256 columns beat 4 x 128 (9.4 vs 8.0 ms before the second pipeline)
-constexpr int kUTilesMax = 6;           // resident B'' tiles per CTA (6 x 32 KB)
-
+constexpr int kUPipes = FWI_UMMA_PIPES; // independent pipelines per CTA (sample groups in flight).  2 x 256 columns: 5.7 ms for N = 4e6 (VR);
+                                        // 4 x 128: 9.2 ms - the single MMA-issuing lane pays ~0.45 us per accumulator use whatever its size
+constexpr int kUNacc = 512 / kUPipes;   // time samples per accumulator use (MMA N; every pipeline owns 512 / pipes TMEM columns)
+constexpr int kUTilesMax = (227 * 1024 - kUPipes * 16384 - 1024) / (kUN * 128);
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
     // K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (1), descriptor version 1
     uint64_t d = 0;
@@ -137,6 +139,7 @@ struct UmmaEvalArgs {
     int chunks_per_trace;       // ceil(T / 128): accumulator stages per trace
     int n_last;                 // MMA N of a trace's last chunk (multiple of 16, <= 128)
     int traces_per_cta;         // resident traces per CTA
+    int ctas_full, ctas_last;   // CTAs working on a trace group with traces_per_cta traces / on the last (possibly smaller) group
     int K, C, T;
     int metric, flags, debug;      // debug (FWI_UMMA_DEBUG): 1 = no MMAs issued, 2 = no TMEM loads / folds (timing experiments)
     uint32_t idesc_full, idesc_last;      // instruction descriptors of a full chunk / of the last chunk of a trace
@@ -148,45 +151,50 @@ struct UmmaEvalArgs {
     double* part;               // [n_trace_groups][3][N] partial sums of the per-trace combination
 };
 
-// grid = (ctas_per_trace_group, n_trace_groups); block = 320.
-// Two pipelines per CTA, each with its own sample group in flight, its own A'' stage, its own TMEM accumulator (256 columns)
-// and its own four epilogue warps; the MMA issuer alternates between them.  Measured on B200: the MMA <-> epilogue
+// grid = (ctas_per_trace_group, n_trace_groups); block = (4 * pipelines + 2) warps.
+// Several pipelines per CTA, each with its own sample group in flight, its own A'' stage, its own TMEM accumulator (512 /
+// pipelines columns) and its own four epilogue warps; the MMA issuer goes round robin over them.  Measured on B200: the MMA <-> epilogue
 // handshake of one accumulator costs ~0.3 us per use and the epilogue's serial work (TMEM load latency, per-trace
 // combination) does not overlap with its own pipeline's MMAs, so two independent pipelines on the same resident B'' tiles
 // is what keeps the tensor core and the epilogue warps busy at the same time.
+constexpr int kUThreads = (4 * kUPipes + 2) * 32;        // 4 epilogue warps per pipeline + TMA producer + MMA issuer
 template <int MODE>
-__global__ void __launch_bounds__(320, 1) mc_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                                                           UmmaEvalArgs a) {
+__global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                                                               UmmaEvalArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* b_smem = reinterpret_cast<float*>(smem);                                    // [tiles][256][32] swizzled
     float* a_smem = reinterpret_cast<float*>(smem + (size_t)kUTilesMax * kUN * kUK * 4); // [pipeline][128][32] swizzled
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kUTilesMax * kUN * kUK * 4 + (size_t)2 * kUM * kUK * 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kUTilesMax * kUN * kUK * 4 + (size_t)kUPipes * kUM * kUK * 4);
     uint64_t* b_full = bars;                       // 1
-    uint64_t* a_full = bars + 1;                   // [2]
-    uint64_t* a_empty = bars + 3;                  // [2]
-    uint64_t* t_full = bars + 5;                   // [2]
-    uint64_t* t_empty = bars + 7;                  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* a_full = bars + 1;                   // [pipes]
+    uint64_t* a_empty = a_full + kUPipes;          // [pipes]
+    uint64_t* t_full = a_empty + kUPipes;          // [pipes]
+    uint64_t* t_empty = t_full + kUPipes;          // [pipes]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + kUPipes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tg = blockIdx.y;                                       // trace group
+    // CTAs are shared out in proportion to the traces a group holds (the last group may hold fewer)
+    const int ncta = (tg == (int)gridDim.y - 1) ? a.ctas_last : a.ctas_full;
+    if ((int)blockIdx.x >= ncta) return;
     const int k0 = tg * a.traces_per_cta, k1 = min(a.K, k0 + a.traces_per_cta);
     const int ntiles = (k1 - k0) * a.tiles_per_trace;                // resident tiles of this CTA
     const int nchunks = (k1 - k0) * a.chunks_per_trace;              // accumulator uses per sample group
+    constexpr int kProd = 4 * kUPipes, kMma = 4 * kUPipes + 1;       // warp indices of the two single-lane roles
 
     if (threadIdx.x == 0) {
         mbar_init(b_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+        for (int s = 0; s < kUPipes; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
         fence_mbar_init();
         fence_proxy_async();
     }
-    if (warp == 9) tmem_alloc(tmem_slot, 512);
+    if (warp == kMma) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == kProd) {
         // ------------------------------------------------ TMA producer: resident B'' tiles once, then the A'' tile of every group
         if (lane == 0) {
             mbar_expect_tx(b_full, (uint32_t)ntiles * kUN * kUK * 4);
@@ -195,24 +203,25 @@ __global__ void __launch_bounds__(320, 1) mc_umma_kernel(const __grid_constant__
                 tma_load_2d(b_smem + (size_t)j * kUN * kUK, &tm_b, 0, (k * a.tiles_per_trace + tt) * kUN, b_full);
             }
             int i = 0;
-            for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x, ++i) {
-                const int p = i & 1, use = i >> 1;                     // pipeline, and how often its A'' stage has been used
+            for (int g = blockIdx.x; g < a.n_groups; g += ncta, ++i) {
+                const int p = i % kUPipes, use = i / kUPipes;          // pipeline, and how often its A'' stage has been used
                 if (use >= 1) mbar_wait(&a_empty[p], (use - 1) & 1);
                 mbar_expect_tx(&a_full[p], kUM * kUK * 4);
                 tma_load_2d(a_smem + (size_t)p * kUM * kUK, &tm_a, 0, g * kUM, &a_full[p]);
             }
         }
-    } else if (warp == 9) {
-        // ------------------------------------------------ MMA issuer (one elected lane), alternating between the two pipelines
+    } else if (warp == kMma) {
+        // ------------------------------------------------ MMA issuer (one elected lane), round robin over the pipelines
         if (lane == 0) {
             mbar_wait(b_full, 0);
-            int grp[2] = {blockIdx.x, blockIdx.x + (int)gridDim.x};      // the group each pipeline works on
-            int use_a[2] = {0, 0}, use_t[2] = {0, 0}, chunk[2] = {0, 0};
+            int grp[kUPipes], use_a[kUPipes], use_t[kUPipes], chunk[kUPipes];
+#pragma unroll
+            for (int p = 0; p < kUPipes; ++p) { grp[p] = blockIdx.x + p * ncta; use_a[p] = 0; use_t[p] = 0; chunk[p] = 0; }
             bool busy = true;
             while (busy) {
                 busy = false;
 #pragma unroll
-                for (int p = 0; p < 2; ++p) {
+                for (int p = 0; p < kUPipes; ++p) {
                     if (grp[p] >= a.n_groups) continue;
                     busy = true;
                     if (chunk[p] == 0) { mbar_wait(&a_full[p], use_a[p] & 1); tc_fence_after(); }
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(320, 1) mc_umma_kernel(const __grid_constant__
                     if (++chunk[p] == nchunks) {
                         umma_commit(&a_empty[p]);                   // all MMAs reading this A'' tile have completed
                         chunk[p] = 0; ++use_a[p];
-                        grp[p] += 2 * gridDim.x;
+                        grp[p] += kUPipes * ncta;
                     }
                 }
             }
@@ -243,7 +252,7 @@ __global__ void __launch_bounds__(320, 1) mc_umma_kernel(const __grid_constant__
         const bool vr_like = a.metric == FWI_METRIC_VR || a.metric == FWI_METRIC_GAU;
         const double Tn = (double)a.T;
         int use_t = 0;
-        for (int g = blockIdx.x + p * gridDim.x; g < a.n_groups; g += 2 * gridDim.x) {
+        for (int g = blockIdx.x + p * ncta; g < a.n_groups; g += kUPipes * ncta) {
             const int64_t n = (int64_t)g * kUM + wq * 32 + lane;
             const bool live = n < a.N;
             double coef[9];
@@ -261,6 +270,8 @@ __global__ void __launch_bounds__(320, 1) mc_umma_kernel(const __grid_constant__
                     // columns the MMA of this chunk wrote (those past T hold 0: B'' is zero-padded); a multiple of 16
                     const int ncol = (ci == a.chunks_per_trace - 1) ? a.n_last : kUNacc;
                     if (!(a.debug & 2)) {
+                        // 32 columns at a time.  (Keeping the next tcgen05.ld in flight while the current values are folded was
+                        // measured slower: 5.99 vs 5.70 ms for N = 4e6, and so were four loads in flight per accumulator.)
                         for (int c0 = 0; c0 < ncol; c0 += 32) {
                             float v[32];
                             tmem_ld32(taddr + c0, v);
@@ -329,7 +340,7 @@ __global__ void __launch_bounds__(320, 1) mc_umma_kernel(const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, 512);
+    if (warp == kMma) tmem_dealloc(tmem_base, 512);
 }
 
 // A''[n][32] from the sampler's (rows, N) layout; `with_d`: the two -1 columns that subtract d (MODE_SSE)
@@ -424,7 +435,7 @@ struct UmmaPath {
     CUtensorMap tm_raw, tm_cen;
 };
 
-constexpr int kUSmem = kUTilesMax * kUN * kUK * 4 + 2 * kUM * kUK * 4 + 256;
+constexpr int kUSmem = kUTilesMax * kUN * kUK * 4 + kUPipes * kUM * kUK * 4 + 256;
 
 int umma_build(UmmaPath** out, int device, const double* G, const double* d, int K, int C, int T, const TraceConst* tc_dev,
                const FlatConst& fc) {
@@ -531,9 +542,13 @@ int umma_eval(UmmaPath* u, const float* M_dev, int64_t ldm, int64_t N, int metri
     if (rc) return rc;
     mc_umma_pack_kernel<<<(unsigned)((Npad + 127) / 128), 128, 0, st>>>(M_dev, ldm, u->C, N, Npad, mode == MODE_SSE ? 1 : 0, u->A);
     FWI_CUDA(cudaGetLastError());
-    const int per_group = (int)std::min<int64_t>(ngroups, std::max(1, u->sms / u->n_tgroups));
+    // CTAs per trace group in proportion to its traces (K = 21, two resident traces: 10 groups x 14 CTAs + 1 group x 7 = 147)
+    const int last_traces = u->K - (u->n_tgroups - 1) * u->traces_per_cta;
+    const int ctas_full = (int)std::min<int64_t>(ngroups, std::max(1, u->sms * u->traces_per_cta / u->K));
+    const int ctas_last = (int)std::min<int64_t>(ngroups, std::max(1, u->sms * last_traces / u->K));
     UmmaEvalArgs a{};
     a.N = N; a.n_groups = (int)ngroups; a.tiles_per_trace = u->tiles_per_trace; a.traces_per_cta = u->traces_per_cta;
+    a.ctas_full = ctas_full; a.ctas_last = ctas_last;
     a.K = u->K; a.C = u->C; a.T = u->T; a.metric = metric; a.flags = flags;
     { const char* e = getenv("FWI_UMMA_DEBUG"); a.debug = e ? atoi(e) : 0; }
     a.chunks_per_trace = (u->T + kUNacc - 1) / kUNacc;
@@ -541,10 +556,10 @@ int umma_eval(UmmaPath* u, const float* M_dev, int64_t ldm, int64_t N, int metri
     auto idesc = [](int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kUM >> 4) << 24); };
     a.idesc_full = idesc(kUNacc); a.idesc_last = idesc(a.n_last);
     a.tc = u->tc; a.gbar = u->gbar; a.gdc = u->gdc; a.M = M_dev; a.ldm = ldm; a.part = u->part;
-    const dim3 grid(per_group, u->n_tgroups);
-    if (mode == MODE_SSE) mc_umma_kernel<MODE_SSE><<<grid, 320, kUSmem, st>>>(tm_a, u->tm_raw, a);
-    else if (mode == MODE_MOM) mc_umma_kernel<MODE_MOM><<<grid, 320, kUSmem, st>>>(tm_a, u->tm_cen, a);
-    else mc_umma_kernel<MODE_MOM_MAX><<<grid, 320, kUSmem, st>>>(tm_a, u->tm_cen, a);
+    const dim3 grid(std::max(ctas_full, ctas_last), u->n_tgroups);
+    if (mode == MODE_SSE) mc_umma_kernel<MODE_SSE><<<grid, kUThreads, kUSmem, st>>>(tm_a, u->tm_raw, a);
+    else if (mode == MODE_MOM) mc_umma_kernel<MODE_MOM><<<grid, kUThreads, kUSmem, st>>>(tm_a, u->tm_cen, a);
+    else mc_umma_kernel<MODE_MOM_MAX><<<grid, kUThreads, kUSmem, st>>>(tm_a, u->tm_cen, a);
     FWI_CUDA(cudaGetLastError());
     mc_umma_finish_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(u->part, u->n_tgroups, N, u->K, metric, flags, u->fc, sim_dev, like_dev);
     FWI_CUDA(cudaGetLastError());

@@ -34,7 +34,7 @@ def check(K, C, T, N, seed=0):
     return worst
 
 ok = True
-for cfg in ((21, 9, 512, 1000), (5, 6, 128, 300), (4, 3, 320, 77), (21, 9, 1024, 260), (7, 9, 72, 129)):
+for cfg in ((21, 9, 512, 1000), (5, 6, 128, 300), (4, 3, 320, 77), (21, 9, 1024, 260), (7, 9, 72, 129), (3, 9, 1536, 40)):
     ok &= check(*cfg) <= 1e-6
 print("UMMA_CHECK_OK" if ok else "UMMA_CHECK_FAILED", flush=True)
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
