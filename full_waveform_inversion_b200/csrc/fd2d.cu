@@ -387,23 +387,30 @@ static int make_tmaps3(fwi_fd2d* p) {
     // take the cheaper of 16 and 14 (512-wide planes: 4 x 37 = 148 tiles of 14 rows, one per SM).  FWI_FD3D_BY overrides.
     {
         const int nzo = (p->z_own1 > 0 ? p->z_own1 : p->nz) - p->z_own0;
-        // peer-memory slabs: with a lower neighbour the last chunk marches downwards, so that both boundaries are pushed
-        // early - that needs at least two chunks; and a 4-plane boundary must not straddle two chunks
-        const int min_ch = (p->peer_arena[1] && nzo >= 4 * kHalo) ? 2 : 1;
-        int force_by = 0;
+        // peer-memory slabs: with a lower neighbour and two or more chunks the last chunk marches downwards, so that both
+        // boundaries are pushed early; a 4-plane boundary must not straddle two chunks
+        // (measured on 8 GPUs, 64 planes per rank, us per launch: one chunk 93.0 / 95.7 with 14- / 16-row tiles, two chunks
+        // 97.9 / 100.1 - a single chunk re-reads 8 instead of 16 halo planes, which outweighs pushing the lower boundary
+        // at the end of the launch; the model charges that late push 3 %).  Thicker slabs (2 and 4 GPUs at 512 planes) were
+        // only measured with two or more chunks and keep them.
+        int min_ch = (p->peer_arena[1] && nzo > 64) ? 2 : 1;
+        int force_by = 0, force_ch = 0;
         if (const char* e = getenv("FWI_FD3D_BY")) force_by = atoi(e);
+        if (const char* e = getenv("FWI_FD3D_NZCH")) force_ch = atoi(e);       // tuning aid: fixed chunk count (1 = the lower boundary is pushed last)
+        if (force_ch >= 1) min_ch = std::min(force_ch, std::max(1, nzo / 8));
         int best_by = 16, best = 1;
         double best_cost = 1e300;
         for (int by : {16, 14}) {
             if (force_by ? by != force_by : (by != 16 && !p->peers())) continue;
             const int txy = p->tiles_x * ((p->ny + by - 1) / by);
-            for (int nzch = min_ch; nzch <= std::max(min_ch, nzo / 8); ++nzch) {
+            for (int nzch = min_ch; nzch <= (force_ch >= 1 ? min_ch : std::max(min_ch, nzo / 8)); ++nzch) {
                 const int zc = (nzo + nzch - 1) / nzch;
                 const int real = (nzo + zc - 1) / zc;
                 if (real < min_ch) continue;
                 if (p->peers() && nzo - (real - 1) * zc < kHalo) continue;
                 const double waves = std::ceil((double)txy * real / p->sm_count);
-                const double cost = waves * (zc + 2 * kHalo) * by;
+                const double late_push = (p->peer_arena[1] && real == 1) ? 1.03 : 1.0;
+                const double cost = waves * (zc + 2 * kHalo) * by * late_push;
                 if (cost < best_cost - 1e-9) { best_cost = cost; best = nzch; best_by = by; }
             }
         }

@@ -1182,6 +1182,16 @@ int fwi_mc_eval(fwi_mc_ctx* c, const float* M, int64_t ldm, const float* frac, i
         const int tv = simul ? c->K * c->T : c->T;
         FWI_REQUIRE(tv >= 60, "fwi_mc_eval: 'gau' needs at least 60 samples for its noise window (FWI:580), got %d", tv);
     }
+    // Tensor-core path (tcgen05, 3 x TF32 split, TMEM epilogue; mc_umma.cu): every metric and mode, one medium.  Default for
+    // batches of 256 samples and more; FWI_FLAG_TENSOR requires it, FWI_FLAG_NO_TENSOR / FWI_MC_TENSOR=0 keep the CUDA-core kernels.
+    {
+        const char* e = getenv("FWI_MC_TENSOR");
+        const bool env_off = e && e[0] == '0';
+        const bool can = c->umma && c->NM == 1 && nfrac == 0 && umma_supports(c->umma, metric, flags);
+        FWI_REQUIRE(!(flags & FWI_FLAG_TENSOR) || can, "fwi_mc_eval: FWI_FLAG_TENSOR but the tensor-core path does not cover this case (two media, Gram mode, T > 1536 or C > 9)");
+        if (can && !(flags & FWI_FLAG_NO_TENSOR) && ((flags & FWI_FLAG_TENSOR) || (!env_off && N >= 256)))
+            return umma_eval(c->umma, M, ldm, N, metric, flags, sim, like, (cudaStream_t)stream);
+    }
     RowSet* rs = &c->base;
     int boundary_fix = 0;
     if (metric == FWI_METRIC_CC_SHIFT) {
@@ -1203,17 +1213,6 @@ int fwi_mc_eval(fwi_mc_ctx* c, const float* M, int64_t ldm, const float* frac, i
     p.phase = c->phase_dev; p.M = M; p.ldm = ldm; p.frac = frac; p.nfrac = nfrac; p.N = N; p.K = c->K; p.Tv = rs->Tv;
     p.metric = metric; p.flags = flags; p.boundary_fix = boundary_fix; p.sim = sim; p.like = like;
 
-    // Tensor-core path (tcgen05, 3 x TF32 split, TMEM epilogue; mc_umma.cu): every metric except the 4x-interpolated
-    // CC-shift, one medium.  Default for batches of 256 samples and more; FWI_FLAG_TENSOR requires it, FWI_FLAG_NO_TENSOR /
-    // FWI_MC_TENSOR=0 keep the CUDA-core kernels.
-    {
-        const char* e = getenv("FWI_MC_TENSOR");
-        const bool env_off = e && e[0] == '0';
-        const bool can = c->umma && c->NM == 1 && nfrac == 0 && umma_supports(c->umma, metric, flags);
-        FWI_REQUIRE(!(flags & FWI_FLAG_TENSOR) || can, "fwi_mc_eval: FWI_FLAG_TENSOR but the tensor-core path does not cover this case (CC-shift, two media, Gram mode, T > 1536 or C > 9)");
-        if (can && !(flags & FWI_FLAG_NO_TENSOR) && ((flags & FWI_FLAG_TENSOR) || (!env_off && N >= 256)))
-            return umma_eval(c->umma, M, ldm, N, metric, flags, sim, like, (cudaStream_t)stream);
-    }
     if (flags & FWI_FLAG_GRAM) {
         FWI_REQUIRE(!norm, "fwi_mc_eval: the Gram mode cannot normalise traces (it never forms them); drop FWI_FLAG_GRAM or FWI_FLAG_NORMALISED");
         FWI_REQUIRE(c->NM == 1 && rs->gram, "fwi_mc_eval: the Gram mode supports single-medium Green's functions only");

@@ -15,6 +15,16 @@
 //                 A'' are 0, so the accumulator is the centred synthetic s' and the fold is sum_t s'^2; the cross moment
 //                 sum_t d' s' = M . (G' d') and the mean M . gbar are 9-term dot products with float64 constants;
 //   MODE_MOM_MAX  (normalised modes, FWI:597-599): additionally max / min of s' (max |s| = max(|max + mu|, |min + mu|)).
+//   CC-shift     (FWI:548-566): every shift rolls data and synthetic together, so the metric is PCC on the 4x linearly
+//                 interpolated traces (np.interp, right edge clamped).  The interpolated synthetic is LINEAR in the
+//                 accumulator's s'[t], so nothing is interpolated on the device: with S2 = sum_t s'[t]^2 and the lag-one
+//                 product P = sum_t s'[t] s'[t+1] (adjacent TMEM columns, i.e. adjacent registers of the epilogue thread)
+//                     sum_i s'_i^2 = 2.75 S2 + 1.25 P + 2.125 s'[T-1]^2 - 0.875 s'[0]^2
+//                 and every first-order term (mean and cross moment of the interpolated rows, s'[0], s'[T-1]) is a 9-term
+//                 dot product with float64 constants built at upload.  The flattened modes interpolate ACROSS trace
+//                 boundaries (FWI:612): the three points after each internal boundary are patched from the neighbouring
+//                 traces' last / first (normalised) values - inside a CTA from a carried value, across trace groups in
+//                 the finishing kernel.
 // The per-trace combination (float64, same expressions as mc_eval_kernel) runs in the same thread.
 //
 // Work split.  B'' of a few traces (6 tiles of 256 x 32 fp32 = 192 KB) stays RESIDENT in shared memory; a CTA walks over
@@ -100,13 +110,19 @@ __device__ __forceinline__ void tmem_ld_wait_dep(float* v) {
 
 // float64 reciprocal / reciprocal square root from the fp32 SFU seed + two Newton steps (FMA only): the fp64 divide and
 // sqrt sequences were the largest part of the per-trace combination
+// (seeds: MUFU.RCP64H / MUFU.RSQ64H work on the double's own exponent, so products of small amplitudes such as
+// s2 * ssd ~ 1e-44 that leave the fp32 range are handled; three Newton steps whatever the seed's accuracy)
 __device__ __forceinline__ double rcp64(double x) {
-    double r = (double)__frcp_rn((float)x);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
     r = fma(r, fma(-x, r, 1.0), r);
     return fma(r, fma(-x, r, 1.0), r);
 }
 __device__ __forceinline__ double rsqrt64(double x) {
-    double y = (double)rsqrtf((float)x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = y * fma(-0.5 * x, y * y, 1.5);
     y = y * fma(-0.5 * x, y * y, 1.5);
     return y * fma(-0.5 * x, y * y, 1.5);
 }
@@ -146,9 +162,11 @@ struct UmmaEvalArgs {
     const TraceConst* tc;       // [K]
     const double* gbar;         // [K][C] mean_t G
     const double* gdc;          // [K][C] sum_t (d - mean d) G
+    const double* shc;          // CC-shift: [K][4][C] = mean_i G_i - mean_t G | sum_i (d_i - mean d_i) G_i | G'[.,0] | G'[.,T-1]   (_i: 4x interpolated)
     const float* M;             // the samples, (rows, N)
     int64_t ldm;
-    double* part;               // [n_trace_groups][3][N] partial sums of the per-trace combination
+    double* part;               // [n_trace_groups][npart][N] partial sums of the per-trace combination
+    int npart;                  // 3 sums (+ the group's first and last normalised synthetic value for the flattened CC-shift patch: 5)
 };
 
 // grid = (ctas_per_trace_group, n_trace_groups); block = (4 * pipelines + 2) warps.
@@ -158,7 +176,7 @@ struct UmmaEvalArgs {
 // combination) does not overlap with its own pipeline's MMAs, so two independent pipelines on the same resident B'' tiles
 // is what keeps the tensor core and the epilogue warps busy at the same time.
 constexpr int kUThreads = (4 * kUPipes + 2) * 32;        // 4 epilogue warps per pipeline + TMA producer + MMA issuer
-template <int MODE>
+template <int MODE, bool SH>
 __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                                                                UmmaEvalArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -261,8 +279,10 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
                 for (int c = 0; c < 9; ++c) coef[c] = (live && c < a.C) ? (double)a.M[(size_t)c * a.ldm + n] : 0.0;
             }
             double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+            double grp_first = 0.0, carry_s = 0.0, carry_d = 0.0;     // flattened CC-shift: boundary values (see the header)
             for (int k = k0; k < k1; ++k) {
                 float s0 = 0.f, s1 = 0.f, s2a = 0.f, s3 = 0.f, vmax = -3.0e38f, vmin = 3.0e38f;
+                float p0 = 0.f, p1 = 0.f, prev = 0.f;                 // CC-shift: lag-one products, last column of the previous piece
                 for (int ci = 0; ci < a.chunks_per_trace; ++ci, ++use_t) {
                     mbar_wait(&t_full[p], use_t & 1);
                     tc_fence_after();
@@ -286,8 +306,14 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
                                         vmax = fmax3(vmax, v[i], v[i + 1]); vmin = fmin3(vmin, v[i], v[i + 1]);
                                         vmax = fmax3(vmax, v[i + 2], v[i + 3]); vmin = fmin3(vmin, v[i + 2], v[i + 3]);
                                     }
+                                    if (SH) {
+                                        // s'[t] s'[t+1]: columns past T hold 0, so the products past the trace's end vanish
+                                        p0 = fmaf(i == 0 ? prev : v[i - 1], v[i], p0); p1 = fmaf(v[i], v[i + 1], p1);
+                                        p0 = fmaf(v[i + 1], v[i + 2], p0); p1 = fmaf(v[i + 2], v[i + 3], p1);
+                                    }
                                 }
                             }
+                            if (SH) prev = v[31];                       // (a 16-column piece is a trace's last: prev is reset)
                         }
                     }
                     tc_fence_before();
@@ -302,6 +328,42 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
                     q1 += sse; q2 += dd;
                     if (a.metric == FWI_METRIC_VR) q0 += fmax(0.0, fma(-sse, rcp64(dd), 1.0));     // FWI:515-519
                     else q0 += exp(-sse / (2.0 * tc.sigma * tc.sigma));                         // FWI:581
+                } else if (SH) {
+                    // ---- CC-shift: moments of the 4x interpolated trace from S2, P and five dot products
+                    const double* sc = a.shc + (size_t)k * 4 * a.C;
+                    double mud = 0.0, dlt = 0.0, sd = 0.0, f = 0.0, l = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {
+                        if (c < a.C) {
+                            mud = fma(coef[c], a.gbar[k * a.C + c], mud); dlt = fma(coef[c], sc[c], dlt);
+                            sd = fma(coef[c], sc[a.C + c], sd);
+                            f = fma(coef[c], sc[2 * a.C + c], f); l = fma(coef[c], sc[3 * a.C + c], l);
+                        }
+                    }
+                    const double Tv = 4.0 * Tn, P = (double)(p0 + p1);
+                    const double ssq = fma(2.75, s2, fma(1.25, P, fma(2.125 * l, l, -0.875 * f * f))) - Tv * dlt * dlt;   // sum_i (s_i - mean_i s)^2
+                    const double mui = mud + dlt;                                               // mean of the interpolated synthetic
+                    if (!simul) {
+                        const double pcc = sd * rsqrt64(ssq * tc.ssd);                          // FWI:572-573 on the interpolated rows
+                        q0 += (pcc < 0.0) ? 0.0 : pcc;
+                    } else {
+                        double aa = 1.0, bb = 1.0;
+                        if (MODE == MODE_MOM_MAX) {
+                            aa = rcp64(fmax(fabs((double)vmax + mud), fabs((double)vmin + mud)));
+                            bb = rcp64(tc.maxd);
+                        }
+                        double A1 = aa * Tv * mui, A2 = aa * aa * (ssq + Tv * mui * mui), A3 = aa * bb * (sd + Tv * tc.mean_d * mui);
+                        const double first = (f + mud) * aa;
+                        if (k > k0) {                                                           // np.interp across the boundary (FWI:612, 554-555)
+                            const double dl = first - carry_s, dd = tc.d_first * bb - carry_d;
+                            A1 += 1.5 * dl;
+                            A2 += 3.0 * carry_s * dl + 0.875 * dl * dl;
+                            A3 += 1.5 * (carry_d * dl + carry_s * dd) + 0.875 * dd * dl;
+                        } else grp_first = first;
+                        carry_s = (l + mud) * aa;
+                        carry_d = tc.d_last * bb;
+                        q0 += A1; q1 += A2; q2 += A3;
+                    }
                 } else {
                     double mud = 0.0, sd = 0.0;
 #pragma unroll
@@ -333,8 +395,9 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
                 }
             }
             if (live) {
-                double* o = a.part + (size_t)tg * 3 * a.N + n;
+                double* o = a.part + (size_t)tg * a.npart * a.N + n;
                 o[0] = q0; o[a.N] = q1; o[2 * a.N] = q2;
+                if (SH && a.npart == 5) { o[3 * a.N] = grp_first; o[4 * a.N] = carry_s; }
             }
         }
     }
@@ -367,16 +430,26 @@ __global__ void mc_umma_pack_kernel(const float* __restrict__ M, int64_t ldm, in
 }
 
 // adds the trace groups' partial sums and applies the final expressions of mc_eval_kernel (FWI:601-632, 682, 774)
-__global__ void mc_umma_finish_kernel(const double* __restrict__ part, int ngroups, int64_t N, int K, int metric, int flags, FlatConst fc,
-                                      float* __restrict__ sim, float* __restrict__ like) {
+// `tc` / `traces_per_cta`: flattened CC-shift only - the boundary patch between the last trace of a group and the first of the next
+__global__ void mc_umma_finish_kernel(const double* __restrict__ part, int npart, int ngroups, int64_t N, int K, int metric, int flags, FlatConst fc,
+                                      const TraceConst* __restrict__ tc, int traces_per_cta, float* __restrict__ sim, float* __restrict__ like) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
+    const bool norm = flags & FWI_FLAG_NORMALISED, simul = flags & FWI_FLAG_SIMULTANEOUS;
     double q0 = 0.0, q1 = 0.0, q2 = 0.0;
     for (int g = 0; g < ngroups; ++g) {
-        const double* o = part + (size_t)g * 3 * N + n;
+        const double* o = part + (size_t)g * npart * N + n;
         q0 += o[0]; q1 += o[N]; q2 += o[2 * N];
+        if (npart == 5 && g > 0) {
+            const int kb = g * traces_per_cta;                                   // first trace of this group
+            const double bl = norm ? 1.0 / tc[kb - 1].maxd : 1.0, bf = norm ? 1.0 / tc[kb].maxd : 1.0;
+            const double cs = (o - (size_t)npart * N)[4 * N], cd = tc[kb - 1].d_last * bl;   // the previous group's last values
+            const double dl = o[3 * N] - cs, dd = tc[kb].d_first * bf - cd;
+            q0 += 1.5 * dl;
+            q1 += 3.0 * cs * dl + 0.875 * dl * dl;
+            q2 += 1.5 * (cd * dl + cs * dd) + 0.875 * dd * dl;
+        }
     }
-    const bool norm = flags & FWI_FLAG_NORMALISED, simul = flags & FWI_FLAG_SIMULTANEOUS;
     const bool vr_like = metric == FWI_METRIC_VR || metric == FWI_METRIC_GAU;
     double result;
     if (vr_like) {
@@ -430,6 +503,10 @@ struct UmmaPath {
     double* gdc = nullptr;       // [K][C]
     const TraceConst* tc = nullptr;   // owned by the Monte-Carlo context
     FlatConst fc{};
+    // CC-shift: constants of the 4x interpolated rows (per trace clamped; the flattened array runs across the boundaries)
+    double* shc = nullptr;            // [K][4][C], see UmmaEvalArgs
+    TraceConst* tc_hr = nullptr;      // [K]
+    FlatConst fc_hr{};
     float* A = nullptr; size_t A_rows = 0;
     double* part = nullptr; size_t part_cap = 0;
     CUtensorMap tm_raw, tm_cen;
@@ -476,12 +553,62 @@ int umma_build(UmmaPath** out, int device, const double* G, const double* d, int
             rr[3 * C] = dhi; rr[3 * C + 1] = dlo;
         }
     }
+    // CC-shift (FWI:548-566): float64 constants of the 4x linearly interpolated rows.  x_i[4t + j] = x[t] + (x[t+1] - x[t]) j/4,
+    // the right edge clamps (np.interp); the flattened array (FWI:612) runs into the next trace's first sample instead.
+    const int Tv = 4 * T;
+    std::vector<double> shc((size_t)K * 4 * C);
+    std::vector<TraceConst> tch(K);
+    {
+        std::vector<double> di(Tv), gi(Tv);
+        auto interp_clamped = [&](const double* x, std::vector<double>& out) {
+            for (int t = 0; t < T; ++t)
+                for (int j = 0; j < 4; ++j) out[4 * t + j] = (t + 1 < T) ? x[t] + (x[t + 1] - x[t]) * (0.25 * j) : x[t];
+        };
+        for (int k = 0; k < K; ++k) {
+            const double* dk = d + (size_t)k * T;
+            interp_clamped(dk, di);
+            TraceConst& q = tch[k];
+            double sum = 0.0, sum2 = 0.0, ssd = 0.0, mx = 0.0;
+            for (int i = 0; i < Tv; ++i) { sum += di[i]; sum2 += di[i] * di[i]; }
+            q.mean_d = sum / Tv; q.sumd2 = sum2;
+            for (int i = 0; i < Tv; ++i) ssd += (di[i] - q.mean_d) * (di[i] - q.mean_d);
+            for (int t = 0; t < T; ++t) mx = std::max(mx, std::fabs(dk[t]));
+            q.ssd = ssd; q.maxd = mx; q.sigma = NAN; q.d_first = dk[0]; q.d_last = dk[T - 1];
+            for (int c = 0; c < C; ++c) {
+                const double* gk = G + ((size_t)k * C + c) * T;
+                interp_clamped(gk, gi);
+                double gs = 0.0, gd = 0.0;
+                for (int i = 0; i < Tv; ++i) { gs += gi[i]; gd += (di[i] - q.mean_d) * gi[i]; }
+                double* sc = &shc[(size_t)k * 4 * C];
+                sc[c] = gs / Tv - gbar[(size_t)k * C + c];
+                sc[C + c] = gd;
+                sc[2 * C + c] = gk[0] - gbar[(size_t)k * C + c];
+                sc[3 * C + c] = gk[T - 1] - gbar[(size_t)k * C + c];
+            }
+        }
+        u->fc_hr = FlatConst{};
+        u->fc_hr.n = (double)K * Tv;
+        const size_t nf = (size_t)K * T;
+        for (int norm = 0; norm < 2; ++norm) {
+            auto at = [&](size_t i) { return d[i] / (norm ? tch[i / T].maxd : 1.0); };     // normalised BEFORE the interpolation (FWI:598, 612)
+            double s1 = 0.0, s2 = 0.0;
+            for (size_t i = 0; i < nf; ++i)
+                for (int j = 0; j < 4; ++j) {
+                    const double x = (i + 1 < nf) ? at(i) + (at(i + 1) - at(i)) * (0.25 * j) : at(i);
+                    s1 += x; s2 += x * x;
+                }
+            u->fc_hr.D1[norm] = s1; u->fc_hr.D2[norm] = s2; u->fc_hr.sigma[norm] = NAN;
+        }
+    }
     DeviceGuard g(device);
     auto fail = [&](int rc) { umma_free(u); return rc; };
     if (cudaMalloc(&u->B_raw, Br.size() * sizeof(float)) != cudaSuccess || cudaMalloc(&u->B_cen, Bc.size() * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&u->gbar, gbar.size() * sizeof(double)) != cudaSuccess || cudaMalloc(&u->gdc, gdc.size() * sizeof(double)) != cudaSuccess) {
+        cudaMalloc(&u->gbar, gbar.size() * sizeof(double)) != cudaSuccess || cudaMalloc(&u->gdc, gdc.size() * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&u->shc, shc.size() * sizeof(double)) != cudaSuccess || cudaMalloc(&u->tc_hr, tch.size() * sizeof(TraceConst)) != cudaSuccess) {
         cudaGetLastError(); set_error("umma_build: out of device memory"); return fail(FWI_ENOMEM);
     }
+    cudaMemcpy(u->shc, shc.data(), shc.size() * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(u->tc_hr, tch.data(), tch.size() * sizeof(TraceConst), cudaMemcpyHostToDevice);
     cudaMemcpy(u->B_raw, Br.data(), Br.size() * sizeof(float), cudaMemcpyHostToDevice);
     cudaMemcpy(u->B_cen, Bc.data(), Bc.size() * sizeof(float), cudaMemcpyHostToDevice);
     cudaMemcpy(u->gbar, gbar.data(), gbar.size() * sizeof(double), cudaMemcpyHostToDevice);
@@ -489,9 +616,11 @@ int umma_build(UmmaPath** out, int device, const double* G, const double* d, int
     int rc = encode_rows32_sw128(&u->tm_raw, u->B_raw, rows, kUN);
     if (!rc) rc = encode_rows32_sw128(&u->tm_cen, u->B_cen, rows, kUN);
     if (rc) return fail(rc);
-    if (cudaFuncSetAttribute(mc_umma_kernel<MODE_SSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(mc_umma_kernel<MODE_MOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(mc_umma_kernel<MODE_MOM_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(mc_umma_kernel<MODE_SSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(mc_umma_kernel<MODE_MOM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(mc_umma_kernel<MODE_MOM_MAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(mc_umma_kernel<MODE_MOM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(mc_umma_kernel<MODE_MOM_MAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmem) != cudaSuccess) {
         cudaGetLastError(); return fail(FWI_OK);          // no tensor-core path on this device: CUDA-core kernels only
     }
     *out = u;
@@ -505,6 +634,8 @@ void umma_free(UmmaPath* u) {
     if (u->B_cen) cudaFree(u->B_cen);
     if (u->gbar) cudaFree(u->gbar);
     if (u->gdc) cudaFree(u->gdc);
+    if (u->shc) cudaFree(u->shc);
+    if (u->tc_hr) cudaFree(u->tc_hr);
     if (u->A) cudaFree(u->A);
     if (u->part) cudaFree(u->part);
     delete u;
@@ -512,7 +643,8 @@ void umma_free(UmmaPath* u) {
 
 bool umma_supports(const UmmaPath* u, int metric, int flags) {
     if (!u) return false;
-    if (metric == FWI_METRIC_CC_SHIFT || (flags & FWI_FLAG_GRAM)) return false;      // 4x interpolated rows / the Gram algorithm stay on the CUDA cores
+    if (flags & FWI_FLAG_GRAM) return false;                                         // the Gram algorithm stays on the CUDA cores
+    if (metric == FWI_METRIC_CC_SHIFT && u->T < 2) return false;
     if (metric == FWI_METRIC_GAU && u->T < 60) return false;
     return true;
 }
@@ -524,6 +656,8 @@ int umma_eval(UmmaPath* u, const float* M_dev, int64_t ldm, int64_t N, int metri
     int mode;
     if (metric == FWI_METRIC_VR || metric == FWI_METRIC_GAU) mode = norm ? MODE_MOM_MAX : MODE_SSE;
     else mode = (simul && norm) ? MODE_MOM_MAX : MODE_MOM;
+    const bool shift = metric == FWI_METRIC_CC_SHIFT;
+    const int npart = (shift && simul) ? 5 : 3;
     const int64_t ngroups = (N + kUM - 1) / kUM, Npad = ngroups * kUM;
     if (u->A_rows < (size_t)Npad) {
         if (u->A) cudaFree(u->A);
@@ -531,11 +665,11 @@ int umma_eval(UmmaPath* u, const float* M_dev, int64_t ldm, int64_t N, int metri
         FWI_CUDA(cudaMalloc(&u->A, (size_t)Npad * kUK * sizeof(float)));
         u->A_rows = (size_t)Npad;
     }
-    if (u->part_cap < (size_t)u->n_tgroups * 3 * N) {
+    if (u->part_cap < (size_t)u->n_tgroups * npart * N) {
         if (u->part) cudaFree(u->part);
         u->part = nullptr; u->part_cap = 0;
-        FWI_CUDA(cudaMalloc(&u->part, (size_t)u->n_tgroups * 3 * N * sizeof(double)));
-        u->part_cap = (size_t)u->n_tgroups * 3 * N;
+        FWI_CUDA(cudaMalloc(&u->part, (size_t)u->n_tgroups * npart * N * sizeof(double)));
+        u->part_cap = (size_t)u->n_tgroups * npart * N;
     }
     CUtensorMap tm_a;
     int rc = encode_rows32_sw128(&tm_a, u->A, (uint64_t)Npad, kUM);
@@ -555,13 +689,16 @@ int umma_eval(UmmaPath* u, const float* M_dev, int64_t ldm, int64_t N, int metri
     a.n_last = ((u->T - (a.chunks_per_trace - 1) * kUNacc) + 15) & ~15;                     // MMA N of a trace's last chunk (multiple of 16)
     auto idesc = [](int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kUM >> 4) << 24); };
     a.idesc_full = idesc(kUNacc); a.idesc_last = idesc(a.n_last);
-    a.tc = u->tc; a.gbar = u->gbar; a.gdc = u->gdc; a.M = M_dev; a.ldm = ldm; a.part = u->part;
+    a.tc = shift ? u->tc_hr : u->tc; a.gbar = u->gbar; a.gdc = u->gdc; a.shc = u->shc; a.M = M_dev; a.ldm = ldm; a.part = u->part; a.npart = npart;
     const dim3 grid(std::max(ctas_full, ctas_last), u->n_tgroups);
-    if (mode == MODE_SSE) mc_umma_kernel<MODE_SSE><<<grid, kUThreads, kUSmem, st>>>(tm_a, u->tm_raw, a);
-    else if (mode == MODE_MOM) mc_umma_kernel<MODE_MOM><<<grid, kUThreads, kUSmem, st>>>(tm_a, u->tm_cen, a);
-    else mc_umma_kernel<MODE_MOM_MAX><<<grid, kUThreads, kUSmem, st>>>(tm_a, u->tm_cen, a);
+    if (mode == MODE_SSE) mc_umma_kernel<MODE_SSE, false><<<grid, kUThreads, kUSmem, st>>>(tm_a, u->tm_raw, a);
+    else if (mode == MODE_MOM && !shift) mc_umma_kernel<MODE_MOM, false><<<grid, kUThreads, kUSmem, st>>>(tm_a, u->tm_cen, a);
+    else if (mode == MODE_MOM) mc_umma_kernel<MODE_MOM, true><<<grid, kUThreads, kUSmem, st>>>(tm_a, u->tm_cen, a);
+    else if (!shift) mc_umma_kernel<MODE_MOM_MAX, false><<<grid, kUThreads, kUSmem, st>>>(tm_a, u->tm_cen, a);
+    else mc_umma_kernel<MODE_MOM_MAX, true><<<grid, kUThreads, kUSmem, st>>>(tm_a, u->tm_cen, a);
     FWI_CUDA(cudaGetLastError());
-    mc_umma_finish_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(u->part, u->n_tgroups, N, u->K, metric, flags, u->fc, sim_dev, like_dev);
+    mc_umma_finish_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(u->part, npart, u->n_tgroups, N, u->K, metric, flags, shift ? u->fc_hr : u->fc,
+                                                                        u->tc_hr, u->traces_per_cta, sim_dev, like_dev);
     FWI_CUDA(cudaGetLastError());
     return FWI_OK;
 }

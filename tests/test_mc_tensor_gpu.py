@@ -28,7 +28,7 @@ def _eval(fw, prob, Ms, metric, norm, simul, extra, like=False):
     return (out[0].cpu().numpy(), out[1].cpu().numpy()) if like else out.cpu().numpy()
 
 
-@pytest.mark.parametrize("metric", ["VR", "CC", "PCC", "gau"])
+@pytest.mark.parametrize("metric", ["VR", "CC", "PCC", "CC-shift", "gau"])
 @pytest.mark.parametrize("norm", [False, True])
 @pytest.mark.parametrize("simul", [False, True])
 def test_tensor_path_golden_all_modes(fw, golden_a, metric, norm, simul):
@@ -55,23 +55,25 @@ def test_tensor_path_vs_oracle_shapes(fw, K, C, T, N):
     Ms = Ms / np.linalg.norm(Ms, axis=1, keepdims=True) * amp
     Ms[0] = orc.perform_inversion(d, G)[:, 0]
     prob = fw.SourceInversion(d, G)
-    for metric in ("VR", "PCC", "gau"):
+    for metric in ("VR", "PCC", "CC-shift", "gau"):
         if metric == "gau" and T < 60:
             continue
         for norm in (False, True):
             for simul in (False, True):
-                want = orc.similarity_batch(d, G, Ms[:48], metric, norm, simul)
+                # CC-shift (lag-one products of adjacent accumulator columns, boundary patches inside a CTA and between trace
+                # groups): the oracle interpolates explicitly (np.interp, FWI:554-555)
+                want = orc.similarity_batch(d, G, Ms[:48 if metric != "CC-shift" else 16], metric, norm, simul)
                 got, like = _eval(fw, prob, Ms, metric, norm, simul, TENSOR, like=True)
                 ref = _eval(fw, prob, Ms, metric, norm, simul, NO_TENSOR)
-                assert np.abs(got[:48] - want).max() <= 1e-6, (metric, norm, simul)
+                assert np.abs(got[:len(want)] - want).max() <= 1e-6, (metric, norm, simul)
                 assert np.abs(got - ref).max() <= 1e-6, (metric, norm, simul)
-                np.testing.assert_allclose(like[:48], orc.likelihood(want), rtol=1e-5, atol=1e-7)
+                np.testing.assert_allclose(like[:len(want)], orc.likelihood(want), rtol=1e-5, atol=1e-7)
     prob.close()
 
 
 def test_tensor_path_is_the_default_for_batches_and_can_be_refused(fw):
-    """N >= 256 takes the tensor cores by default; CC-shift, two media and the Gram mode never do; FWI_FLAG_TENSOR on an
-    uncovered case is an error, not a silent fallback."""
+    """N >= 256 takes the tensor cores by default (CC-shift included); two media and the Gram mode never do; FWI_FLAG_TENSOR
+    on an uncovered case is an error, not a silent fallback."""
     import torch
     d, G, _ = orc.synthetic_inputs(K=6, C=9, T=128, seed=3)
     Ms = np.random.default_rng(2).standard_normal((600, 9))
@@ -80,9 +82,13 @@ def test_tensor_path_is_the_default_for_batches_and_can_be_refused(fw):
     b = _eval(fw, prob, Ms, "VR", False, False, TENSOR)
     c = _eval(fw, prob, Ms, "VR", False, False, NO_TENSOR)
     assert np.array_equal(a, b) and not np.array_equal(a, c) and np.abs(a - c).max() <= 1e-6
+    for simul in (False, True):
+        a = _eval(fw, prob, Ms, "CC-shift", True, simul, 0)
+        b = _eval(fw, prob, Ms, "CC-shift", True, simul, TENSOR)
+        c = _eval(fw, prob, Ms, "CC-shift", True, simul, NO_TENSOR)
+        assert np.array_equal(a, b) and not np.array_equal(a, c) and np.abs(a - c).max() <= 1e-6
     with pytest.raises(ValueError):
-        _eval(fw, prob, Ms, "CC-shift", False, False, TENSOR)
-    _eval(fw, prob, Ms, "CC-shift", False, False, 0)                     # ... but runs on the CUDA cores without the flag
+        _eval(fw, prob, Ms, "VR", False, False, TENSOR | 8)               # the Gram algorithm is not a tensor-core mode
     prob.close()
     d2, G2, _ = orc.synthetic_inputs(K=6, C=9, T=128, seed=3, n_media=2)
     prob2 = fw.SourceInversion(d2, G2)
@@ -91,3 +97,24 @@ def test_tensor_path_is_the_default_for_batches_and_can_be_refused(fw):
     with pytest.raises(ValueError):
         prob2.eval_dev(M_dev, 0, TENSOR, frac_dev=fr)
     prob2.close()
+
+
+def test_tensor_path_small_amplitudes(fw):
+    """Displacement-scale data (1e-11): products such as sum s'^2 . sum d'^2 ~ 1e-44 leave the fp32 range, which the
+    float64 reciprocal / rsqrt seeds of the per-trace combination must survive (every metric x mode, vs the oracle)."""
+    d, G, _ = orc.synthetic_inputs(K=5, C=9, T=160, seed=11)
+    sc = 1e-11 / np.abs(d).max()
+    d = d * sc
+    G = G * sc
+    amp = float(np.linalg.norm(orc.perform_inversion(d, G)))
+    Ms = np.random.default_rng(5).standard_normal((130, 9))
+    Ms = Ms / np.linalg.norm(Ms, axis=1, keepdims=True) * amp
+    prob = fw.SourceInversion(d, G)
+    for metric in ("VR", "PCC", "CC-shift", "gau"):
+        for norm in (False, True):
+            for simul in (False, True):
+                want = orc.similarity_batch(d, G, Ms[:16], metric, norm, simul)
+                got = _eval(fw, prob, Ms, metric, norm, simul, TENSOR)
+                assert np.all(np.isfinite(got)), (metric, norm, simul)
+                assert np.abs(got[:16] - want).max() <= 1e-6, (metric, norm, simul)
+    prob.close()

@@ -16,7 +16,7 @@ def check(K, C, T, N, seed=0):
     M_dev = torch.tensor(Ms.T.copy(), dtype=torch.float32, device="cuda")
     prob = fw.SourceInversion(d, G)
     worst = 0.0
-    for metric in ("VR", "PCC", "CC", "gau"):
+    for metric in ("VR", "PCC", "CC", "CC-shift", "gau"):
         if metric == "gau" and T < 60:
             continue
         for norm in (False, True):
@@ -34,7 +34,7 @@ def check(K, C, T, N, seed=0):
     return worst
 
 ok = True
-for cfg in ((21, 9, 512, 1000), (5, 6, 128, 300), (4, 3, 320, 77), (21, 9, 1024, 260), (7, 9, 72, 129), (3, 9, 1536, 40)):
+for cfg in ((21, 9, 512, 1000), (5, 6, 128, 300), (4, 3, 320, 77), (21, 9, 1024, 260), (7, 9, 72, 129), (3, 9, 1536, 40), (33, 9, 61, 300)):
     ok &= check(*cfg) <= 1e-6
 print("UMMA_CHECK_OK" if ok else "UMMA_CHECK_FAILED", flush=True)
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
@@ -43,7 +43,8 @@ amp = float(np.linalg.norm(orc.perform_inversion(d, G)))
 prob = fw.SourceInversion(d, G)
 for n in (10_000, N):
     MTs, _, _, _ = prob.sample_eval_dev(6, 1, 0, n, amp, 0, 0, reduce=False)
-    for metric, fl in (("VR", 0), ("VR", 2), ("VR", 1), ("VR", 3), ("PCC", 0), ("PCC", 3), ("gau", 0)):
+    for metric, fl in (("VR", 0), ("VR", 2), ("VR", 1), ("VR", 3), ("PCC", 0), ("PCC", 3), ("gau", 0),
+                       ("CC-shift", 0), ("CC-shift", 2), ("CC-shift", 3)):
         out = []
         for name, extra in (("tensor", TENSOR), ("cuda-core", NO_TENSOR)):
             fn = lambda: prob.eval_dev(MTs, fw.METRICS.index(metric), fl | extra, want_likelihood=True)
