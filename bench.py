@@ -233,7 +233,8 @@ def track_a_numbers(device, dist=None, cpu=True):
                            "cuda_core_fp32": {"samples_per_s": N / dt_c, "ms": dt_c * 1e3, "fp32_tflops_direct": N * flops / dt_c / 1e12}}
     # the other metric families on the tensor cores vs the CUDA cores (N = 4e6, device-resident, sampler included)
     fam = {}
-    for name, metric, fl in (("VR_normalised_flattened", 0, 3), ("PCC_per_trace", 2, 0), ("PCC_normalised_flattened", 2, 3), ("gau_per_trace", 4, 0)):
+    for name, metric, fl in (("VR_normalised_flattened", 0, 3), ("PCC_per_trace", 2, 0), ("PCC_normalised_flattened", 2, 3), ("gau_per_trace", 4, 0),
+                             ("CC_shift_per_trace", 3, 0), ("CC_shift_normalised_flattened", 3, 3)):
         N = 4_000_000
         prob.sample_eval_dev(6, 1, 0, N, amp, metric, fl, reduce=False)
         prob.sample_eval_dev(6, 1, 0, N, amp, metric, fl | NO_TENSOR, reduce=False)

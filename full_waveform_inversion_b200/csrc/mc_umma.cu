@@ -51,8 +51,29 @@ constexpr int kUM = 128;                // samples per MMA tile (TMEM lanes)
 constexpr int kUN = 256;                // time samples per resident B'' tile (one TMA box)
 constexpr int kUPipes = FWI_UMMA_PIPES; // independent pipelines per CTA (sample groups in flight).  2 x 256 columns: 5.7 ms for N = 4e6 (VR);
                                         // 4 x 128: 9.2 ms - the single MMA-issuing lane pays ~0.45 us per accumulator use whatever its size
-constexpr int kUNacc = 512 / kUPipes;   // time samples per accumulator use (MMA N; every pipeline owns 512 / pipes TMEM columns)
-constexpr int kUTilesMax = (227 * 1024 - kUPipes * 16384 - 1024) / (kUN * 128);
+#ifndef FWI_UMMA_EXP
+#define FWI_UMMA_EXP 0                      // timing experiments: 1 = TMEM loads without folds, 2 = folds without TMEM loads
+#endif
+#ifndef FWI_UMMA_TRACE
+#define FWI_UMMA_TRACE 0                    // timing experiment: CTA (0,0) prints the clock at the handshake events of pipeline 0
+#endif
+#ifndef FWI_UMMA_LDPIPE
+#define FWI_UMMA_LDPIPE 1                   // full chunks: next piece's tcgen05.ld in flight while the current piece is folded
+#endif
+#ifndef FWI_UMMA_LDUNROLL
+#define FWI_UMMA_LDUNROLL 4                 // unroll factor of the pipelined piece loop (2 pieces per iteration; 4 = a whole 256-column chunk)
+#endif
+#ifndef FWI_UMMA_ISSUERS
+#define FWI_UMMA_ISSUERS 1                  // MMA-issuing warps: 1 (round robin over the pipelines) or one per pipeline
+#endif
+#ifndef FWI_UMMA_STAGES
+#define FWI_UMMA_STAGES 1
+#endif
+constexpr int kUStages = FWI_UMMA_STAGES;   // accumulator stages per pipeline (its MMAs run ahead of its epilogue by stages - 1 uses)
+constexpr int kUNacc = 512 / (kUPipes * kUStages);   // time samples per accumulator use (MMA N; every stage owns that many TMEM columns)
+constexpr int kUCst = 52;               // float64 constants per resident trace in shared memory: gbar[9] | gdc[9] (CC-shift: the interpolated
+                                        // cross moment) | CC-shift: dgb[9], G'[.,0][9], G'[.,T-1][9] | TraceConst (7) at 45
+constexpr int kUTilesMax = (227 * 1024 - kUPipes * 16384 - 256) / (kUN * 128 + kUCst * 8);     // resident B'' tiles (+ a trace's constants each)
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
     // K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (1), descriptor version 1
     uint64_t d = 0;
@@ -72,6 +93,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// one lane of a converged warp (the tcgen05 instructions take uniform-register operands: with the WHOLE warp running the issuer
+// loop and only the instruction itself under this predicate, the descriptors stay in uniform registers; a loop under
+// `if (lane == 0)` makes the compiler wrap every tcgen05.mma in an elect / R2UR.BROADCAST / branch sequence of ~16 instructions)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
@@ -175,7 +204,14 @@ struct UmmaEvalArgs {
 // handshake of one accumulator costs ~0.3 us per use and the epilogue's serial work (TMEM load latency, per-trace
 // combination) does not overlap with its own pipeline's MMAs, so two independent pipelines on the same resident B'' tiles
 // is what keeps the tensor core and the epilogue warps busy at the same time.
-constexpr int kUThreads = (4 * kUPipes + 2) * 32;        // 4 epilogue warps per pipeline + TMA producer + MMA issuer
+#if FWI_UMMA_TRACE
+constexpr int kTrFirst = 84, kTrN = 48;          // accumulator uses traced (per pipeline): the CTA's 3rd and 4th sample group
+__device__ long long g_trace[2][kUPipes][kTrN][6];
+#endif
+constexpr int kULdUnroll = FWI_UMMA_LDUNROLL;
+constexpr int kUIssuers = FWI_UMMA_ISSUERS;
+static_assert(kUIssuers == 1 || kUIssuers == kUPipes, "one MMA issuer, or one per pipeline");
+constexpr int kUThreads = (4 * kUPipes + 1 + kUIssuers) * 32;        // 4 epilogue warps per pipeline + TMA producer + MMA issuer(s)
 template <int MODE, bool SH>
 __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                                                                UmmaEvalArgs a) {
@@ -186,9 +222,10 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
     uint64_t* b_full = bars;                       // 1
     uint64_t* a_full = bars + 1;                   // [pipes]
     uint64_t* a_empty = a_full + kUPipes;          // [pipes]
-    uint64_t* t_full = a_empty + kUPipes;          // [pipes]
-    uint64_t* t_empty = t_full + kUPipes;          // [pipes]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + kUPipes);
+    uint64_t* t_full = a_empty + kUPipes;          // [pipes][stages]
+    uint64_t* t_empty = t_full + kUPipes * kUStages;   // [pipes][stages]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + kUPipes * kUStages);
+    double* cst = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(bars) + 256);     // [resident traces][kUCst]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tg = blockIdx.y;                                       // trace group
@@ -202,9 +239,23 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
 
     if (threadIdx.x == 0) {
         mbar_init(b_full, 1);
-        for (int s = 0; s < kUPipes; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+        for (int s = 0; s < kUPipes; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < kUPipes * kUStages; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
         fence_mbar_init();
         fence_proxy_async();
+    }
+    // The resident traces' constants go to shared memory once: the per-trace fold reads up to 52 of them per thread, and as
+    // (L1-missing) global loads they cost ~2000 cycles per trace on the epilogue's critical path.
+    for (int i = threadIdx.x; i < (k1 - k0) * kUCst; i += blockDim.x) {
+        const int k = k0 + i / kUCst, j = i % kUCst;
+        double v = 0.0;
+        if (j < 9) { if (j < a.C) v = a.gbar[k * a.C + j]; }
+        else if (j < 18) { if (j - 9 < a.C) v = SH ? a.shc[(size_t)k * 4 * a.C + a.C + (j - 9)] : a.gdc[k * a.C + (j - 9)]; }
+        else if (j < 45) {
+            const int w = (j - 18) / 9, c = (j - 18) % 9;                  // dgb, G'[.,0], G'[.,T-1]
+            if (SH && c < a.C) v = a.shc[(size_t)k * 4 * a.C + (w == 0 ? 0 : w + 1) * a.C + c];
+        } else v = reinterpret_cast<const double*>(a.tc + k)[j - 45];
+        cst[i] = v;
     }
     if (warp == kMma) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -228,13 +279,28 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
                 tma_load_2d(a_smem + (size_t)p * kUM * kUK, &tm_a, 0, g * kUM, &a_full[p]);
             }
         }
-    } else if (warp == kMma) {
-        // ------------------------------------------------ MMA issuer (one elected lane), round robin over the pipelines
-        if (lane == 0) {
+    } else if (warp >= kMma) {
+        // ------------------------------------------------ MMA issuer (one elected lane), round robin over the pipelines.
+        // The lane's own instructions sit on every accumulator's critical path (release -> MMAs -> commit), and a lone thread
+        // issues a dependent instruction every 4-10 cycles: everything the MMAs need (descriptors, instruction word, TMEM
+        // address) is therefore advanced incrementally AFTER the commit and ready in registers before the wait - no divisions,
+        // no descriptor assembly between the wait and the four tcgen05.mma.
+        {                                                       // all 32 lanes run the loop (uniform control flow and values)
             mbar_wait(b_full, 0);
-            int grp[kUPipes], use_a[kUPipes], use_t[kUPipes], chunk[kUPipes];
+            tc_fence_after();
+            constexpr uint64_t kDescHi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+            const uint64_t b_desc0 = kDescHi | (uint64_t)((smem_u32(b_smem) >> 4) & 0x3FFF);
+            const uint32_t trace_step = (uint32_t)a.tiles_per_trace * kUN * (kUK * 4 / 16);      // descriptor address units (16 B) per trace
+            const int cpt = a.chunks_per_trace;
+            int grp[kUPipes], chunk[kUPipes], ci[kUPipes];
+            uint32_t use_a[kUPipes], use_t[kUPipes], b_tr[kUPipes], b_off[kUPipes];
+            uint64_t a_desc[kUPipes];
 #pragma unroll
-            for (int p = 0; p < kUPipes; ++p) { grp[p] = blockIdx.x + p * ncta; use_a[p] = 0; use_t[p] = 0; chunk[p] = 0; }
+            for (int p = 0; p < kUPipes; ++p) {
+                grp[p] = (kUIssuers == 1 || p == warp - kMma) ? blockIdx.x + p * ncta : a.n_groups;      // (not mine: done)
+                chunk[p] = 0; ci[p] = 0; use_a[p] = 0; use_t[p] = 0; b_tr[p] = 0; b_off[p] = 0;
+                a_desc[p] = kDescHi | (uint64_t)((smem_u32(a_smem + (size_t)p * kUM * kUK) >> 4) & 0x3FFF);
+            }
             bool busy = true;
             while (busy) {
                 busy = false;
@@ -242,21 +308,42 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
                 for (int p = 0; p < kUPipes; ++p) {
                     if (grp[p] >= a.n_groups) continue;
                     busy = true;
-                    if (chunk[p] == 0) { mbar_wait(&a_full[p], use_a[p] & 1); tc_fence_after(); }
-                    if (use_t[p] >= 1) { mbar_wait(&t_empty[p], (use_t[p] - 1) & 1); tc_fence_after(); }
-                    const int kk = chunk[p] / a.chunks_per_trace, ci = chunk[p] % a.chunks_per_trace;
-                    const uint32_t a_addr = smem_u32(a_smem + (size_t)p * kUM * kUK);
-                    const uint32_t b_addr = smem_u32(b_smem + ((size_t)(kk * a.tiles_per_trace) * kUN + (size_t)ci * kUNacc) * kUK);
-                    const uint32_t idesc = (ci == a.chunks_per_trace - 1) ? a.idesc_last : a.idesc_full;
-                    if (!(a.debug & 1))
-#pragma unroll
-                    for (int ks = 0; ks < kUK / 8; ++ks)
-                        umma_tf32(tmem_base + p * kUNacc, umma_smem_desc(a_addr + ks * 32), umma_smem_desc(b_addr + ks * 32), idesc, ks > 0);
-                    umma_commit(&t_full[p]);                        // accumulator ready for this pipeline's epilogue warps
+                    const uint32_t ts = p * kUStages + use_t[p] % kUStages;     // accumulator stage of this use
+                    const uint32_t tm = tmem_base + ts * kUNacc;
+                    const uint64_t ad = a_desc[p], bd = b_desc0 + b_off[p];
+                    const uint32_t idesc = (ci[p] == cpt - 1) ? a.idesc_last : a.idesc_full;
+#if FWI_UMMA_TRACE
+                    const long long tr0 = clock64();
+#endif
+                    if (chunk[p] == 0) mbar_wait(&a_full[p], use_a[p] & 1);
+                    if (use_t[p] >= kUStages) mbar_wait(&t_empty[ts], (use_t[p] / kUStages - 1) & 1);
+                    tc_fence_after();
+#if FWI_UMMA_TRACE
+                    const long long tr1 = clock64();
+#endif
+                    const bool last_chunk = chunk[p] + 1 == nchunks;
+                    if (elect_one()) {
+                        if (!(a.debug & 1)) {                                   // a K-step of 8 floats advances the start address by 32 B
+                            umma_tf32(tm, ad, bd, idesc, 0);
+                            umma_tf32(tm, ad + 2, bd + 2, idesc, 1);
+                            umma_tf32(tm, ad + 4, bd + 4, idesc, 1);
+                            umma_tf32(tm, ad + 6, bd + 6, idesc, 1);
+                        }
+                        umma_commit(&t_full[ts]);                   // accumulator ready for this pipeline's epilogue warps
+                        if (last_chunk) umma_commit(&a_empty[p]);   // all MMAs reading this A'' tile have completed
+                    }
+                    __syncwarp();
+#if FWI_UMMA_TRACE
+                    if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && use_t[p] >= kTrFirst && use_t[p] < kTrFirst + kTrN) {
+                        long long* t = g_trace[0][p][use_t[p] - kTrFirst];
+                        t[0] = tr0; t[1] = tr1; t[2] = clock64(); t[3] = 0;
+                    }
+#endif
                     ++use_t[p];
+                    if (++ci[p] == cpt) { ci[p] = 0; b_tr[p] += trace_step; b_off[p] = b_tr[p]; }
+                    else b_off[p] += kUNacc * (kUK * 4 / 16);
                     if (++chunk[p] == nchunks) {
-                        umma_commit(&a_empty[p]);                   // all MMAs reading this A'' tile have completed
-                        chunk[p] = 0; ++use_a[p];
+                        chunk[p] = 0; ci[p] = 0; b_tr[p] = 0; b_off[p] = 0; ++use_a[p];
                         grp[p] += kUPipes * ncta;
                     }
                 }
@@ -283,45 +370,107 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
             for (int k = k0; k < k1; ++k) {
                 float s0 = 0.f, s1 = 0.f, s2a = 0.f, s3 = 0.f, vmax = -3.0e38f, vmin = 3.0e38f;
                 float p0 = 0.f, p1 = 0.f, prev = 0.f;                 // CC-shift: lag-one products, last column of the previous piece
+                // the trace's constants and the first-order terms (9-term dot products with float64 constants) do not need the
+                // accumulator: they are issued here, so that their loads and fp64 chains overlap the wait for this trace's first MMAs
+                const double* ck = cst + (k - k0) * kUCst;
+                const TraceConst tc = *reinterpret_cast<const TraceConst*>(ck + 45);
+                double mud = 0.0, sd = 0.0, dlt = 0.0, f = 0.0, l = 0.0;
+                if (MODE != MODE_SSE) {
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {                     // (components past C hold 0 in both factors)
+                        mud = fma(coef[c], ck[c], mud);
+                        sd = fma(coef[c], ck[9 + c], sd);
+                        if (SH) { dlt = fma(coef[c], ck[18 + c], dlt); f = fma(coef[c], ck[27 + c], f); l = fma(coef[c], ck[36 + c], l); }
+                    }
+                }
+#if FWI_UMMA_TRACE
+                if (blockIdx.x == 0 && blockIdx.y == 0 && (warp & 3) == 0 && lane == 0 && use_t >= kTrFirst && use_t < kTrFirst + kTrN)
+                    g_trace[1][p][use_t - kTrFirst][5] = clock64();                // constants and dot products of this trace issued
+#endif
                 for (int ci = 0; ci < a.chunks_per_trace; ++ci, ++use_t) {
-                    mbar_wait(&t_full[p], use_t & 1);
+                    const int ts = p * kUStages + use_t % kUStages;
+#if FWI_UMMA_TRACE
+                    const long long te0 = clock64();
+#endif
+                    mbar_wait(&t_full[ts], (use_t / kUStages) & 1);
                     tc_fence_after();
-                    const uint32_t taddr = tmem_base + p * kUNacc + ((uint32_t)(wq * 32) << 16);
+#if FWI_UMMA_TRACE
+                    const long long te1 = clock64();
+                    long long te2 = 0;
+#endif
+                    const uint32_t taddr = tmem_base + ts * kUNacc + ((uint32_t)(wq * 32) << 16);
                     // columns the MMA of this chunk wrote (those past T hold 0: B'' is zero-padded); a multiple of 16
                     const int ncol = (ci == a.chunks_per_trace - 1) ? a.n_last : kUNacc;
-                    if (!(a.debug & 2)) {
-                        // 32 columns at a time.  (Keeping the next tcgen05.ld in flight while the current values are folded was
-                        // measured slower: 5.99 vs 5.70 ms for N = 4e6, and so were four loads in flight per accumulator.)
-                        for (int c0 = 0; c0 < ncol; c0 += 32) {
-                            float v[32];
-                            tmem_ld32(taddr + c0, v);
-                            tmem_ld_wait_dep(v);
-                            const bool half = ncol - c0 < 32;           // a trace's last piece may hold 16 columns
+                    // one 32-column piece of the accumulator (a trace's last piece may hold 16 columns: `half`)
+                    auto fold = [&](const float (&v)[32], const bool half) {
+#if FWI_UMMA_EXP == 1
+                        s0 += v[0];
+                        if (false)
+#endif
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                if (i < 16 || !half) {
-                                    s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
-                                    s2a = fmaf(v[i + 2], v[i + 2], s2a); s3 = fmaf(v[i + 3], v[i + 3], s3);
-                                    if (MODE == MODE_MOM_MAX) {
-                                        vmax = fmax3(vmax, v[i], v[i + 1]); vmin = fmin3(vmin, v[i], v[i + 1]);
-                                        vmax = fmax3(vmax, v[i + 2], v[i + 3]); vmin = fmin3(vmin, v[i + 2], v[i + 3]);
-                                    }
-                                    if (SH) {
-                                        // s'[t] s'[t+1]: columns past T hold 0, so the products past the trace's end vanish
-                                        p0 = fmaf(i == 0 ? prev : v[i - 1], v[i], p0); p1 = fmaf(v[i], v[i + 1], p1);
-                                        p0 = fmaf(v[i + 1], v[i + 2], p0); p1 = fmaf(v[i + 2], v[i + 3], p1);
-                                    }
+                        for (int i = 0; i < 32; i += 4) {
+                            if (i < 16 || !half) {
+                                s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
+                                s2a = fmaf(v[i + 2], v[i + 2], s2a); s3 = fmaf(v[i + 3], v[i + 3], s3);
+                                if (MODE == MODE_MOM_MAX) {
+                                    vmax = fmax3(vmax, v[i], v[i + 1]); vmin = fmin3(vmin, v[i], v[i + 1]);
+                                    vmax = fmax3(vmax, v[i + 2], v[i + 3]); vmin = fmin3(vmin, v[i + 2], v[i + 3]);
+                                }
+                                if (SH) {
+                                    // s'[t] s'[t+1]: columns past T hold 0, so the products past the trace's end vanish
+                                    p0 = fmaf(i == 0 ? prev : v[i - 1], v[i], p0); p1 = fmaf(v[i], v[i + 1], p1);
+                                    p0 = fmaf(v[i + 1], v[i + 2], p0); p1 = fmaf(v[i + 2], v[i + 3], p1);
                                 }
                             }
-                            if (SH) prev = v[31];                       // (a 16-column piece is a trace's last: prev is reset)
                         }
+                        if (SH) prev = v[31];                           // (a 16-column piece is a trace's last: prev is reset)
+                    };
+                    auto release = [&]() {                              // accumulator drained by this warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&t_empty[ts]);
+#if FWI_UMMA_TRACE
+                        te2 = clock64();
+#endif
+                    };
+                    if (a.debug & 2) {
+                        release();
+                    } else if (FWI_UMMA_LDPIPE && ncol == kUNacc) {
+                        // full chunk, unrolled: the next piece's tcgen05.ld is in flight while the current piece is folded, and the
+                        // accumulator goes back to the MMA issuer as soon as its last piece is in registers
+                        float va[32], vb[32];
+                        tmem_ld32(taddr, va);
+#pragma unroll kULdUnroll
+                        for (int i = 0; i < kUNacc / 32; i += 2) {
+                            tmem_ld_wait_dep(va);
+                            tmem_ld32(taddr + (i + 1) * 32, vb);
+                            fold(va, false);
+                            tmem_ld_wait_dep(vb);
+                            if (i + 2 < kUNacc / 32) tmem_ld32(taddr + (i + 2) * 32, va); else release();
+                            fold(vb, false);
+                        }
+                    } else {
+                        for (int c0 = 0; c0 < ncol; c0 += 32) {
+                            float v[32];
+#if FWI_UMMA_EXP == 2
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) asm volatile("" : "=f"(v[i]));
+#else
+                            tmem_ld32(taddr + c0, v);
+                            tmem_ld_wait_dep(v);
+#endif
+                            fold(v, ncol - c0 < 32);
+                        }
+                        release();
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&t_empty[p]);         // accumulator drained by this warp
+#if FWI_UMMA_TRACE
+                    if (blockIdx.x == 0 && blockIdx.y == 0 && (warp & 3) == 0 && lane == 0 && use_t >= kTrFirst && use_t < kTrFirst + kTrN) {
+                        long long* t = g_trace[1][p][use_t - kTrFirst];
+                        t[0] = te0; t[1] = te1; t[2] = te2; t[3] = clock64();
+                    }
+#endif
                 }
                 // ---- combine trace k (float64; the expressions of mc_eval_kernel's fold)
-                const TraceConst tc = a.tc[k];
                 const double s2 = (double)((s0 + s1) + (s2a + s3));
                 if (MODE == MODE_SSE) {
                     const double sse = s2, dd = tc.sumd2;
@@ -330,16 +479,6 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
                     else q0 += exp(-sse / (2.0 * tc.sigma * tc.sigma));                         // FWI:581
                 } else if (SH) {
                     // ---- CC-shift: moments of the 4x interpolated trace from S2, P and five dot products
-                    const double* sc = a.shc + (size_t)k * 4 * a.C;
-                    double mud = 0.0, dlt = 0.0, sd = 0.0, f = 0.0, l = 0.0;
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) {
-                        if (c < a.C) {
-                            mud = fma(coef[c], a.gbar[k * a.C + c], mud); dlt = fma(coef[c], sc[c], dlt);
-                            sd = fma(coef[c], sc[a.C + c], sd);
-                            f = fma(coef[c], sc[2 * a.C + c], f); l = fma(coef[c], sc[3 * a.C + c], l);
-                        }
-                    }
                     const double Tv = 4.0 * Tn, P = (double)(p0 + p1);
                     const double ssq = fma(2.75, s2, fma(1.25, P, fma(2.125 * l, l, -0.875 * f * f))) - Tv * dlt * dlt;   // sum_i (s_i - mean_i s)^2
                     const double mui = mud + dlt;                                               // mean of the interpolated synthetic
@@ -365,11 +504,6 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
                         q0 += A1; q1 += A2; q2 += A3;
                     }
                 } else {
-                    double mud = 0.0, sd = 0.0;
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) {
-                        if (c < a.C) { mud = fma(coef[c], a.gbar[k * a.C + c], mud); sd = fma(coef[c], a.gdc[k * a.C + c], sd); }
-                    }
                     double aa = 1.0, bb = 1.0;
                     if (MODE == MODE_MOM_MAX) {
                         aa = rcp64(fmax(fabs((double)vmax + mud), fabs((double)vmin + mud)));     // FWI:598-599
@@ -393,6 +527,10 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
                         q2 += aa * bb * (sd + Tn * tc.mean_d * mud);
                     }
                 }
+#if FWI_UMMA_TRACE
+                if (blockIdx.x == 0 && blockIdx.y == 0 && (warp & 3) == 0 && lane == 0 && use_t - 1 >= kTrFirst && use_t - 1 < kTrFirst + kTrN)
+                    g_trace[1][p][use_t - 1 - kTrFirst][4] = clock64() + (long long)(q0 * 0.0);      // trace combined (depends on its result)
+#endif
             }
             if (live) {
                 double* o = a.part + (size_t)tg * a.npart * a.N + n;
@@ -403,6 +541,18 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
+#if FWI_UMMA_TRACE
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        const long long t0 = g_trace[0][0][0][0];
+        for (int i = 0; i < kTrN; ++i)
+            for (int p = 0; p < kUPipes; ++p) {
+                const long long* I = g_trace[0][p][i];
+                const long long* E = g_trace[1][p][i];
+                printf("use %3d p%d | issuer: wait %6lld wake %6lld committed %6lld | epilogue: consts %6lld wait %6lld wake %6lld released %6lld folded %6lld combined %6lld\n",
+                       kTrFirst + i, p, I[0] - t0, I[1] - t0, I[2] - t0, E[5] ? E[5] - t0 : 0, E[0] - t0, E[1] - t0, E[2] - t0, E[3] - t0, E[4] ? E[4] - t0 : 0);
+            }
+    }
+#endif
     if (warp == kMma) tmem_dealloc(tmem_base, 512);
 }
 
@@ -512,7 +662,9 @@ struct UmmaPath {
     CUtensorMap tm_raw, tm_cen;
 };
 
-constexpr int kUSmem = kUTilesMax * kUN * kUK * 4 + kUPipes * kUM * kUK * 4 + 256;
+constexpr int kUSmem = kUTilesMax * kUN * kUK * 4 + kUPipes * kUM * kUK * 4 + 256 + kUTilesMax * kUCst * 8;
+static_assert(kUSmem <= 227 * 1024, "shared memory budget");
+static_assert(sizeof(TraceConst) == 7 * sizeof(double), "TraceConst is copied to shared memory as 7 doubles");
 
 int umma_build(UmmaPath** out, int device, const double* G, const double* d, int K, int C, int T, const TraceConst* tc_dev,
                const FlatConst& fc) {
