@@ -337,7 +337,7 @@ struct fwi_fd2d {
     int variant = 0;                  // 0 = one-tile-per-CTA kernel, 2 = two-steps-per-pass kernel (temporal blocking)
     int sm_count = 148;
     CUtensorMap tb_cur[8], tb_old[8], tb_m;     // temporally blocked kernel (variant 2)
-    int cz = 32, tiles_x2 = 0, tiles_z2 = 0;
+    int cz = 32, tb_nw = 8, tiles_x2 = 0, tiles_z2 = 0;
     float *m = nullptr, *vp = nullptr, *gx = nullptr, *gz = nullptr;
     void* arena = nullptr; size_t l2_persist_bytes = 0;
     float* fld[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // forward 0..3, adjoint 4..7 (one-step kernels use 0/1 and 4/5)
@@ -647,7 +647,8 @@ static int launch_step(fwi_fd2d* p, int mode, int cur, float* oldnew, const Poin
     p->launches++;
     if (p->ny > 1) return launch_step3(p, mode, cur, oldnew, inj, inj_vals, rec, rec_out, snap, st, snap_prev);
 #define CFG(BZV, NWV) if (p->bz == BZV && p->nw == NWV) return launch_step_cfg<BZV, NWV>(p, mode, cur, oldnew, inj, inj_vals, rec, rec_out, snap, st, snap_prev)
-    CFG(32, 4); CFG(64, 8); CFG(16, 2);      // the sweep's winner (default), and one taller / one flatter tile for tests
+    CFG(32, 4); CFG(64, 8); CFG(16, 2);      // the round-1 sweep's winner, and one taller / one flatter tile for tests
+    CFG(28, 4); CFG(42, 6); CFG(56, 8);      // 7 rows per warp: heights among which pick_tile() finds one whose tiles fill whole waves
 #undef CFG
     set_error("fd2d: unsupported tile configuration bz=%d nw=%d", p->bz, p->nw);
     return FWI_EINVAL;
@@ -719,8 +720,8 @@ static int launch_tb2(fwi_fd2d* p, int mode, const State& s, int jc, int jd, con
                       const float* inj1, const float* inj2, const PointList* rec, float* rec1, float* rec2, float* snap1, float* snap2,
                       cudaStream_t st) {
     p->launches++;
-#define TB(CZV) if (p->cz == CZV) return launch_tb2_cfg<CZV, 8>(p, mode, s, jc, jd, inj_ext, inj_own, inj1, inj2, rec, rec1, rec2, snap1, snap2, st)
-    TB(32); TB(24); TB(16);
+#define TB(CZV, NWV) if (p->cz == CZV && p->tb_nw == NWV) return launch_tb2_cfg<CZV, NWV>(p, mode, s, jc, jd, inj_ext, inj_own, inj1, inj2, rec, rec1, rec2, snap1, snap2, st)
+    TB(32, 8); TB(24, 8); TB(16, 8);
 #undef TB
     set_error("fd2d: unsupported temporal-blocking tile cz=%d", p->cz);
     return FWI_EINVAL;
@@ -1036,6 +1037,23 @@ static int init_plan(fwi_fd2d* p, int device, int nz, int ny, int nx, float h, f
     return FWI_OK;
 }
 
+// Tile height of the one-step kernel.  All tiles of a step are resident at once (3-6 CTAs per SM), so a step lasts as long as
+// the SM with the most tiles: 1000 x 3000 in 128 x 32 tiles is 768 tiles = 5.2 per SM, i.e. 28 SMs carry 6 and set the pace
+// (0.865 balance), while 42-row tiles are 576 = 3.9 per SM (0.97) with less halo (50 rows read for 42 instead of 40 for 32).
+// Model cost: ceil(tiles / SMs) x (rows + 4) - the 8 halo rows are loaded but not computed.  Measured at 1000 x 3000, us per
+// forward+adjoint step pair: 32 rows 16.67, 28: 15.34, 42: 15.50, 56: 15.56 (forward step 6.77 / 5.83 / 5.94 / 5.85); at
+// 1500 x 3000: 27.9 / 25.9 / 26.1 / 26.8.  The kernels are bit-identical, only the decomposition differs.
+static void pick_tile(int nz, int nx, int sms, int* bz, int* nw) {
+    const int cand[][2] = {{32, 4}, {28, 4}, {42, 6}, {56, 8}};          // (5 and 7 warps per CTA measured 1.5x slower at 1000 x 3000)
+    const long tx = (nx + kBX - 1) / kBX;
+    double best = 1e300;
+    for (const auto& c : cand) {
+        const long tiles = tx * ((nz + c[0] - 1) / c[0]);
+        const double cost = (double)((tiles + sms - 1) / sms) * (c[0] + 4);
+        if (cost < best - 1e-9) { best = cost; *bz = c[0]; *nw = c[1]; }
+    }
+}
+
 int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, float alpha, fwi_fd2d** out) {
     int rc = create_plan(device, nz, 1, nx, h, dt, nabs, alpha, out);
     if (rc) return rc;
@@ -1050,6 +1068,13 @@ int fwi_fd2d_create(int device, int nz, int nx, float h, float dt, int nabs, flo
     if (!force_tile && nz >= 32 && nx >= 128) {
         if (pts <= 2.0e6) rc = fwi_fd2d_set_tb2(*out, 24);
         else if (pts > 7.5e6) rc = fwi_fd2d_set_tb2(*out, 32);
+        if (rc) { fwi_fd2d_destroy(*out); *out = nullptr; return rc; }
+    }
+    if ((*out)->variant == 0 && nz >= 32) {
+        int bz = 32, nw = 4;
+        pick_tile(nz, nx, (*out)->sm_count, &bz, &nw);
+        if (const char* t = getenv("FWI_FD2D_BZ")) { const int v = atoi(t); if (v == 28 || v == 42 || v == 56) { bz = v; nw = v / 7; } else if (v == 32) { bz = 32; nw = 4; } }   // tuning aid
+        rc = fwi_fd2d_set_tile(*out, bz, nw);
         if (rc) { fwi_fd2d_destroy(*out); *out = nullptr; }
     }
     return rc;
@@ -1086,7 +1111,7 @@ int fwi_fd2d_destroy(fwi_fd2d* p) {
 
 int fwi_fd2d_set_tile(fwi_fd2d* p, int bz, int nw) {
     FWI_REQUIRE(p, "fwi_fd2d_set_tile: NULL plan");
-    const bool ok = (bz == 32 && nw == 4) || (bz == 64 && nw == 8) || (bz == 16 && nw == 2);
+    const bool ok = (bz == 32 && nw == 4) || (bz == 64 && nw == 8) || (bz == 16 && nw == 2) || (bz == 28 && nw == 4) || (bz == 42 && nw == 6) || (bz == 56 && nw == 8);
     FWI_REQUIRE(ok, "fwi_fd2d_set_tile: unsupported (bz=%d, nw=%d)", bz, nw);
     FWI_REQUIRE(p->ny == 1, "fwi_fd2d_set_tile: 2-D plans only");
     DeviceGuard g(p->device);
@@ -1106,6 +1131,7 @@ int fwi_fd2d_set_tb2(fwi_fd2d* p, int cz) {
     FWI_CUDA(cudaStreamSynchronize(p->work));
     drop_graphs(p);
     p->variant = 2; p->cz = cz;
+    p->tb_nw = 8;                                                      // warps per CTA (4 warps at 24 rows measured 8 % slower)
     p->src.release(); p->rec.release(); p->nsrc = p->nrec = 0;
     p->src_ext2.release(); p->src_own2.release(); p->rec_ext2.release(); p->rec_own2.release();
     return make_tmaps(p);

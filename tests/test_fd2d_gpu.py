@@ -64,6 +64,7 @@ def test_forward_traces_and_wavefield(ac, nz, nx, nt, nsrc, kw):
 
 
 @pytest.mark.parametrize("kind,cfg", [("tile", (32, 4)), ("tile", (64, 8)), ("tile", (16, 2)), ("graphs", False),
+                                      ("tile", (28, 4)), ("tile", (42, 6)), ("tile", (56, 8)),
                                       ("tb2", 32), ("tb2", 16), ("tb2", 24)])
 def test_kernel_variants_agree(ac, kind, cfg):
     """Every step-kernel variant (one-tile-per-CTA shapes, two-steps-per-pass, plain launches) gives the oracle's traces and gradient."""
