@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--cpu-sample-nt", type=int, default=600)
     ap.add_argument("--force-dist", action="store_true", help="diagnostic: initialise NCCL even with one rank")
+    ap.add_argument("--no-graphs", action="store_true", help="diagnostic: individual launches instead of CUDA-graph replay of the time loops")
     return ap.parse_args()
 
 
@@ -505,7 +506,7 @@ def run_b200(args):
     w = workload(args)
     nz, nx, nt = w["nz"], w["nx"], w["nt"]
     tile = tuple(int(x) for x in args.tile.split(",")) if args.tile else None
-    prop = ac.Propagator2D((nz, nx), w["h"], w["dt"], nabs=w["nabs"], alpha=w["alpha"], device=local, tile=tile, tb2=(args.tb2 or None))
+    prop = ac.Propagator2D((nz, nx), w["h"], w["dt"], nabs=w["nabs"], alpha=w["alpha"], device=local, tile=tile, tb2=(args.tb2 or None), graphs=not args.no_graphs)
     v_dev = torch.from_numpy(w["v"]).to(dev)
     wav_dev = torch.from_numpy(w["wav"]).to(dev)
     nrun = args.warmup + args.steps

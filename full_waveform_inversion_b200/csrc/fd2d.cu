@@ -77,7 +77,9 @@ __global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constan
     }
     float4 gx4 = make_float4(1.f, 1.f, 1.f, 1.f);
     if (col_ok) gx4 = ld4(a.gx + x);
-    // (prefetching the adjoint's snapshot rows into L2 from here was measured: 17.3 vs 17.0 ms per 1000-step gradient, not kept)
+    // (prefetching the adjoint's snapshot rows into L2 from here was measured: 17.3 vs 17.0 ms per 1000-step gradient, not kept;
+    //  so was a bulk L2 prefetch, cp.async.bulk.prefetch.L2, of the two snapshot tiles of the NEXT deferred-imaging launch
+    //  issued by the propagate-only step before it: 16.5 vs 15.6 us per forward+adjoint step pair at 1000 x 3000)
 #if FWI_PREFETCH_ROW0
     // u_{n-1} and m of this warp's first rows: neither is written by the step this launch is chained to (u_{n-1} is the
     // output of step n-2, which completed before step n-1 passed its own wait), and requesting them here takes one L2

@@ -8,7 +8,7 @@ from full_waveform_inversion_b200 import acoustic as ac
 nz, nx, nt = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (1000, 3000, 600)
 
 def bench(**kw):
-    prop = ac.Propagator2D((nz, nx), 10.0, 7e-4, nabs=40, **kw)
+    prop = ac.Propagator2D((nz, nx), 10.0, 7e-4, nabs=40, graphs=os.environ.get('GRAPHS', '1') != '0', **kw)
     prop.set_model(torch.full((nz, nx), 2500.0, device="cuda"))
     prop.set_geometry([(4, nx // 2)], [(4, x) for x in range(0, nx, int(os.environ.get('REC_STRIDE', '1')))])
     wav = torch.from_numpy(ac.ricker(nt, 7e-4, 10.0)).cuda()
