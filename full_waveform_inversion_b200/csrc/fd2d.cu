@@ -393,9 +393,8 @@ static int make_tmaps3(fwi_fd2d* p) {
         // boundaries are pushed early; a 4-plane boundary must not straddle two chunks
         // (measured on 8 GPUs, 64 planes per rank, us per launch: one chunk 93.0 / 95.7 with 14- / 16-row tiles, two chunks
         // 97.9 / 100.1 - a single chunk re-reads 8 instead of 16 halo planes, which outweighs pushing the lower boundary
-        // at the end of the launch; the model charges that late push 3 %).  Thicker slabs (2 and 4 GPUs at 512 planes) were
-        // only measured with two or more chunks and keep them.
-        int min_ch = (p->peer_arena[1] && nzo > 64) ? 2 : 1;
+        // at the end of the launch; the model charges that late push 3 %; 4 GPUs, 128 planes per rank: 152.4 vs 157.2 us)
+        int min_ch = 1;
         int force_by = 0, force_ch = 0;
         if (const char* e = getenv("FWI_FD3D_BY")) force_by = atoi(e);
         if (const char* e = getenv("FWI_FD3D_NZCH")) force_ch = atoi(e);       // tuning aid: fixed chunk count (1 = the lower boundary is pushed last)
