@@ -60,6 +60,11 @@ constexpr int kUPipes = FWI_UMMA_PIPES; // independent pipelines per CTA (sample
 #ifndef FWI_UMMA_LDPIPE
 #define FWI_UMMA_LDPIPE 1                   // full chunks: next piece's tcgen05.ld in flight while the current piece is folded
 #endif
+#ifndef FWI_UMMA_F32X2
+#define FWI_UMMA_F32X2 0                    // 1: sum of squares with the packed fma.rn.f32x2 (FFMA2, two accumulator elements per instruction).
+                                            // Measured, M samples/s at N = 4e6 (0 / 1): VR 919 / 863, normalised VR 539 / 500, PCC 721 / 742,
+                                            // gau 752 / 797, CC-shift 543 / 548, normalised CC-shift 408 / 399 - not the default
+#endif
 #ifndef FWI_UMMA_LDUNROLL
 #define FWI_UMMA_LDUNROLL 4                 // unroll factor of the pipelined piece loop (2 pieces per iteration; 4 = a whole 256-column chunk)
 #endif
@@ -154,6 +159,15 @@ __device__ __forceinline__ double rsqrt64(double x) {
     y = y * fma(-0.5 * x, y * y, 1.5);
     y = y * fma(-0.5 * x, y * y, 1.5);
     return y * fma(-0.5 * x, y * y, 1.5);
+}
+// packed fp32 pair arithmetic (sm_100: one instruction, two IEEE fma's): acc.{lo,hi} += {a,b}^2
+__device__ __forceinline__ void sq_acc2(uint64_t& acc, float a, float b) {
+    asm("{\n\t.reg .b64 p;\n\tmov.b64 p, {%1, %2};\n\tfma.rn.f32x2 %0, p, p, %0;\n\t}" : "+l"(acc) : "f"(a), "f"(b));
+}
+__device__ __forceinline__ float pair_sum(uint64_t acc) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc));
+    return lo + hi;
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {      // FMNMX3: one instruction for two comparisons
     float d;
@@ -369,6 +383,7 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
             double grp_first = 0.0, carry_s = 0.0, carry_d = 0.0;     // flattened CC-shift: boundary values (see the header)
             for (int k = k0; k < k1; ++k) {
                 float s0 = 0.f, s1 = 0.f, s2a = 0.f, s3 = 0.f, vmax = -3.0e38f, vmin = 3.0e38f;
+                uint64_t s01 = 0, s23 = 0;                            // the same four partial sums as packed pairs (FWI_UMMA_F32X2)
                 float p0 = 0.f, p1 = 0.f, prev = 0.f;                 // CC-shift: lag-one products, last column of the previous piece
                 // the trace's constants and the first-order terms (9-term dot products with float64 constants) do not need the
                 // accumulator: they are issued here, so that their loads and fp64 chains overlap the wait for this trace's first MMAs
@@ -410,8 +425,11 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             if (i < 16 || !half) {
-                                s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
-                                s2a = fmaf(v[i + 2], v[i + 2], s2a); s3 = fmaf(v[i + 3], v[i + 3], s3);
+                                if (FWI_UMMA_F32X2) { sq_acc2(s01, v[i], v[i + 1]); sq_acc2(s23, v[i + 2], v[i + 3]); }
+                                else {
+                                    s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
+                                    s2a = fmaf(v[i + 2], v[i + 2], s2a); s3 = fmaf(v[i + 3], v[i + 3], s3);
+                                }
                                 if (MODE == MODE_MOM_MAX) {
                                     vmax = fmax3(vmax, v[i], v[i + 1]); vmin = fmin3(vmin, v[i], v[i + 1]);
                                     vmax = fmax3(vmax, v[i + 2], v[i + 3]); vmin = fmin3(vmin, v[i + 2], v[i + 3]);
@@ -471,7 +489,7 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
 #endif
                 }
                 // ---- combine trace k (float64; the expressions of mc_eval_kernel's fold)
-                const double s2 = (double)((s0 + s1) + (s2a + s3));
+                const double s2 = FWI_UMMA_F32X2 ? (double)(pair_sum(s01) + pair_sum(s23)) : (double)((s0 + s1) + (s2a + s3));
                 if (MODE == MODE_SSE) {
                     const double sse = s2, dd = tc.sumd2;
                     q1 += sse; q2 += dd;
