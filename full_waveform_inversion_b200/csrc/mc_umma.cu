@@ -60,6 +60,12 @@ constexpr int kUPipes = FWI_UMMA_PIPES; // independent pipelines per CTA (sample
 #ifndef FWI_UMMA_LDPIPE
 #define FWI_UMMA_LDPIPE 1                   // full chunks: next piece's tcgen05.ld in flight while the current piece is folded
 #endif
+#ifndef FWI_UMMA_FUSEPACK
+#define FWI_UMMA_FUSEPACK 0                 // 1: the producer warp builds the A'' tile in shared memory from the samples (no pack kernel, no
+                                            // 128 B per sample A'' array).  Measured at N = 4e6: VR 767 M samples/s against 919 with the pack kernel
+                                            // + TMA (the warp's ~600 instructions per tile compete with the epilogue warps of its sub-partition
+                                            // and follow the stage's release; a TMA load is one instruction) - kept as a memory-saving option
+#endif
 #ifndef FWI_UMMA_F32X2
 #define FWI_UMMA_F32X2 0                    // 1: sum of squares with the packed fma.rn.f32x2 (FFMA2, two accumulator elements per instruction).
                                             // Measured, M samples/s at N = 4e6 (0 / 1): VR 919 / 863, normalised VR 539 / 500, PCC 721 / 742,
@@ -168,6 +174,28 @@ __device__ __forceinline__ float pair_sum(uint64_t acc) {
     float lo, hi;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc));
     return lo + hi;
+}
+__device__ __forceinline__ void row_set(float (&row)[32], int idx, float v) {      // runtime index, registers only
+#pragma unroll
+    for (int q = 0; q < 32; ++q) row[q] = (q == idx) ? v : row[q];
+}
+__host__ __device__ inline float tf32_round(float x);
+// A''[n] = [M_hi | M_hi | M_lo | -1 -1 (with_d) | 0 ...]; CT = the number of components when it is known at compile time
+template <int CT>
+__device__ __forceinline__ void a_row(float (&row)[32], const float (&m)[9], int C, bool with_d) {
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        if (c < (CT ? CT : C)) {
+            const float x = m[c];
+            const float hi = tf32_round(x), lo = tf32_round(x - hi);
+            if (CT) { row[c] = hi; row[CT + c] = hi; row[2 * CT + c] = lo; }
+            else { row[c] = hi; row_set(row, C + c, hi); row_set(row, 2 * C + c, lo); }
+        }
+    }
+    if (with_d) {
+        if (CT) { row[3 * CT] = -1.f; row[3 * CT + 1] = -1.f; }
+        else { row_set(row, 3 * C, -1.f); row_set(row, 3 * C + 1, -1.f); }
+    }
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {      // FMNMX3: one instruction for two comparisons
     float d;
@@ -285,6 +313,7 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
                 const int k = k0 + j / a.tiles_per_trace, tt = j % a.tiles_per_trace;
                 tma_load_2d(b_smem + (size_t)j * kUN * kUK, &tm_b, 0, (k * a.tiles_per_trace + tt) * kUN, b_full);
             }
+#if !FWI_UMMA_FUSEPACK
             int i = 0;
             for (int g = blockIdx.x; g < a.n_groups; g += ncta, ++i) {
                 const int p = i % kUPipes, use = i / kUPipes;          // pipeline, and how often its A'' stage has been used
@@ -292,7 +321,52 @@ __global__ void __launch_bounds__(kUThreads, 1) mc_umma_kernel(const __grid_cons
                 mbar_expect_tx(&a_full[p], kUM * kUK * 4);
                 tma_load_2d(a_smem + (size_t)p * kUM * kUK, &tm_a, 0, g * kUM, &a_full[p]);
             }
+#endif
         }
+#if FWI_UMMA_FUSEPACK
+        // The A'' tile of a sample group straight from the sampler's (rows, N) layout: each lane splits the coefficients of four
+        // samples into tf32 hi / lo parts and writes the 128-byte rows in the layout a SWIZZLE_128B TMA box would have produced
+        // (16-byte chunk c of row r at chunk position c ^ (r & 7) of its 8-row group), then makes the writes visible to the
+        // async proxy the tensor core reads through.
+        // The coefficients of the NEXT group are requested right after a tile is handed over, so that only the split and the
+        // shared-memory stores follow the wait for the stage (the global loads took ~3x a TMA load's latency otherwise).
+        __syncwarp();
+        float xv[kUM / 32][9];
+        auto request = [&](int g) {
+#pragma unroll
+            for (int j = 0; j < kUM / 32; ++j) {
+                const int64_t n = (int64_t)g * kUM + lane + 32 * j;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) xv[j][c] = (g < a.n_groups && n < a.N && c < a.C) ? __ldg(a.M + (size_t)c * a.ldm + n) : 0.f;
+            }
+        };
+        request(blockIdx.x);
+        int i = 0;
+        for (int g = blockIdx.x; g < a.n_groups; g += ncta, ++i) {
+            const int p = i % kUPipes, use = i / kUPipes;              // pipeline, and how often its A'' stage has been used
+            if (use >= 1) mbar_wait(&a_empty[p], (use - 1) & 1);
+            float* dst = a_smem + (size_t)p * kUM * kUK;
+#pragma unroll
+            for (int j = 0; j < kUM / 32; ++j) {
+                const int r = lane + 32 * j;
+                const bool live = (int64_t)g * kUM + r < a.N;
+                float row[kUK];
+#pragma unroll
+                for (int q = 0; q < kUK; ++q) row[q] = 0.f;
+                if (a.C == 9) a_row<9>(row, xv[j], 9, live && MODE == MODE_SSE);
+                else if (a.C == 6) a_row<6>(row, xv[j], 6, live && MODE == MODE_SSE);
+                else if (a.C == 3) a_row<3>(row, xv[j], 3, live && MODE == MODE_SSE);
+                else a_row<0>(row, xv[j], a.C, live && MODE == MODE_SSE);
+#pragma unroll
+                for (int c8 = 0; c8 < kUK / 4; ++c8)
+                    *reinterpret_cast<float4*>(dst + (size_t)r * kUK + ((c8 ^ (r & 7)) << 2)) = make_float4(row[4 * c8], row[4 * c8 + 1], row[4 * c8 + 2], row[4 * c8 + 3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[p]);
+            request(g + ncta);
+        }
+#endif
     } else if (warp >= kMma) {
         // ------------------------------------------------ MMA issuer (one elected lane), round robin over the pipelines.
         // The lane's own instructions sit on every accumulator's critical path (release -> MMAs -> commit), and a lone thread
@@ -829,7 +903,7 @@ int umma_eval(UmmaPath* u, const float* M_dev, int64_t ldm, int64_t N, int metri
     const bool shift = metric == FWI_METRIC_CC_SHIFT;
     const int npart = (shift && simul) ? 5 : 3;
     const int64_t ngroups = (N + kUM - 1) / kUM, Npad = ngroups * kUM;
-    if (u->A_rows < (size_t)Npad) {
+    if (!FWI_UMMA_FUSEPACK && u->A_rows < (size_t)Npad) {
         if (u->A) cudaFree(u->A);
         u->A = nullptr; u->A_rows = 0;
         FWI_CUDA(cudaMalloc(&u->A, (size_t)Npad * kUK * sizeof(float)));
@@ -842,10 +916,14 @@ int umma_eval(UmmaPath* u, const float* M_dev, int64_t ldm, int64_t N, int metri
         u->part_cap = (size_t)u->n_tgroups * npart * N;
     }
     CUtensorMap tm_a;
-    int rc = encode_rows32_sw128(&tm_a, u->A, (uint64_t)Npad, kUM);
-    if (rc) return rc;
-    mc_umma_pack_kernel<<<(unsigned)((Npad + 127) / 128), 128, 0, st>>>(M_dev, ldm, u->C, N, Npad, mode == MODE_SSE ? 1 : 0, u->A);
-    FWI_CUDA(cudaGetLastError());
+    memset(&tm_a, 0, sizeof(tm_a));
+    int rc = FWI_OK;
+    if (!FWI_UMMA_FUSEPACK) {
+        rc = encode_rows32_sw128(&tm_a, u->A, (uint64_t)Npad, kUM);
+        if (rc) return rc;
+        mc_umma_pack_kernel<<<(unsigned)((Npad + 127) / 128), 128, 0, st>>>(M_dev, ldm, u->C, N, Npad, mode == MODE_SSE ? 1 : 0, u->A);
+        FWI_CUDA(cudaGetLastError());
+    }
     // CTAs per trace group in proportion to its traces (K = 21, two resident traces: 10 groups x 14 CTAs + 1 group x 7 = 147)
     const int last_traces = u->K - (u->n_tgroups - 1) * u->traces_per_cta;
     const int ctas_full = (int)std::min<int64_t>(ngroups, std::max(1, u->sms * u->traces_per_cta / u->K));
