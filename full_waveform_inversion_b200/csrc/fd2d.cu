@@ -56,12 +56,25 @@ struct Step2DArgs {
 // implicit trigger only the launch latency and the prologue overlap and the CTAs stay staggered.
 #define FWI_PDL_TRIGGER 0
 #endif
+#ifndef FWI_M_SMEM
+// 1: the tile's rows of m (static inside a sweep) are staged in shared memory by a TMA load issued BEFORE the dependency wait
+#define FWI_M_SMEM 0
+#endif
+constexpr size_t step_tile_floats(int bz) { return ((size_t)(128 + 2 * kHalo) * (bz + 2 * kHalo) + 31) / 32 * 32; }    // [SZ][SX] rounded up to a 128-byte multiple
 template <int BZ, int NW, int MODE>
-__global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constant__ CUtensorMap tm_cur, Step2DArgs a) {
+__global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constant__ CUtensorMap tm_cur,
+#if FWI_M_SMEM
+                                                             const __grid_constant__ CUtensorMap tm_m,
+#endif
+                                                             Step2DArgs a) {
     constexpr int BX = 128, SX = BX + 2 * kHalo, SZ = BZ + 2 * kHalo, RPW = BZ / NW;
     static_assert(BZ % NW == 0, "rows must split evenly over warps");
-    extern __shared__ __align__(128) float tile[];          // [SZ][SX]
+    extern __shared__ __align__(128) float tile[];          // [SZ][SX] (+ [BZ][BX] of m)
     __shared__ __align__(8) uint64_t bar;
+#if FWI_M_SMEM
+    __shared__ __align__(8) uint64_t bar_m;
+    float* sM = tile + step_tile_floats(BZ);
+#endif
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tx0 = blockIdx.x * BX, tz0 = blockIdx.y * BZ;
@@ -72,8 +85,15 @@ __global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constan
     //      step n+1 runs while step n is still draining (the launch latency and the tail of a 6 us kernel overlap)
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
+#if FWI_M_SMEM
+        mbar_init(&bar_m, 1);
+#endif
         fence_mbar_init();
         fence_proxy_async();
+#if FWI_M_SMEM
+        mbar_expect_tx(&bar_m, BZ * BX * (uint32_t)sizeof(float));
+        tma_load_2d(sM, &tm_m, tx0, tz0, &bar_m);
+#endif
     }
     float4 gx4 = make_float4(1.f, 1.f, 1.f, 1.f);
     if (col_ok) gx4 = ld4(a.gx + x);
@@ -88,7 +108,12 @@ __global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constan
 #pragma unroll
     for (int r = 0; r < FWI_PREFETCH_ROW0; ++r) {
         o4p[r] = make_float4(0.f, 0.f, 0.f, 0.f); m4p[r] = o4p[r];
-        if (col_ok && zw + r < a.nz) { o4p[r] = ld4(a.oldnew + (size_t)(zw + r) * a.px + x); m4p[r] = ld4(a.m + (size_t)(zw + r) * a.px + x); }
+        if (col_ok && zw + r < a.nz) {
+            o4p[r] = ld4(a.oldnew + (size_t)(zw + r) * a.px + x);
+#if !FWI_M_SMEM
+            m4p[r] = ld4(a.m + (size_t)(zw + r) * a.px + x);
+#endif
+        }
     }
 #endif
     griddep_wait();                 // step n complete and visible (no-op for a plain launch)
@@ -102,6 +127,9 @@ __global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constan
     __syncthreads();        // barrier init visible to every waiter
 
     mbar_wait(&bar, 0);
+#if FWI_M_SMEM
+    mbar_wait(&bar_m, 0);
+#endif
 #if FWI_PDL_TRIGGER == 3
     griddep_launch_dependents();
 #endif
@@ -127,7 +155,10 @@ __global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constan
 #pragma unroll
                 for (int k = 0; k < 9; ++k) { zc[k][0] = win[k].x; zc[k][1] = win[k].y; zc[k][2] = win[k].z; zc[k][3] = win[k].w; }
                 const size_t off = (size_t)z * a.px + x;
-#if FWI_PREFETCH_ROW0
+#if FWI_M_SMEM
+                const float4 o4 = (r < FWI_PREFETCH_ROW0) ? o4p[r < FWI_PREFETCH_ROW0 ? r : 0] : ld4(a.oldnew + off);
+                const float4 m4 = ld4(sM + (warp * RPW + r) * BX + 4 * lane);
+#elif FWI_PREFETCH_ROW0
                 const float4 o4 = (r < FWI_PREFETCH_ROW0) ? o4p[r < FWI_PREFETCH_ROW0 ? r : 0] : ld4(a.oldnew + off);
                 const float4 m4 = (r < FWI_PREFETCH_ROW0) ? m4p[r < FWI_PREFETCH_ROW0 ? r : 0] : ld4(a.m + off);
 #else
@@ -344,6 +375,7 @@ struct fwi_fd2d {
     void* arena = nullptr; size_t l2_persist_bytes = 0;
     float* fld[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // forward 0..3, adjoint 4..7 (one-step kernels use 0/1 and 4/5)
     CUtensorMap tmap[8];
+    CUtensorMap tmap_m;               // FWI_M_SMEM: 128 x bz box of m
     float* acc = nullptr;
     float* snap = nullptr; size_t snap_steps = 0;
     float* ckpt = nullptr; size_t ckpt_slots = 0;
@@ -460,6 +492,13 @@ static int make_tmaps(fwi_fd2d* p) {
         const uint64_t strides[1] = {(uint64_t)p->px * sizeof(float)};
         const uint32_t box[2] = {(uint32_t)(kBX + 2 * kHalo), (uint32_t)(p->bz + 2 * kHalo)};
         int rc = encode_tiled_f32(&p->tmap[i], p->fld[i], 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims_p[2] = {(uint64_t)p->px, (uint64_t)p->nz};
+        const uint64_t strides[1] = {(uint64_t)p->px * sizeof(float)};
+        const uint32_t box_m[2] = {(uint32_t)kBX, (uint32_t)p->bz};
+        int rc = encode_tiled_f32(&p->tmap_m, p->m, 2, dims_p, strides, box_m);
         if (rc) return rc;
     }
     return FWI_OK;
@@ -589,7 +628,21 @@ static int launch_step_cfg(fwi_fd2d* p, int mode, int cur, float* oldnew, const 
     a.rec = (rec && rec->n) ? rec->dev() : PointListDev{nullptr, nullptr, nullptr};
     a.rec_out = rec_out;
     const dim3 grid(p->tiles_x, p->tiles_z), block(NW * 32);
+#if FWI_M_SMEM
+    const size_t smem = (step_tile_floats(BZ) + (size_t)BZ * kBX) * sizeof(float);
+#define STEP_TMAPS p->tmap[cur], p->tmap_m
+    static bool smem_attr_set = false;          // per <BZ, NW> instantiation: tile + m rows exceed the 48 KB default
+    if (!smem_attr_set) {
+        FWI_CUDA(cudaFuncSetAttribute(fd2d_step_kernel<BZ, NW, STEP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FWI_CUDA(cudaFuncSetAttribute(fd2d_step_kernel<BZ, NW, STEP_FWD_SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FWI_CUDA(cudaFuncSetAttribute(fd2d_step_kernel<BZ, NW, STEP_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FWI_CUDA(cudaFuncSetAttribute(fd2d_step_kernel<BZ, NW, STEP_ADJ2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_attr_set = true;
+    }
+#else
     const size_t smem = (size_t)(kBX + 2 * kHalo) * (BZ + 2 * kHalo) * sizeof(float);
+#define STEP_TMAPS p->tmap[cur]
+#endif
     // Programmatic dependent launch: consecutive steps are chained with a programmatic edge (also inside captured graphs),
     // the kernel orders itself behind its predecessor with griddepcontrol.wait.
     cudaLaunchConfig_t cfg{};
@@ -599,10 +652,11 @@ static int launch_step_cfg(fwi_fd2d* p, int mode, int cur, float* oldnew, const 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = (p->pdl && p->pdl_chain) ? 1 : 0;
     p->pdl_chain = true;
-    if (mode == STEP_FWD) FWI_CUDA(cudaLaunchKernelEx(&cfg, fd2d_step_kernel<BZ, NW, STEP_FWD>, p->tmap[cur], a));
-    else if (mode == STEP_FWD_SAVE) FWI_CUDA(cudaLaunchKernelEx(&cfg, fd2d_step_kernel<BZ, NW, STEP_FWD_SAVE>, p->tmap[cur], a));
-    else if (mode == STEP_ADJ2) FWI_CUDA(cudaLaunchKernelEx(&cfg, fd2d_step_kernel<BZ, NW, STEP_ADJ2>, p->tmap[cur], a));
-    else FWI_CUDA(cudaLaunchKernelEx(&cfg, fd2d_step_kernel<BZ, NW, STEP_ADJ>, p->tmap[cur], a));
+    if (mode == STEP_FWD) FWI_CUDA(cudaLaunchKernelEx(&cfg, fd2d_step_kernel<BZ, NW, STEP_FWD>, STEP_TMAPS, a));
+    else if (mode == STEP_FWD_SAVE) FWI_CUDA(cudaLaunchKernelEx(&cfg, fd2d_step_kernel<BZ, NW, STEP_FWD_SAVE>, STEP_TMAPS, a));
+    else if (mode == STEP_ADJ2) FWI_CUDA(cudaLaunchKernelEx(&cfg, fd2d_step_kernel<BZ, NW, STEP_ADJ2>, STEP_TMAPS, a));
+    else FWI_CUDA(cudaLaunchKernelEx(&cfg, fd2d_step_kernel<BZ, NW, STEP_ADJ>, STEP_TMAPS, a));
+#undef STEP_TMAPS
     return FWI_OK;
 }
 
