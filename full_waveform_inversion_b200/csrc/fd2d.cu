@@ -56,13 +56,33 @@ struct Step2DArgs {
 // implicit trigger only the launch latency and the prologue overlap and the CTAs stay staggered.
 #define FWI_PDL_TRIGGER 0
 #endif
+#ifndef FWI_ROW_PIPE
+// rows of u_{n-1} / m requested AHEAD of the row being computed (rolling, on top of FWI_PREFETCH_ROW0 = depth).  Without it the
+// loads of row r + 1 sit behind the store of row r in program order (the compiler cannot prove the rows disjoint), so a warp
+// pays one L2 round trip per row.  0 = off
+#define FWI_ROW_PIPE 0
+#endif
+#ifndef FWI_L1_PREFETCH
+// rows of u_{n-1} / m (beyond the FWI_PREFETCH_ROW0 rows held in registers) requested into L1 with prefetch.global.L1 before the
+// dependency wait: no registers, and the row loop's loads then hit L1 instead of paying an L2 round trip each.  0 = off
+#define FWI_L1_PREFETCH 0
+#endif
+#ifndef FWI_STEP_MINB
+#define FWI_STEP_MINB 0           // > 0: __launch_bounds__ min CTAs per SM of the step kernel (caps the registers)
+#endif
+#if FWI_STEP_MINB > 0
+#define FWI_STEP_BOUNDS(nthreads) __launch_bounds__(nthreads, FWI_STEP_MINB)
+#else
+// no minimum given: ptxas settles at 80 registers (3 CTAs of 256 threads per SM); with an explicit minimum of 1 it takes 110
+#define FWI_STEP_BOUNDS(nthreads) __launch_bounds__(nthreads)
+#endif
 #ifndef FWI_M_SMEM
 // 1: the tile's rows of m (static inside a sweep) are staged in shared memory by a TMA load issued BEFORE the dependency wait
 #define FWI_M_SMEM 0
 #endif
 constexpr size_t step_tile_floats(int bz) { return ((size_t)(128 + 2 * kHalo) * (bz + 2 * kHalo) + 31) / 32 * 32; }    // [SZ][SX] rounded up to a 128-byte multiple
 template <int BZ, int NW, int MODE>
-__global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constant__ CUtensorMap tm_cur,
+__global__ void FWI_STEP_BOUNDS(NW * 32) fd2d_step_kernel(const __grid_constant__ CUtensorMap tm_cur,
 #if FWI_M_SMEM
                                                              const __grid_constant__ CUtensorMap tm_m,
 #endif
@@ -116,6 +136,14 @@ __global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constan
         }
     }
 #endif
+#if FWI_L1_PREFETCH
+#pragma unroll
+    for (int r = FWI_PREFETCH_ROW0; r < RPW && r < FWI_PREFETCH_ROW0 + FWI_L1_PREFETCH; ++r)
+        if (col_ok && zw + r < a.nz) {
+            prefetch_l1(a.oldnew + (size_t)(zw + r) * a.px + x);
+            prefetch_l1(a.m + (size_t)(zw + r) * a.px + x);
+        }
+#endif
     griddep_wait();                 // step n complete and visible (no-op for a plain launch)
 #if FWI_PDL_TRIGGER == 1
     griddep_launch_dependents();    // every CTA of this grid is resident once all have passed here: step n+2's may queue up
@@ -155,7 +183,18 @@ __global__ void __launch_bounds__(NW * 32) fd2d_step_kernel(const __grid_constan
 #pragma unroll
                 for (int k = 0; k < 9; ++k) { zc[k][0] = win[k].x; zc[k][1] = win[k].y; zc[k][2] = win[k].z; zc[k][3] = win[k].w; }
                 const size_t off = (size_t)z * a.px + x;
-#if FWI_M_SMEM
+#if FWI_ROW_PIPE
+                // queue: o4p[k] / m4p[k] hold row r + k; row r + FWI_PREFETCH_ROW0 is requested now, before row r's store
+                const float4 o4 = o4p[0], m4 = m4p[0];
+                float4 o4n = make_float4(0.f, 0.f, 0.f, 0.f), m4n = o4n;
+                if (r + FWI_PREFETCH_ROW0 < RPW && z + FWI_PREFETCH_ROW0 < a.nz) {
+                    o4n = ld4(a.oldnew + off + (size_t)FWI_PREFETCH_ROW0 * a.px);
+                    m4n = ld4(a.m + off + (size_t)FWI_PREFETCH_ROW0 * a.px);
+                }
+#pragma unroll
+                for (int k = 0; k + 1 < FWI_PREFETCH_ROW0; ++k) { o4p[k] = o4p[k + 1]; m4p[k] = m4p[k + 1]; }
+                o4p[FWI_PREFETCH_ROW0 - 1] = o4n; m4p[FWI_PREFETCH_ROW0 - 1] = m4n;
+#elif FWI_M_SMEM
                 const float4 o4 = (r < FWI_PREFETCH_ROW0) ? o4p[r < FWI_PREFETCH_ROW0 ? r : 0] : ld4(a.oldnew + off);
                 const float4 m4 = ld4(sM + (warp * RPW + r) * BX + 4 * lane);
 #elif FWI_PREFETCH_ROW0

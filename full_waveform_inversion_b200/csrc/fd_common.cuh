@@ -59,6 +59,7 @@ __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("grid
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // streaming (evict-first) accesses for the wavefield snapshots: written once / read once, must not evict the
 // L2-resident wavefields
 __device__ __forceinline__ void st4_stream(float* p, const float4& v) { __stcs(reinterpret_cast<float4*>(p), v); }
