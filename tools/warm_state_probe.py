@@ -25,5 +25,8 @@ for i in range(nshots):
     ts.append(e0.elapsed_time(e1)); at.append(time.perf_counter() - t0)
     if idle and i == nshots // 2:
         time.sleep(idle)
+    if os.environ.get("FWI_PROBE_TRIGGER_GB") and i == 5:          # provoke the slow state, then keep the load on
+        burst = torch.empty(int(float(os.environ["FWI_PROBE_TRIGGER_GB"]) * 1024**3), dtype=torch.uint8, device=dev)
+        burst.fill_(1); torch.cuda.synchronize(); del burst
 print("ms per shot  :", " ".join("%.1f" % t for t in ts))
 print("s since start:", " ".join("%.1f" % t for t in at))
