@@ -150,3 +150,43 @@ def test_no_receivers_no_sources_and_tiny_grids(mods):
     with pytest.raises(ValueError):
         prop.gradient(np.zeros((30, 0), np.float32), np.zeros((30, 2), np.float32))   # a gradient needs a source
     prop.close()
+
+
+# ------------------------------------------------------------------------------------------------ Track B: pad columns
+@pytest.mark.parametrize("case", ["tile", "tile_checkpointed", "tb2", "tb2_checkpointed", "3d", "3d_checkpointed"])
+def test_pad_columns_of_every_wavefield_buffer_stay_zero(mods, case):
+    """Rows are padded to 32 floats; the step kernels compute the pad columns [nx, px) too (m = 0 there) and the slab
+    protocol relies on them staying zero in all 8 wavefield buffers - also in the buffers that are only cleared when
+    the plan is created (2/3/6/7: second pair of the two-steps-per-pass kernel, checkpoint restores)."""
+    import torch
+    ac, _ = mods
+    three_d = case.startswith("3d")
+    shape = (36, 40, 150) if three_d else (90, 300)                       # nx not a multiple of 32: 10 / 20 pad columns
+    nt = 60
+    v = fo.layered_model(shape, 1500.0, 3500.0, 3).astype(np.float32)
+    dt = fo.stable_dt(3500.0, 10.0, 3 if three_d else 2)
+    wav = fo.ricker(nt, dt, 15.0).astype(np.float32)
+    kw = {}
+    if case.startswith("tb2"):
+        kw["tb2"] = 24
+    elif not three_d:
+        kw["tile"] = (32, 4)
+    prop = (ac.Propagator3D if three_d else ac.Propagator2D)(shape, 10.0, dt, nabs=10, **kw)
+    prop.set_model(torch.from_numpy(v).cuda())
+    if three_d:
+        prop.set_geometry([(5, 20, shape[2] - 2)], [(4, 10, shape[2] - 1), (6, 30, 3)])      # points in the last real columns
+    else:
+        prop.set_geometry([(5, shape[1] - 2)], [(4, shape[1] - 1), (6, 3)])
+    if case.endswith("checkpointed"):
+        plane = int(np.prod(shape[:-1])) * ((shape[-1] + 31) // 32 * 32) * 4
+        prop.set_memory_limit(30 * plane)                                  # half the nt = 60 snapshots fit: checkpointed segments
+    obs = prop.forward(wav).clone() * 0.5
+    prop.gradient(wav, obs)
+    prop.gradient(wav, obs)
+    torch.cuda.synchronize()
+    nx = shape[-1]
+    for idx in range(8):
+        pad = prop.field_view(idx)[..., nx:]
+        assert pad.numel() > 0
+        assert float(pad.abs().max()) == 0.0, "buffer %d has non-zero pad columns" % idx
+    prop.close()
