@@ -530,10 +530,23 @@ def run_b200(args):
     grad = torch.zeros((nz, nx), dtype=torch.float32, device=dev)
     grad_host = torch.empty((nz, nx), dtype=torch.float32).pin_memory()
 
+    # Rank barrier of the timed regions: the GPU is drained first, then the ranks meet on the CPU (gloo).  An NCCL barrier is a
+    # collective KERNEL, and NCCL kernels issued while the GPUs are busy are among the triggers of the slow state.
+    cpu_group = None
+    if world > 1 and os.environ.get("FWI_BENCH_NCCL_BARRIER") != "1":
+        try:
+            cpu_group = dist.new_group(backend="gloo")
+        except Exception as exc:                                   # no usable interface for gloo: fall back to NCCL
+            print("bench: gloo barrier group unavailable (%r), using NCCL barriers" % (exc,), file=sys.stderr)
+
     def barrier():
-        if world > 1:
-            dist.barrier()
         torch.cuda.synchronize(dev)
+        if world > 1:
+            if cpu_group is not None:
+                dist.barrier(group=cpu_group)
+            else:
+                dist.barrier()
+                torch.cuda.synchronize(dev)
 
     def one_step(i, host_io):
         src, rec = my_shots[i]
@@ -550,6 +563,8 @@ def run_b200(args):
     # ---- device-resident timing (value) ------------------------------------------------------------------
     for i in range(args.warmup):
         one_step(i, False)
+    if world > 1:
+        dist.all_reduce(grad)           # warm-up of the collective too: NCCL sets its connections up on first use (~0.4 s)
     barrier()
     # settle: the first second after the 60 GB snapshot buffer is created runs ~20 % slow (first-touch of fresh
     # HBM pages); keep stepping (untimed) until two consecutive steps agree within 2 %, at most 12 extra steps.
